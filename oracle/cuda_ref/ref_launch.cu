@@ -1,0 +1,35 @@
+/* TEST INFRASTRUCTURE — extern "C" launch shim appended (by oracle/Makefile) to the reference's
+ * own kernel definitions.  Launch shapes follow the reference wrappers
+ * (masked_ordered_ball_query_gpu.cu:106, masked_grid_subsampling_gpu.cu:159,
+ * masked_nearest_query_gpu.cu:71, group_points_gpu.cu:40,76).  All pointers are device pointers;
+ * scratch must be zero-filled by the caller like the reference's torch::zeros. */
+extern "C" {
+int ref_cuda_ball_query(int b, int n, int m, float radius, int nsample, const float* q, const float* s,
+                        const int* qm, const int* sm, int* idx, int* idx_mask, float* dists, int* tempidxs,
+                        cudaStream_t st) {
+  masked_ordered_query_ball_point_kernel<<<b, ref_n_threads(m), 0, st>>>(b, n, m, radius, nsample, q, s, qm, sm,
+                                                                         idx, idx_mask, dists, tempidxs);
+  return (int)cudaGetLastError();
+}
+int ref_cuda_grid_subsampling(int b, int n, int m, float dl, const float* xyz, const int* mask, float* sub,
+                              int* submask, int* mapidxs, int* tempidxs, float* temp_subxyz, cudaStream_t st) {
+  masked_grid_subsampling_kernel<<<b, 1, 0, st>>>(n, m, dl, xyz, mask, sub, submask, mapidxs, tempidxs, temp_subxyz);
+  return (int)cudaGetLastError();
+}
+int ref_cuda_nearest_query(int b, int n, int m, const float* q, const float* s, const int* qm, const int* sm,
+                           int* idx, int* idx_mask, cudaStream_t st) {
+  masked_nearest_query_kernel<<<b, ref_n_threads(m), 0, st>>>(b, n, m, q, s, qm, sm, idx, idx_mask);
+  return (int)cudaGetLastError();
+}
+int ref_cuda_group_points(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx,
+                          float* out, cudaStream_t st) {
+  group_points_kernel<<<b, ref_block_config(npoints, c), 0, st>>>(b, c, n, npoints, nsample, points, idx, out);
+  return (int)cudaGetLastError();
+}
+int ref_cuda_group_points_grad(int b, int c, int n, int npoints, int nsample, const float* grad_out,
+                               const int* idx, float* grad_points, cudaStream_t st) {
+  group_points_grad_kernel<<<b, ref_block_config(npoints, c), 0, st>>>(b, c, n, npoints, nsample, grad_out, idx,
+                                                                       grad_points);
+  return (int)cudaGetLastError();
+}
+}
