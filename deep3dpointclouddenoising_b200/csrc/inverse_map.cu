@@ -1,0 +1,196 @@
+// Inverse neighbour map: CSR by support point of an idx tensor (B, M, nsample).
+//
+// Every backward kernel of the path (gather grad, PosPool, PseudoGrid, max-pool, nearest upsample)
+// is a sum over "all (query, slot) pairs that gathered support i".  The reference scatters with
+// float atomicAdd (ref: u_net_arch/pt_custom_ops/_ext_src/src/group_points_gpu.cu:58-68) and is
+// therefore non-deterministic; here the pairs of each support are listed once, in ascending
+// (query, slot) order, and every backward kernel reduces its segment sequentially: no float atomics,
+// bit-reproducible gradients.
+//
+// Build: integer histogram -> per-cloud exclusive scan -> cursor fill (integer atomics; the order
+// inside a segment is arbitrary at this point) -> per-segment sort (a warp for short segments, a
+// block-wide bitonic network for long ones).  Entries are (query << 8) | slot.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kShortLen = 64;   // segments up to this length are sorted by one warp
+constexpr int kSortSmem = 8192;  // longer ones by a block, in shared memory up to this many entries
+constexpr int kSortThreads = 256;
+
+__global__ void count_kernel(const int* __restrict__ idx, long long total, int P, int N, int* __restrict__ counts) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int b = (int)(e / P);
+  atomicAdd(&counts[(size_t)b * N + d3d_clamp_index(idx[e], N)], 1);
+}
+
+// one block per cloud: rowptr[b*N + i] = b*P + exclusive prefix of counts[b, :]; cursor <- rowptr
+__global__ void __launch_bounds__(1024)
+scan_kernel(int* __restrict__ counts_then_cursor, int N, int P, int B, int* __restrict__ rowptr) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* cnt = counts_then_cursor + (size_t)b * N;
+  int* rp = rowptr + (size_t)b * N;
+  if (tid == 0) carry = b * P;
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int i = base + tid;
+    const int c = i < N ? cnt[i] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_tot[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(D3D_FULL_MASK, wi, o);
+        if (lane >= o) wi += up;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + warp_tot[warp] + incl - c;
+    if (i < N) { rp[i] = excl; cnt[i] = excl; }
+    __syncthreads();
+    if (tid == 1023) carry = excl + c;
+    __syncthreads();
+  }
+  if (b == B - 1 && tid == 0) rowptr[(size_t)B * N] = B * P;
+}
+
+__global__ void fill_kernel(const int* __restrict__ idx, long long total, int P, int N, int nsample,
+                            int* __restrict__ cursor, int* __restrict__ unsorted) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int b = (int)(e / P);
+  const int p = (int)(e - (long long)b * P);
+  const int j = p / nsample, k = p - j * nsample;
+  const int pos = atomicAdd(&cursor[(size_t)b * N + d3d_clamp_index(idx[e], N)], 1);
+  unsorted[pos] = (j << 8) | k;
+}
+
+// warp per support: segments <= kShortLen are rank-sorted here; longer ones are queued for the block sorter
+__global__ void sort_short_kernel(const int* __restrict__ rowptr, int rows, const int* __restrict__ unsorted,
+                                  int* __restrict__ entries, int* __restrict__ long_rows, int* __restrict__ long_count) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (row >= rows) return;
+  const int beg = rowptr[row], len = rowptr[row + 1] - beg;
+  if (len > kShortLen) {
+    if (lane == 0) long_rows[atomicAdd(long_count, 1)] = row;
+    return;
+  }
+  // entries are unique -> rank = number of smaller entries
+  int own0 = lane < len ? unsorted[beg + lane] : 0x7fffffff;
+  int own1 = lane + 32 < len ? unsorted[beg + lane + 32] : 0x7fffffff;
+  int r0 = 0, r1 = 0;
+  for (int t = 0; t < len; ++t) {
+    const int other = t < 32 ? __shfl_sync(D3D_FULL_MASK, own0, t) : __shfl_sync(D3D_FULL_MASK, own1, t - 32);
+    r0 += other < own0 ? 1 : 0;
+    r1 += other < own1 ? 1 : 0;
+  }
+  if (lane < len) entries[beg + r0] = own0;
+  if (lane + 32 < len) entries[beg + r1] = own1;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_long_kernel(const int* __restrict__ rowptr, const int* __restrict__ long_rows, const int* __restrict__ long_count,
+                 int* unsorted, int* __restrict__ entries) {
+  __shared__ int buf[kSortSmem];
+  const int n_long = *long_count;
+  for (int it = blockIdx.x; it < n_long; it += gridDim.x) {
+    const int row = long_rows[it];
+    const int beg = rowptr[row], len = rowptr[row + 1] - beg;
+    int P2 = 1;
+    while (P2 < len) P2 <<= 1;
+    if (P2 <= kSortSmem) {
+      for (int i = threadIdx.x; i < P2; i += kSortThreads) buf[i] = i < len ? unsorted[beg + i] : 0x7fffffff;
+      __syncthreads();
+      for (int k = 2; k <= P2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = threadIdx.x; t < (P2 >> 1); t += kSortThreads) {
+            const int a = ((t & ~(j - 1)) << 1) | (t & (j - 1)), c = a | j;
+            const int va = buf[a], vc = buf[c];
+            if ((va > vc) == ((a & k) == 0)) { buf[a] = vc; buf[c] = va; }
+          }
+          __syncthreads();
+        }
+      for (int i = threadIdx.x; i < len; i += kSortThreads) entries[beg + i] = buf[i];
+      __syncthreads();
+    } else {
+      // very long segment: odd-even merge is overkill; rank counting straight from global memory
+      // (L1/L2 resident), out of place.  O(len^2 / 256) per thread, only for > 8192 entries.
+      for (int i = threadIdx.x; i < len; i += kSortThreads) {
+        const int own = unsorted[beg + i];
+        int r = 0;
+        for (int t = 0; t < len; ++t) r += unsorted[beg + t] < own ? 1 : 0;
+        entries[beg + r] = own;
+      }
+    }
+  }
+}
+
+struct InvWs {
+  int* cursor;
+  int* unsorted;
+  int* long_rows;
+  int* long_count;
+};
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+InvWs carve(void* ws, int B, int N, int M, int nsample) {
+  unsigned char* p = (unsigned char*)ws;
+  InvWs w;
+  w.cursor = (int*)p; p += align256((size_t)B * N * sizeof(int));
+  w.unsorted = (int*)p; p += align256((size_t)B * M * nsample * sizeof(int));
+  w.long_rows = (int*)p; p += align256((size_t)B * N * sizeof(int));
+  w.long_count = (int*)p;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t d3d_inverse_map_workspace_bytes(int B, int N, int M, int nsample) {
+  if (B <= 0 || N <= 0 || M <= 0 || nsample <= 0) return 0;
+  return 2 * align256((size_t)B * N * sizeof(int)) + align256((size_t)B * M * nsample * sizeof(int)) + 256;
+}
+
+int d3d_build_inverse_map(const int* idx, int B, int N, int M, int nsample, int* rowptr, int* entries, void* ws,
+                          size_t ws_bytes, void* stream) {
+  D3D_REQUIRE(idx && rowptr && entries);
+  D3D_REQUIRE(B >= 0 && N > 0 && M >= 0 && nsample > 0 && nsample <= 256);
+  const long long total = (long long)B * M * nsample;
+  if (total >= (1ll << 31) || (long long)M >= (1ll << 23)) return D3D_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return 0;
+  if (!ws || ws_bytes < d3d_inverse_map_workspace_bytes(B, N, M, nsample)) return D3D_ERR_WORKSPACE;
+  InvWs w = carve(ws, B, N, M, nsample);
+  const int P = M * nsample;
+  cudaError_t e = cudaMemsetAsync(w.cursor, 0, (size_t)B * N * sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(w.long_count, 0, sizeof(int), st);
+  if (e != cudaSuccess) return (int)e;
+  if (total > 0) count_kernel<<<d3d_ceil_div(total, 256), 256, 0, st>>>(idx, total, P, N, w.cursor);
+  scan_kernel<<<B, 1024, 0, st>>>(w.cursor, N, P, B, rowptr);
+  if (total > 0) {
+    fill_kernel<<<d3d_ceil_div(total, 256), 256, 0, st>>>(idx, total, P, N, nsample, w.cursor, w.unsorted);
+    const int rows = B * N;
+    sort_short_kernel<<<d3d_ceil_div((long long)rows * 32, 256), 256, 0, st>>>(rowptr, rows, w.unsorted, entries,
+                                                                             w.long_rows, w.long_count);
+    sort_long_kernel<<<148 * 4, kSortThreads, 0, st>>>(rowptr, w.long_rows, w.long_count, w.unsorted, entries);
+  }
+  return d3d_launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+"""Autograd Functions over the fused kernels.  Inputs and outputs use the reference's channel-major
+(B, C, N) layout; the layout change to channel-last happens inside (d3d_cm_to_cl / d3d_cl_to_cm), so the
+callers — the modules mirroring pt_utils.py and local_aggregation_operators.py — keep the reference API.
+
+Differentiable w.r.t. features (and PseudoGrid's kernel_weights) only, like the reference
+(pt_utils.py:43-62: GroupingOperation returns a gradient for features, None for idx; coordinates never
+receive gradients because the grouped xyz come from non-differentiable index ops on leaf tensors).
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+
+
+class PosPoolFunction(Function):
+    """local_aggregation_operators.py:140-147,165-183 with position_embedding='xyz', reduction sum/avg."""
+
+    @staticmethod
+    def forward(ctx, features, query_xyz, support_xyz, query_mask, nbr, radius, reduction):
+        feat_cl = ops.cm_to_cl(features.contiguous())
+        out_cl = ops.pospool_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, radius, reduction)
+        ctx.nbr, ctx.radius, ctx.reduction = nbr, radius, reduction
+        ctx.save_for_backward(query_xyz, support_xyz, query_mask)
+        return ops.cl_to_cm(out_cl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        query_xyz, support_xyz, query_mask = ctx.saved_tensors
+        nbr = ctx.nbr
+        rowptr, entries = nbr.csr()
+        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,
+                                nbr.nsample, ctx.radius, ctx.reduction)
+        return ops.cl_to_cm(gf_cl), None, None, None, None, None, None
+
+
+class PseudoGridFunction(Function):
+    """local_aggregation_operators.py:467-503 (depthwise KPConv aggregation, convolution_mode='sum')."""
+
+    @staticmethod
+    def forward(ctx, features, kernel_weights, query_xyz, support_xyz, query_mask, nbr, k_points, extent, influence,
+                precision):
+        feat_cl = ops.cm_to_cl(features.contiguous())
+        w = kernel_weights.contiguous()
+        out_cl = ops.pseudogrid_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, k_points, w,
+                                    extent, influence, precision)
+        ctx.nbr, ctx.extent, ctx.influence = nbr, extent, influence
+        ctx.save_for_backward(feat_cl, w, query_xyz, support_xyz, query_mask, k_points)
+        return ops.cl_to_cm(out_cl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat_cl, w, query_xyz, support_xyz, query_mask, k_points = ctx.saved_tensors
+        nbr = ctx.nbr
+        rowptr, entries = nbr.csr()
+        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        gf_cl, gw = ops.pseudogrid_bwd(g_cl, feat_cl, query_xyz, support_xyz, nbr.idx, rowptr, entries, nbr.nvalid,
+                                       query_mask, k_points, w, ctx.extent, ctx.influence,
+                                       need_feat=ctx.needs_input_grad[0], need_weights=ctx.needs_input_grad[1])
+        gf = ops.cl_to_cm(gf_cl) if gf_cl is not None else None
+        return gf, gw, None, None, None, None, None, None, None, None
+
+
+class GatherMaxFunction(Function):
+    """grouping_operation + F.max_pool2d over the nsample axis (pt_utils.py:136,202-205)."""
+
+    @staticmethod
+    def forward(ctx, features, nbr):
+        feat_cl = ops.cm_to_cl(features.contiguous())
+        out_cl, arg = ops.gather_max_fwd(feat_cl, nbr.idx)
+        ctx.nbr = nbr
+        ctx.save_for_backward(arg)
+        return ops.cl_to_cm(out_cl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (arg,) = ctx.saved_tensors
+        rowptr, entries = ctx.nbr.csr()
+        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        gf_cl = ops.gather_max_bwd(g_cl, arg, rowptr, entries, ctx.nbr.n_support)
+        return ops.cl_to_cm(gf_cl), None
+
+
+class NearestGatherFunction(Function):
+    """grouping_operation with the nearest-neighbour index, then [..., 0] (pt_utils.py:168,226)."""
+
+    @staticmethod
+    def forward(ctx, features, nbr):
+        feat_cl = ops.cm_to_cl(features.contiguous())
+        out_cl = ops.nearest_gather_fwd(feat_cl, nbr.idx.view(nbr.idx.shape[0], nbr.idx.shape[1]))
+        ctx.nbr = nbr
+        return ops.cl_to_cm(out_cl)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        rowptr, entries = ctx.nbr.csr()
+        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        gf_cl = ops.nearest_gather_bwd(g_cl, rowptr, entries, ctx.nbr.n_support)
+        return ops.cl_to_cm(gf_cl), None

@@ -1,0 +1,94 @@
+"""Point ResNet backbone (mirror of u_net_arch/models/backbones/resnet.py: Bottleneck :22-68, ResNet :71-188).
+
+Same module tree and parameter names (conv1, la1, btnk1, layer{1..4}.strided_bottleneck,
+layer{1..4}.bottlneck{i} — the reference's spelling — with conv1 / local_aggregation / conv2 / shortcut /
+maxpool inside each bottleneck) and the same end_points dictionary, so state dicts are interchangeable.
+The 1x1 convolutions and BatchNorm stay in PyTorch (outside the hot path); everything
+between them — subsampling, neighbour lists, max-pool, local aggregation — runs on the fused kernels.
+One forward builds each distinct neighbour list once (neighbors.cache) instead of 14 ball queries.
+"""
+import torch.nn as nn
+
+from ... import neighbors as _neighbors
+from ...pt_custom_ops.pt_utils import MaskedMaxPool
+from ..local_aggregation_operators import LocalAggregation
+
+
+def _conv_bn(cin, cout, momentum, relu):
+    layers = [nn.Conv1d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm1d(cout, momentum=momentum)]
+    if relu:
+        layers.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*layers)
+
+
+class MultiInputSequential(nn.Sequential):
+    def forward(self, *inputs):
+        for module in self._modules.values():
+            inputs = module(*inputs)
+        return inputs
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, in_channels, out_channels, bottleneck_ratio, radius, nsample, config, downsample=False,
+                 sampleDl=None, npoint=None):
+        super().__init__()
+        self.in_channels, self.out_channels, self.downsample = in_channels, out_channels, downsample
+        mid = out_channels // bottleneck_ratio
+        if downsample:
+            self.maxpool = MaskedMaxPool(npoint, radius, nsample, sampleDl)
+        self.conv1 = _conv_bn(in_channels, mid, config.bn_momentum, relu=True)
+        self.local_aggregation = LocalAggregation(mid, mid, radius, nsample, config)
+        self.conv2 = _conv_bn(mid, out_channels, config.bn_momentum, relu=False)
+        self.relu = nn.ReLU(inplace=True)
+        if in_channels != out_channels:
+            self.shortcut = _conv_bn(in_channels, out_channels, config.bn_momentum, relu=False)
+
+    def forward(self, xyz, mask, features):
+        if self.downsample:
+            query_xyz, query_mask, identity = self.maxpool(xyz, mask, features)
+        else:
+            query_xyz, query_mask, identity = xyz, mask, features
+        out = self.conv1(features)
+        out = self.local_aggregation(query_xyz, xyz, query_mask, mask, out)
+        out = self.conv2(out)
+        if self.in_channels != self.out_channels:
+            identity = self.shortcut(identity)
+        return query_xyz, query_mask, self.relu(out + identity)
+
+
+class ResNet(nn.Module):
+    def __init__(self, config, input_features_dim, radius, sampleDl, nsamples, npoints, width=144, depth=2,
+                 bottleneck_ratio=2):
+        super().__init__()
+        self.input_features_dim = input_features_dim
+        half = width // 2
+        self.conv1 = _conv_bn(input_features_dim, half, config.bn_momentum, relu=True)
+        self.la1 = LocalAggregation(half, half, radius, nsamples[0], config)
+        self.btnk1 = Bottleneck(half, width, bottleneck_ratio, radius, nsamples[0], config)
+        # four strided stages: each halves the resolution (grid cell x2) and doubles radius and width
+        for stage in range(4):
+            sampleDl *= 2
+            layer = MultiInputSequential()
+            layer.add_module("strided_bottleneck",
+                             Bottleneck(width, 2 * width, bottleneck_ratio, radius, nsamples[stage], config,
+                                        downsample=True, sampleDl=sampleDl, npoint=npoints[stage]))
+            radius *= 2
+            width *= 2
+            for i in range(depth - 1):
+                layer.add_module(f"bottlneck{i}",
+                                 Bottleneck(width, width, bottleneck_ratio, radius, nsamples[stage + 1], config))
+            setattr(self, f"layer{stage + 1}", layer)
+
+    def forward(self, xyz, mask, features, end_points=None):
+        _neighbors.cache.clear()  # neighbour lists are valid for one forward only
+        if not end_points:
+            end_points = {}
+        features = self.conv1(features)
+        features = self.la1(xyz, xyz, mask, mask, features)
+        xyz, mask, features = self.btnk1(xyz, mask, features)
+        end_points['res1_xyz'], end_points['res1_mask'], end_points['res1_features'] = xyz, mask, features
+        for stage in range(4):
+            xyz, mask, features = getattr(self, f"layer{stage + 1}")(xyz, mask, features)
+            tag = f"res{stage + 2}"
+            end_points[tag + '_xyz'], end_points[tag + '_mask'], end_points[tag + '_features'] = xyz, mask, features
+        return end_points

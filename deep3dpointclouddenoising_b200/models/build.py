@@ -1,0 +1,50 @@
+"""Model factory for offset regression (mirror of u_net_arch/models/build.py:42-67, 236-262)."""
+import torch.nn as nn
+
+from .backbones import ResNet
+from .heads import MultiDimHeadResNet
+from .losses import MaskedL1Loss
+
+OFFSET_REG_DIM = 3
+
+
+class OffsetRegressionModel(nn.Module):
+    def __init__(self, config, backbone, head, num_classes, input_features_dim, radius, sampleDl, nsamples, npoints,
+                 width=144, depth=2, bottleneck_ratio=2):
+        super().__init__()
+        if input_features_dim == 0:
+            input_features_dim = 3  # the dataset feeds xyz as features (offset_dataset.py:726)
+        if backbone != 'resnet':
+            raise NotImplementedError(f"Backbone {backbone} not implemented in Offset Regression Model")
+        self.backbone = ResNet(config, input_features_dim, radius, sampleDl, nsamples, npoints, width=width,
+                               depth=depth, bottleneck_ratio=bottleneck_ratio)
+        if head != 'offset_reg_head':
+            raise NotImplementedError(f"Head {backbone} not implemented in Offset Regression Model")
+        # attribute name kept from the reference (state-dict prefix 'segmentation_head.')
+        self.segmentation_head = MultiDimHeadResNet(OFFSET_REG_DIM, width, radius, nsamples, isGAN=config.GAN)
+
+    def forward(self, xyz, mask, features):
+        return self.segmentation_head(self.backbone(xyz, mask, features))
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, (nn.Conv1d, nn.Conv2d)):
+                nn.init.kaiming_normal_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+
+def build_offset_regression(config):
+    model = OffsetRegressionModel(config, config.backbone, config.head, config.num_classes, config.input_features_dim,
+                                  config.radius, config.sampleDl, config.nsamples, config.npoints, config.width,
+                                  config.depth, config.bottleneck_ratio)
+    if config.loss == 'L1':
+        criterion = MaskedL1Loss()
+    elif config.loss is None:
+        raise ValueError("Please specify a loss in the config file")
+    elif config.loss in ('chamfer_L1', 'chamfer', 'chamfer_sparse', 'l1_chamfer_sparse',
+                         'l1_chamfer_adaptive_to_chamfer', 'l1_chamfer_adaptive_to_l1'):
+        raise NotImplementedError(f"The loss {config.loss} needs pytorch3d's knn (outside the hot path, SURVEY.md row f3)")
+    else:
+        raise ValueError(f"The loss {config.loss} is not implemented")
+    return model, criterion

@@ -1,0 +1,293 @@
+"""Tensor-level host side of the C ABI: argument checks, output/workspace allocation, stream hand-off.
+
+torch is used here for device memory and streams only; every byte of compute is in libd3d_b200.so.
+Error behaviour mirrors the reference extension (u_net_arch/pt_custom_ops/_ext_src/include/utils.h:10-30):
+wrong dtype / non-contiguous / CPU tensors raise RuntimeError with the reference's wording.
+"""
+import torch
+
+from . import _lib
+
+REDUCTIONS = {"sum": 0, "avg": 1, "mean": 1}
+INFLUENCES = {"constant": 0, "linear": 1, "gaussian": 2}
+
+launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as gpu_launches evidence)
+
+
+def _count():
+    global launch_count
+    launch_count += 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError("CPU not supported")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {'a float' if dtype == torch.float32 else 'an int'} tensor")
+    return t
+
+
+def _f32(t, name):
+    return _chk(t, torch.float32, name)
+
+
+def _i32(t, name):
+    return _chk(t, torch.int32, name)
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# neighbourhood construction
+# ------------------------------------------------------------------------------------------------
+def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_nvalid=False):
+    """(idx, idx_mask[, nvalid]) — _ext.masked_ordered_ball_query (masked_ordered_ball_query.cpp:13-59)."""
+    L = _lib.load()
+    q, s = _f32(query_xyz, "query_xyz"), _f32(support_xyz, "support_xyz")
+    qm, sm = _i32(query_mask, "query_mask"), _i32(support_mask, "support_mask")
+    B, M, N = q.shape[0], q.shape[1], s.shape[1]
+    with torch.cuda.device(q.device):
+        idx = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
+        msk = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
+        nv = torch.empty((B, M), dtype=torch.int32, device=q.device) if want_nvalid else None
+        ws = _ws(L.d3d_ball_query_workspace_bytes(B), q.device)
+        _lib.check(L.d3d_ball_query(_p(q), _p(s), _p(qm), _p(sm), B, M, N, float(radius), int(nsample), _p(idx),
+                                    _p(msk), _p(nv), _p(ws), ws.numel(), _stream()), "d3d_ball_query")
+    _count()
+    return (idx, msk, nv) if want_nvalid else (idx, msk)
+
+
+def nearest_query(query_xyz, support_xyz, query_mask, support_mask):
+    """(idx, idx_mask) of shape (B, M, 1) — _ext.masked_nearest_query (masked_nearest_query.cpp:12-47)."""
+    L = _lib.load()
+    q, s = _f32(query_xyz, "query_xyz"), _f32(support_xyz, "support_xyz")
+    qm, sm = _i32(query_mask, "query_mask"), _i32(support_mask, "support_mask")
+    B, M, N = q.shape[0], q.shape[1], s.shape[1]
+    with torch.cuda.device(q.device):
+        idx = torch.empty((B, M, 1), dtype=torch.int32, device=q.device)
+        msk = torch.empty((B, M, 1), dtype=torch.int32, device=q.device)
+        ws = _ws(L.d3d_nearest_query_workspace_bytes(B), q.device)
+        _lib.check(L.d3d_nearest_query(_p(q), _p(s), _p(qm), _p(sm), B, M, N, _p(idx), _p(msk), _p(ws), ws.numel(),
+                                       _stream()), "d3d_nearest_query")
+    _count()
+    return idx, msk
+
+
+def grid_subsample(xyz, mask, npoint, sample_dl):
+    """(sub_xyz, sub_mask) — _ext.masked_grid_subsampling (masked_grid_subsampling.cpp:13-44)."""
+    L = _lib.load()
+    p, mk = _f32(xyz, "points"), _i32(mask, "mask")
+    B, N = p.shape[0], p.shape[1]
+    with torch.cuda.device(p.device):
+        sub = torch.empty((B, npoint, 3), dtype=torch.float32, device=p.device)
+        subm = torch.empty((B, npoint), dtype=torch.int32, device=p.device)
+        ws = _ws(L.d3d_grid_subsample_workspace_bytes(B, N), p.device)
+        _lib.check(L.d3d_grid_subsample(_p(p), _p(mk), B, N, int(npoint), float(sample_dl), _p(sub), _p(subm), _p(ws),
+                                        ws.numel(), _stream()), "d3d_grid_subsample")
+    _count()
+    return sub, subm
+
+
+# ------------------------------------------------------------------------------------------------
+# gather in the reference layout
+# ------------------------------------------------------------------------------------------------
+def group_points(points, idx):
+    """(B,C,N),(B,M,ns) -> (B,C,M,ns) — _ext.group_points (group_points.cpp:17-40)."""
+    L = _lib.load()
+    p, i = _f32(points, "points"), _i32(idx, "idx")
+    B, C, N = p.shape
+    M, ns = i.shape[1], i.shape[2]
+    with torch.cuda.device(p.device):
+        out = torch.empty((B, C, M, ns), dtype=torch.float32, device=p.device)
+        _lib.check(L.d3d_group_points(_p(p), _p(i), B, C, N, M, ns, _p(out), _stream()), "d3d_group_points")
+    _count()
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """(B,C,M,ns),(B,M,ns) -> (B,C,n) — _ext.group_points_grad (group_points.cpp:42-65), deterministic."""
+    L = _lib.load()
+    g, i = _f32(grad_out, "grad_out"), _i32(idx, "idx")
+    B, C, M, ns = g.shape
+    with torch.cuda.device(g.device):
+        out = torch.empty((B, C, int(n)), dtype=torch.float32, device=g.device)
+        ws = _ws(L.d3d_group_points_grad_workspace_bytes(B, int(n), M, ns), g.device)
+        _lib.check(L.d3d_group_points_grad(_p(g), _p(i), B, C, int(n), M, ns, _p(out), _p(ws), ws.numel(), _stream()),
+                   "d3d_group_points_grad")
+    _count()
+    return out
+
+
+def build_inverse_map(idx, n_support):
+    """CSR (rowptr (B*N+1,), entries (B*M*ns,)) of idx (B, M, ns) or (B, M)."""
+    L = _lib.load()
+    i = _i32(idx, "idx")
+    if i.dim() == 2:
+        i = i.unsqueeze(-1)
+    B, M, ns = i.shape
+    with torch.cuda.device(i.device):
+        rowptr = torch.empty((B * n_support + 1,), dtype=torch.int32, device=i.device)
+        entries = torch.empty((max(B * M * ns, 1),), dtype=torch.int32, device=i.device)
+        ws = _ws(L.d3d_inverse_map_workspace_bytes(B, n_support, M, ns), i.device)
+        _lib.check(L.d3d_build_inverse_map(_p(i), B, int(n_support), M, ns, _p(rowptr), _p(entries), _p(ws),
+                                           ws.numel(), _stream()), "d3d_build_inverse_map")
+    _count()
+    return rowptr, entries
+
+
+def cm_to_cl(x):
+    """(B, C, N) -> (B, N, C)."""
+    L = _lib.load()
+    x = _f32(x, "features")
+    B, C, N = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, N, C), dtype=torch.float32, device=x.device)
+        _lib.check(L.d3d_cm_to_cl(_p(x), B, C, N, _p(out), _stream()), "d3d_cm_to_cl")
+    _count()
+    return out
+
+
+def cl_to_cm(x):
+    """(B, N, C) -> (B, C, N)."""
+    L = _lib.load()
+    x = _f32(x, "features")
+    B, N, C = x.shape
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, C, N), dtype=torch.float32, device=x.device)
+        _lib.check(L.d3d_cl_to_cm(_p(x), B, C, N, _p(out), _stream()), "d3d_cl_to_cm")
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused aggregation (channel-last tensors)
+# ------------------------------------------------------------------------------------------------
+def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius, reduction):
+    L = _lib.load()
+    f = _f32(feat_cl, "features")
+    B, N, C = f.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    with torch.cuda.device(f.device):
+        out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
+        _lib.check(L.d3d_pospool_fwd(_p(f), _p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")),
+                                     _p(_i32(idx, "idx")), _p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")),
+                                     B, M, N, C, ns, float(radius), REDUCTIONS[reduction], _p(out), _stream()),
+                   "d3d_pospool_fwd")
+    _count()
+    return out
+
+
+def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, query_mask, n_support, nsample, radius,
+                reduction):
+    L = _lib.load()
+    g = _f32(grad_out_cl, "grad_out")
+    B, M, C = g.shape
+    with torch.cuda.device(g.device):
+        out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
+        _lib.check(L.d3d_pospool_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
+                                     _p(query_mask), B, M, int(n_support), C, int(nsample), float(radius),
+                                     REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_bwd")
+    _count()
+    return out
+
+
+def pseudogrid_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, kpoints, weights, extent, influence,
+                   precision=0):
+    L = _lib.load()
+    f = _f32(feat_cl, "features")
+    B, N, C = f.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    kp, w = _f32(kpoints, "K_points"), _f32(weights, "kernel_weights")
+    K = kp.shape[0]
+    with torch.cuda.device(f.device):
+        out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
+        _lib.check(L.d3d_pseudogrid_fwd(_p(f), _p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")),
+                                        _p(_i32(idx, "idx")), _p(_i32(nvalid, "nvalid")),
+                                        _p(_i32(query_mask, "query_mask")), _p(kp), _p(w), B, M, N, C, ns, K,
+                                        float(extent), INFLUENCES[influence], int(precision), _p(out), _stream()),
+                   "d3d_pseudogrid_fwd")
+    _count()
+    return out
+
+
+def pseudogrid_bwd(grad_out_cl, feat_cl, query_xyz, support_xyz, idx, rowptr, entries, nvalid, query_mask, kpoints,
+                   weights, extent, influence, need_feat=True, need_weights=True):
+    L = _lib.load()
+    g, f = _f32(grad_out_cl, "grad_out"), _f32(feat_cl, "features")
+    B, M, C = g.shape
+    N = f.shape[1]
+    ns = idx.shape[2]
+    K = kpoints.shape[0]
+    with torch.cuda.device(g.device):
+        gf = torch.empty((B, N, C), dtype=torch.float32, device=g.device) if need_feat else None
+        gw = torch.empty((K, C), dtype=torch.float32, device=g.device) if need_weights else None
+        ws = _ws(L.d3d_pseudogrid_bwd_workspace_bytes(B, M, C, K), g.device)
+        _lib.check(L.d3d_pseudogrid_bwd(_p(g), _p(f), _p(query_xyz), _p(support_xyz), _p(idx), _p(rowptr), _p(entries),
+                                        _p(nvalid), _p(query_mask), _p(kpoints), _p(weights), B, M, N, C, ns, K,
+                                        float(extent), INFLUENCES[influence], _p(gf), _p(gw), _p(ws), ws.numel(),
+                                        _stream()), "d3d_pseudogrid_bwd")
+    _count()
+    return gf, gw
+
+
+def gather_max_fwd(feat_cl, idx):
+    L = _lib.load()
+    f, i = _f32(feat_cl, "features"), _i32(idx, "idx")
+    B, N, C = f.shape
+    M, ns = i.shape[1], i.shape[2]
+    with torch.cuda.device(f.device):
+        out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
+        arg = torch.empty((B, M, C), dtype=torch.uint8, device=f.device)
+        _lib.check(L.d3d_gather_max_fwd(_p(f), _p(i), B, M, N, C, ns, _p(out), _p(arg), _stream()), "d3d_gather_max_fwd")
+    _count()
+    return out, arg
+
+
+def gather_max_bwd(grad_out_cl, argslot, rowptr, entries, n_support):
+    L = _lib.load()
+    g = _f32(grad_out_cl, "grad_out")
+    B, M, C = g.shape
+    with torch.cuda.device(g.device):
+        out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
+        _lib.check(L.d3d_gather_max_bwd(_p(g), _p(argslot), _p(rowptr), _p(entries), B, M, int(n_support), C, _p(out),
+                                        _stream()), "d3d_gather_max_bwd")
+    _count()
+    return out
+
+
+def nearest_gather_fwd(feat_cl, idx):
+    L = _lib.load()
+    f, i = _f32(feat_cl, "features"), _i32(idx, "idx")
+    B, N, C = f.shape
+    M = i.shape[1]
+    with torch.cuda.device(f.device):
+        out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
+        _lib.check(L.d3d_nearest_gather_fwd(_p(f), _p(i), B, M, N, C, _p(out), _stream()), "d3d_nearest_gather_fwd")
+    _count()
+    return out
+
+
+def nearest_gather_bwd(grad_out_cl, rowptr, entries, n_support):
+    L = _lib.load()
+    g = _f32(grad_out_cl, "grad_out")
+    B, M, C = g.shape
+    with torch.cuda.device(g.device):
+        out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
+        _lib.check(L.d3d_nearest_gather_bwd(_p(g), _p(rowptr), _p(entries), B, M, int(n_support), C, _p(out), _stream()),
+                   "d3d_nearest_gather_bwd")
+    _count()
+    return out

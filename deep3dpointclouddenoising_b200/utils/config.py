@@ -1,0 +1,112 @@
+"""Global experiment config with the reference's keys, defaults and strict yaml overlay.
+
+Mirrors u_net_arch/utils/config.py: a module-level attribute dictionary `config` (:4-142) and
+`update_config(path)` (:145-156), which copies a yaml file over the defaults and raises ValueError for
+any key the defaults do not know.  `easydict` (the reference's container) is not a dependency here;
+AttrDict below gives the same attribute + item access.  Reference cfgs/*.yaml files load unchanged.
+"""
+import copy
+
+import yaml
+
+
+class AttrDict(dict):
+    """dict with attribute access, nested dicts converted on assignment (what easydict provides)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __setitem__(self, k, v):
+        if isinstance(v, dict) and not isinstance(v, AttrDict):
+            v = AttrDict(v)
+        super().__setitem__(k, v)
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    __setattr__ = __setitem__
+
+    def __deepcopy__(self, memo):
+        return AttrDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+
+_DEFAULTS = {
+    # experiment options (config.py:9-24)
+    "experiment_name": "", "noise_level": -1, "outlier_percentage": -1, "epoch_model_used": -1, "loss": "l1",
+    "jitter": 0, "norm": 0, "GAN": 0, "load_path_generator": "", "load_path_discriminator": "",
+    "head_discriminator": "None", "freeze_gen": 0, "architecture": "U-Net", "noise_type": "gaussian",
+    "sample_Dl_patches": 0.05, "fourier_features": 0,
+    # training options (:30-41)
+    "epochs": 50, "start_epoch": 1, "base_learning_rate": 0.01, "lr_scheduler": "step", "optimizer": "sgd",
+    "warmup_epoch": 5, "warmup_multiplier": 100, "lr_decay_steps": 20, "lr_decay_rate": 0.7, "weight_decay": 0,
+    "momentum": 0.9, "grid_clip_norm": -1,
+    # model (:45-55)
+    "backbone": "resnet", "head": "resnet_cls", "radius": 0.05, "sampleDl": 0.02, "density_parameter": 5.0,
+    "nsamples": [], "npoints": [], "width": 144, "depth": 2, "bottleneck_ratio": 2, "bn_momentum": 0.1,
+    # data (:60-85)
+    "datasets": "modelnet40", "data_root": "", "num_classes": 40, "num_parts": 0, "features": [],
+    "input_features_dim": 1, "katz_params": [], "katz_type": "std", "batch_size": 32, "num_points": 5000,
+    "num_workers": 4, "x_angle_range": 0.0, "y_angle_range": 0.0, "z_angle_range": 0.0, "scale_low": 2.0 / 3.0,
+    "scale_high": 3.0 / 2.0, "noise_std": 0.01, "noise_clip": 0.05, "translate_range": 0.2, "color_drop": 0.2,
+    "augment_symmetries": [0, 0, 0],
+    # scene segmentation related (:92-93)
+    "in_radius": 2.0, "num_steps": 500,
+    # io and misc (:98-105)
+    "load_path": "", "print_freq": 10, "save_freq": 10, "val_freq": 10, "log_dir": "log", "local_rank": 0,
+    "amp_opt_level": "", "rng_seed": 0,
+    # local aggregation (:110-141)
+    "local_aggregation_type": "pospool",
+    "pospool": {"position_embedding": "xyz", "reduction": "sum", "output_conv": False},
+    "adaptive_weight": {"weight_type": "dp", "num_mlps": 1, "shared_channels": 1, "weight_softmax": False,
+                        "reduction": "avg", "output_conv": False},
+    "pointwisemlp": {"feature_type": "dp_df", "num_mlps": 1, "reduction": "max"},
+    "pseudo_grid": {"fixed_kernel_points": "center", "KP_influence": "linear", "KP_extent": 1.0,
+                    "num_kernel_points": 15, "convolution_mode": "sum", "output_conv": False},
+    "attention": {"type": "Non-local"},
+}
+
+config = AttrDict(copy.deepcopy(_DEFAULTS))
+
+# Not in the reference: selects the arithmetic of the PseudoGrid contraction.
+#   'fp32' CUDA cores (parity tolerance 1e-5) | 'bf16' tcgen05 tensor cores (separate tolerance)
+# Kept outside the yaml-checked key set so that reference yaml files stay valid and unknown keys still raise.
+runtime = AttrDict({"pseudo_grid_precision": "fp32"})
+
+
+def reset_config():
+    """Back to the defaults (the reference has no such call; tests need it because `config` is global)."""
+    config.clear()
+    for k, v in copy.deepcopy(_DEFAULTS).items():
+        config[k] = v
+    return config
+
+
+def update_config(config_file):
+    with open(config_file) as f:
+        overlay = yaml.load(f, Loader=yaml.FullLoader)
+    for key, value in (overlay or {}).items():
+        if key not in config:
+            raise ValueError("{} key must exist in config.py".format(key))
+        if isinstance(value, dict):
+            for sub_key, sub_value in value.items():
+                config[key][sub_key] = sub_value
+        else:
+            config[key] = value
+
+
+def apply_train_geometry(cfg, in_radius=0.05):
+    """The geometry train_dist.py imposes on every yaml before building the model (train_dist.py:125-137):
+    in_radius 0.05, sampleDl = in_radius/32, radius = max(in_radius*sqrt(3)/32, 0.025),
+    nsamples [52,39,32,26,26], npoints [N/4, N/16, N/32, N/128] from the yaml's num_points."""
+    import numpy as np
+    cfg.in_radius = in_radius
+    cfg.sampleDl = cfg.in_radius / 32
+    cfg.radius = max(cfg.in_radius * np.sqrt(3) / 32, 0.025)
+    cfg.nsamples = [52, 39, 32, 26, 26]
+    cfg.npoints = [max(int(cfg.num_points / d), 1) for d in (4.0, 16.0, 32.0, 128.0)]
+    return cfg

@@ -1,0 +1,167 @@
+/* d3d_b200.h — C ABI of the B200-native neighbourhood + local-aggregation path.
+ *
+ * One shared library (deep3dpointclouddenoising_b200/libd3d_b200.so, built by plain nvcc for
+ * sm_100a, no torch / ATen / pybind types anywhere in the signatures).  Every entry point
+ *   - takes raw DEVICE pointers, sizes, scalars, a caller-provided workspace and a cudaStream_t
+ *     (passed as void* so that this header needs no CUDA include),
+ *   - only enqueues work on that stream (no allocation, no synchronisation, no host read-back),
+ *   - returns 0 on success, a positive cudaError_t if a launch failed, or a negative D3D_ERR_*
+ *     for a rejected argument.  It never calls exit() (the reference does: cuda_utils.h:35-44).
+ *
+ * Paths cited as "ref:" are relative to /root/reference/u_net_arch/.
+ *
+ * Conventions shared by all functions
+ *   xyz arrays      float32 (B, N, 3) contiguous                       ref: pt_custom_ops/_ext_src/include/utils.h:15-30
+ *   masks           int32   (B, N)   0/1 with the valid entries a PREFIX (kernels stop at the first 0,
+ *                                    ref: _ext_src/src/masked_ordered_ball_query_gpu.cu:50-52)
+ *   idx             int32   (B, M, nsample)
+ *   "cm" features   float32 (B, C, N)   channel-major — the reference's layout (Conv1d layout)
+ *   "cl" features   float32 (B, N, C)   channel-last  — the layout the fused kernels gather from
+ */
+#ifndef D3D_B200_H_
+#define D3D_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3D_ERR_BAD_ARG     (-1)  /* null pointer, non-positive size, nsample out of range ...   */
+#define D3D_ERR_UNSUPPORTED (-2)  /* a size beyond what the kernels were built for               */
+#define D3D_ERR_WORKSPACE   (-3)  /* workspace missing or smaller than *_workspace_bytes()        */
+
+#define D3D_MAX_NSAMPLE 255       /* slot numbers are packed in 8 bits of an inverse-map entry    */
+
+/* ABI version of this header; bumped on any signature change. */
+int d3d_abi_version(void);
+/* Human-readable description of a return code (static storage). */
+const char* d3d_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. Neighbourhood construction (bit-exact with the reference kernels)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces  _ext.masked_ordered_ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample)
+ *   ref: _ext_src/src/masked_ordered_ball_query.cpp:13-59, _ext_src/src/masked_ordered_ball_query_gpu.cu:11-96
+ *        (binding: _ext_src/src/bindings.cpp:11; Python caller: pt_custom_ops/pt_utils.py:71-72).
+ * Out: idx, idx_mask (B, M, nsample) int32.  nvalid (B, M) int32 may be NULL; when given it receives
+ * min(#in-radius supports, nsample) per query BEFORE the query mask is applied (the fused aggregation
+ * kernels use it instead of the dense idx_mask).
+ * Workspace: d3d_ball_query_workspace_bytes(B).  Unlike the reference no (B, M, 3*nsample) scratch
+ * tensors are needed (masked_ordered_ball_query.cpp:38-44). */
+size_t d3d_ball_query_workspace_bytes(int B);
+int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                   const int* support_mask, int B, int M, int N, float radius, int nsample,
+                   int* idx, int* idx_mask, int* nvalid, void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces  _ext.masked_nearest_query(query_xyz, support_xyz, query_mask, support_mask)
+ *   ref: _ext_src/src/masked_nearest_query.cpp:12-47, _ext_src/src/masked_nearest_query_gpu.cu:8-62
+ *        (binding: bindings.cpp:13; caller: pt_utils.py:87).
+ * Out: idx, idx_mask (B, M) int32 (the reference shapes them (B, M, 1)); idx = -1 when no support
+ * has d2 < 100 (masked_nearest_query_gpu.cu:36-38). */
+size_t d3d_nearest_query_workspace_bytes(int B);
+int d3d_nearest_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
+                      const int* support_mask, int B, int M, int N, int* idx, int* idx_mask,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* Replaces  _ext.masked_grid_subsampling(xyz, mask, npoint, sampleDl)
+ *   ref: _ext_src/src/masked_grid_subsampling.cpp:13-44, _ext_src/src/masked_grid_subsampling_gpu.cu:11-153
+ *        (binding: bindings.cpp:14; caller: pt_utils.py:102).
+ * Out: sub_xyz (B, m, 3) float32, sub_mask (B, m) int32.
+ * Workspace: d3d_grid_subsample_workspace_bytes(B, N) (only used when a cloud does not fit in
+ * shared memory, N > 16384). */
+size_t d3d_grid_subsample_workspace_bytes(int B, int N);
+int d3d_grid_subsample(const float* xyz, const int* mask, int B, int N, int m, float sample_dl,
+                       float* sub_xyz, int* sub_mask, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Gather and its gradient (the reference's layout: channel-major in, (B, C, M, nsample) out)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces  _ext.group_points(points, idx)          ref: _ext_src/src/group_points.cpp:17-40,
+ *                                                         _ext_src/src/group_points_gpu.cu:13-44
+ * out[b,c,j,k] = points[b,c,idx[b,j,k]];  points (B,C,N) cm, out (B,C,M,nsample). */
+int d3d_group_points(const float* points, const int* idx, int B, int C, int N, int M, int nsample,
+                     float* out, void* stream);
+
+/* Replaces  _ext.group_points_grad(grad_out, idx, N)   ref: group_points.cpp:42-65, group_points_gpu.cu:48-80
+ * grad_points[b,c,i] = sum over (j,k) with idx[b,j,k]==i of grad_out[b,c,j,k], summed in ascending
+ * (j,k) — deterministic, no float atomics (the reference uses atomicAdd, group_points_gpu.cu:65).
+ * Workspace: d3d_group_points_grad_workspace_bytes (an inverse map is built inside the call). */
+size_t d3d_group_points_grad_workspace_bytes(int B, int N, int M, int nsample);
+int d3d_group_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M, int nsample,
+                          float* grad_points, void* ws, size_t ws_bytes, void* stream);
+
+/* Inverse neighbour map (CSR by support point) of one idx tensor; shared by every backward kernel
+ * of a (query set, support set) pair.
+ *   rowptr  (B*N + 1) int32: entries of support (b,i) are entries[rowptr[b*N+i] .. rowptr[b*N+i+1])
+ *   entries (B*M*nsample) int32: (j << 8) | k, ascending inside each segment
+ * Indices outside [0, N) are treated as 0 like the reference's clamp (pt_utils.py:126-127). */
+size_t d3d_inverse_map_workspace_bytes(int B, int N, int M, int nsample);
+int d3d_build_inverse_map(const int* idx, int B, int N, int M, int nsample, int* rowptr, int* entries,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* Layout helpers: (B,C,N) cm <-> (B,N,C) cl. */
+int d3d_cm_to_cl(const float* src_cm, int B, int C, int N, float* dst_cl, void* stream);
+int d3d_cl_to_cm(const float* src_cl, int B, int C, int N, float* dst_cm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. Fused local aggregation (what the reference computes in eager PyTorch on the materialised
+ *    (B, C, M, nsample) gather).  All feature tensors here are channel-last.
+ *    mask semantics: fm[b,j,k] = query_mask[b,j] ? (k < nvalid[b,j]) : 1
+ *    (= idx_mask + (1 - query_mask), ref: models/local_aggregation_operators.py:171,490)
+ * ---------------------------------------------------------------------------------------------- */
+
+#define D3D_REDUCE_SUM 0
+#define D3D_REDUCE_AVG 1
+
+/* PosPool, position_embedding 'xyz'       ref: models/local_aggregation_operators.py:140-147,165-183
+ * out[b,j,c] = sum_k fm * ((S[idx]-Q[j])[c%3] * (1/radius)) * F[b,idx[b,j,k],c]   ( / sum_k fm for AVG ) */
+int d3d_pospool_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz,
+                    const int* idx, const int* nvalid, const int* query_mask, int B, int M, int N, int C,
+                    int nsample, float radius, int reduction, float* out_cl, void* stream);
+int d3d_pospool_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
+                    const int* rowptr, const int* entries, const int* nvalid, const int* query_mask,
+                    int B, int M, int N, int C, int nsample, float radius, int reduction,
+                    float* grad_feat_cl, void* stream);
+
+#define D3D_KP_CONSTANT 0
+#define D3D_KP_LINEAR   1
+#define D3D_KP_GAUSSIAN 2
+
+/* PseudoGrid (depthwise KPConv)           ref: models/local_aggregation_operators.py:467-503
+ * out[b,j,c] = sum_k W[k,c] * sum_m w[b,j,k,m] * F[b,idx[b,j,m],c],
+ * w = influence(|| (S[idx]-Q[j]) - K[k] ||, extent) * fm;  kpoints (K,3), weights (K,C), K <= 16.
+ * precision: 0 = fp32 CUDA cores; 1 = bf16 tcgen05 contraction of [slots x K] . [K x C] (fp32 accumulate) */
+int d3d_pseudogrid_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz,
+                       const int* idx, const int* nvalid, const int* query_mask, const float* kpoints,
+                       const float* weights, int B, int M, int N, int C, int nsample, int K, float extent,
+                       int influence, int precision, float* out_cl, void* stream);
+/* grad wrt features (via the inverse map) and wrt weights (deterministic two-pass reduction).
+ * Workspace: d3d_pseudogrid_bwd_workspace_bytes. */
+size_t d3d_pseudogrid_bwd_workspace_bytes(int B, int M, int C, int K);
+int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const float* query_xyz,
+                       const float* support_xyz, const int* idx, const int* rowptr, const int* entries,
+                       const int* nvalid, const int* query_mask, const float* kpoints, const float* weights,
+                       int B, int M, int N, int C, int nsample, int K, float extent, int influence,
+                       float* grad_feat_cl, float* grad_weights, void* ws, size_t ws_bytes, void* stream);
+
+/* MaskedMaxPool's gather + max over all nsample slots   ref: pt_custom_ops/pt_utils.py:199-205
+ * out[b,j,c] = max_k F[b,idx[b,j,k],c]; argslot (B,M,C) uint8 = first slot attaining the max. */
+int d3d_gather_max_fwd(const float* feat_cl, const int* idx, int B, int M, int N, int C, int nsample,
+                       float* out_cl, uint8_t* argslot, void* stream);
+int d3d_gather_max_bwd(const float* grad_out_cl, const uint8_t* argslot, const int* rowptr,
+                       const int* entries, int B, int M, int N, int C, float* grad_feat_cl, void* stream);
+
+/* MaskedUpsample(mode='nearest')           ref: pt_custom_ops/pt_utils.py:222-226
+ * out[b,j,c] = F[b,idx[b,j],c]; idx (B,M) (negative indices read row 0). */
+int d3d_nearest_gather_fwd(const float* feat_cl, const int* idx, int B, int M, int N, int C, float* out_cl,
+                           void* stream);
+int d3d_nearest_gather_bwd(const float* grad_out_cl, const int* rowptr, const int* entries, int B, int M,
+                           int N, int C, float* grad_feat_cl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3D_B200_H_ */

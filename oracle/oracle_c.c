@@ -13,7 +13,8 @@
  * Floating point: the device build of the reference contracts the squared distance to
  *   d2 = fma(dz, dz, fma(dx, dx, dy*dy))          (SASS: FADD FADD FMUL FADD FFMA FFMA, dy first)
  * so it is spelled with explicit fmaf() here and this file is compiled with -ffp-contract=off.
- * Everything else in the reference kernels is single IEEE operations (sub, mul, div, floor).
+ * The grid-subsampling kernel has one more contraction: "x - floor(min/dl)*dl" is a single FFMA on the
+ * device (see oracle_grid_subsampling).  Everything else is single IEEE operations (mul, div, floor).
  */
 #include <math.h>
 #include <stdint.h>
@@ -141,16 +142,19 @@ void oracle_grid_subsampling(int b, int n, int m, float dl, const float* xyz, co
         if (c < lo[d]) lo[d] = c;
       }
     const float inv = 1 / dl;                                   /* rounded reciprocal first (:48) */
-    float org[3];
-    for (int d = 0; d < 3; ++d) org[d] = floorf(lo[d] * inv) * dl;
-    const int NX = (int)floorf((hi[0] - org[0]) / dl) + 1;
-    const int NY = (int)floorf((hi[1] - org[1]) / dl) + 1;
+    /* origin = floor(min*inv)*dl is never rounded on its own in the device build: nvcc contracts every
+     * "coordinate - origin" into one FFMA (SASS of the reference kernel: FFMA R, -Rfloor, Rdl, Rcoord),
+     * so the restatement keeps the floor() factor and spells the fma out (:48-54, :67-69). */
+    float fl[3];
+    for (int d = 0; d < 3; ++d) fl[d] = floorf(lo[d] * inv);
+    const int NX = (int)floorf(fmaf(-fl[0], dl, hi[0]) / dl) + 1;
+    const int NY = (int)floorf(fmaf(-fl[1], dl, hi[1]) / dl) + 1;
     int v = prefix_len(mask + (size_t)bi * n, n);
     pair_t* cell = (pair_t*)malloc(sizeof(pair_t) * (size_t)(n > 0 ? n : 1));
     for (int i = 0; i < v; ++i) {
-      const int ix = (int)floorf((P[3 * i + 0] - org[0]) / dl);
-      const int iy = (int)floorf((P[3 * i + 1] - org[1]) / dl);
-      const int iz = (int)floorf((P[3 * i + 2] - org[2]) / dl);
+      const int ix = (int)floorf(fmaf(-fl[0], dl, P[3 * i + 0]) / dl);
+      const int iy = (int)floorf(fmaf(-fl[1], dl, P[3 * i + 1]) / dl);
+      const int iz = (int)floorf(fmaf(-fl[2], dl, P[3 * i + 2]) / dl);
       cell[i].key = (int32_t)(ix + NX * iy + NX * NY * iz);     /* int32 arithmetic like the kernel */
       cell[i].val = i;
     }

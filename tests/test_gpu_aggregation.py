@@ -1,0 +1,161 @@
+"""GPU parity, fused aggregation: PosPool / PseudoGrid / max-pool / nearest upsample, forward and backward,
+through the public modules, against (a) the committed outputs and gradients of the reference's own Python
+modules and (b) the float oracle (oracle/aggregation_ref.py) on larger seeded inputs.
+
+Tolerances (fp32): outputs rtol 1e-5 / atol 1e-6 (a sum of <= nsample products in a different order);
+gradients rtol 1e-4 / atol 1e-5 (the reference's own backward is an unordered atomicAdd).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deep3dpointclouddenoising_b200 import synthetic
+from oracle import aggregation_ref as agg
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FWD = dict(rtol=1e-5, atol=2e-6)
+BWD = dict(rtol=1e-4, atol=2e-5)
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+def _cfg(**over):
+    from deep3dpointclouddenoising_b200.utils.config import AttrDict
+    c = AttrDict(bn_momentum=0.1, density_parameter=5.0, local_aggregation_type='pospool',
+                 pospool=AttrDict(position_embedding='xyz', reduction='avg', output_conv=False),
+                 pseudo_grid=AttrDict(fixed_kernel_points='center', KP_influence='linear', KP_extent=1.0,
+                                      num_kernel_points=15, convolution_mode='sum', output_conv=False))
+    for k, v in over.items():
+        c[k] = v
+    return c
+
+
+def _run(op, args, feat, params=(), gout=None):
+    feat = feat.clone().requires_grad_(True)
+    y = op(*args, feat)
+    grads = torch.autograd.grad(y, (feat,) + tuple(params), gout)
+    return y.detach().cpu().numpy(), [g.cpu().numpy() for g in grads]
+
+
+@pytest.mark.parametrize("tag", ["self", "strided"])
+def test_operators_against_reference_python_goldens(cuda_device, tag):
+    from deep3dpointclouddenoising_b200.models import local_aggregation_operators as lao
+    g = np.load(os.path.join(GOLD, "aggregation.npz"))
+    B, N, C, ns = [int(x) for x in g["meta"]]
+    radius = float(g["radius"])
+    xyz, m = dev(g["points"], cuda_device), dev(g["mask"], cuda_device)
+    q, qm = (xyz, m) if tag == "self" else (dev(g["sub_xyz"], cuda_device), dev(g["sub_mask"], cuda_device))
+    feats = dev(g["features"], cuda_device)
+    for red, emb, key in (("avg", "xyz", "avg"), ("sum", "xyz", "sum"), ("max", "xyz", "max"), ("avg", "sin_cos", "sincos")):
+        cfg = _cfg()
+        cfg.pospool.reduction, cfg.pospool.position_embedding = red, emb
+        op = lao.PosPool(C, C, radius, ns, cfg).to(cuda_device)
+        op.out_transform = torch.nn.Identity()
+        y, (gf,) = _run(op, (q, xyz, qm, m), feats, gout=dev(g[f"pospool_{tag}_{key}_gout"], cuda_device))
+        tol = FWD if emb == "xyz" else dict(rtol=1e-4, atol=1e-5)  # sin/cos of 100*dp: libm vs device sin
+        np.testing.assert_allclose(y, g[f"pospool_{tag}_{key}_out"], **tol)
+        np.testing.assert_allclose(gf, g[f"pospool_{tag}_{key}_gfeat"], **BWD)
+    for infl in ("linear", "constant"):
+        pre = f"pseudogrid_{tag}_{infl}"
+        cfg = _cfg()
+        cfg.pseudo_grid.KP_influence = infl
+        op = lao.PseudoGrid(C, C, radius, ns, cfg).to(cuda_device)
+        op.out_transform = torch.nn.Identity()
+        assert np.array_equal(op.K_points.cpu().numpy(), g[pre + "_kpoints"])  # shipped table == reference fixture
+        assert abs(op.extent - float(g[pre + "_extent"])) < 1e-9
+        with torch.no_grad():
+            op.kernel_weights.copy_(dev(g[pre + "_weights"], cuda_device))
+        y, (gf, gw) = _run(op, (q, xyz, qm, m), feats, (op.kernel_weights,), dev(g[pre + "_gout"], cuda_device))
+        np.testing.assert_allclose(y, g[pre + "_out"], rtol=1e-5, atol=5e-6)
+        np.testing.assert_allclose(gf, g[pre + "_gfeat"], **BWD)
+        np.testing.assert_allclose(gw, g[pre + "_gweights"], rtol=1e-4, atol=2e-4)
+
+
+def test_maxpool_and_upsample_against_reference_python_goldens(cuda_device):
+    from deep3dpointclouddenoising_b200.pt_custom_ops import pt_utils
+    g = np.load(os.path.join(GOLD, "aggregation.npz"))
+    B, N, C, ns = [int(x) for x in g["meta"]]
+    radius = float(g["radius"])
+    xyz, m = dev(g["points"], cuda_device), dev(g["mask"], cuda_device)
+    pool = pt_utils.MaskedMaxPool(96, radius, ns, 0.00625)
+    f = dev(g["features"], cuda_device).requires_grad_(True)
+    sx, sm, sf = pool(xyz, m, f)
+    assert np.array_equal(sx.cpu().numpy(), g["maxpool_sub_xyz"]) and np.array_equal(sm.cpu().numpy(), g["maxpool_sub_mask"])
+    assert np.array_equal(sf.detach().cpu().numpy(), g["maxpool_out"])  # a max of copies: exact
+    (gf,) = torch.autograd.grad(sf, f, dev(g["maxpool_gout"], cuda_device))
+    np.testing.assert_allclose(gf.cpu().numpy(), g["maxpool_gfeat"], **BWD)
+    up = pt_utils.MaskedUpsample(radius, ns, mode='nearest')
+    cf = dev(g["upsample_features"], cuda_device).requires_grad_(True)
+    y = up(xyz, sx, m, sm, cf)
+    assert np.array_equal(y.detach().cpu().numpy(), g["upsample_out"])
+    (gf,) = torch.autograd.grad(y, cf, dev(g["upsample_gout"], cuda_device))
+    np.testing.assert_allclose(gf.cpu().numpy(), g["upsample_gfeat"], **BWD)
+
+
+@pytest.mark.parametrize("C,N,M,ns,radius", [(72, 2048, 2048, 52, 0.025), (144, 2048, 512, 39, 0.03), (288, 512, 512, 32, 0.05),
+                                             (576, 256, 64, 26, 0.08), (1152, 64, 64, 26, 0.4), (12, 300, 300, 7, 0.02)])
+def test_fused_ops_against_float_oracle(cuda_device, oracle, C, N, M, ns, radius):
+    """Every channel width of the U-Net (72..1152 -> 1..9 float4 per lane) and a narrow one."""
+    from deep3dpointclouddenoising_b200 import fused, neighbors
+    B = 2
+    pts, mask, _, _ = synthetic.make_batch(500 + C, B, N, ragged=True)
+    if M == N:
+        q, qm = pts, mask
+    else:
+        q, qm = oracle.grid_subsampling(pts, mask, M, 0.05 / 32 * (N / M) ** 0.5)
+    idx, msk = oracle.ball_query(q, pts, qm, mask, radius, ns)
+    rng = np.random.default_rng(C)
+    f = rng.standard_normal((B, C, N)).astype(np.float32)
+    gout = rng.standard_normal((B, C, M)).astype(np.float32)
+    kp = (rng.standard_normal((15, 3)) * 0.4 * radius).astype(np.float32)
+    w = (rng.standard_normal((15, C)) * 0.2).astype(np.float32)
+    extent = 0.4 * radius
+    # float oracle on the CPU
+    tf = torch.from_numpy(f).requires_grad_(True)
+    tw = torch.from_numpy(w).requires_grad_(True)
+    targs = [torch.from_numpy(np.ascontiguousarray(a)) for a in (q, pts, qm, idx, msk)]
+    o_pp = agg.pospool(tf, targs[0], targs[1], targs[2], targs[3], targs[4], radius, 'avg')
+    (o_pp_g,) = torch.autograd.grad(o_pp, tf, torch.from_numpy(gout))
+    o_pg = agg.pseudogrid(tf, tw, torch.from_numpy(kp), targs[0], targs[1], targs[2], targs[3], targs[4], extent)
+    o_pg_g, o_pg_gw = torch.autograd.grad(o_pg, (tf, tw), torch.from_numpy(gout))
+    o_mp = agg.max_pool(tf, targs[3])
+    (o_mp_g,) = torch.autograd.grad(o_mp, tf, torch.from_numpy(gout))
+    # CUDA
+    dq, ds, dqm, dsm = dev(q, cuda_device), dev(pts, cuda_device), dev(qm, cuda_device), dev(mask, cuda_device)
+    nbr = neighbors.ball_neighbors(dq, ds, dqm, dsm, radius, ns)
+    assert np.array_equal(nbr.idx.cpu().numpy(), idx)
+    df = dev(f, cuda_device).requires_grad_(True)
+    dw = dev(w, cuda_device).requires_grad_(True)
+    dg = dev(gout, cuda_device)
+    y = fused.PosPoolFunction.apply(df, dq, ds, dqm, nbr, radius, 'avg')
+    np.testing.assert_allclose(y.detach().cpu().numpy(), o_pp.detach().numpy(), **FWD)
+    np.testing.assert_allclose(torch.autograd.grad(y, df, dg)[0].cpu().numpy(), o_pp_g.numpy(), **BWD)
+    y = fused.PseudoGridFunction.apply(df, dw, dq, ds, dqm, nbr, dev(kp, cuda_device), extent, 'linear', 0)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), o_pg.detach().numpy(), rtol=1e-5, atol=1e-5)
+    gf, gw = torch.autograd.grad(y, (df, dw), dg)
+    np.testing.assert_allclose(gf.cpu().numpy(), o_pg_g.numpy(), **BWD)
+    np.testing.assert_allclose(gw.cpu().numpy(), o_pg_gw.numpy(), rtol=1e-3, atol=1e-3 * np.abs(o_pg_gw.numpy()).max())
+    y = fused.GatherMaxFunction.apply(df, nbr)
+    assert np.array_equal(y.detach().cpu().numpy(), o_mp.detach().numpy())
+    np.testing.assert_allclose(torch.autograd.grad(y, df, dg)[0].cpu().numpy(), o_mp_g.numpy(), **BWD)
+
+
+def test_backward_is_deterministic(cuda_device):
+    """Two backward passes give identical bits (segmented reduction, no float atomics)."""
+    from deep3dpointclouddenoising_b200 import fused, neighbors
+    pts, mask, feats, _ = synthetic.make_batch(9, 4, 4096, ragged=True)
+    dx, dm = dev(pts, cuda_device), dev(mask, cuda_device)
+    f = torch.randn(4, 72, 4096, device=cuda_device, requires_grad=True)
+    g = torch.randn(4, 72, 4096, device=cuda_device)
+    grads = []
+    for _ in range(2):
+        neighbors.cache.clear()
+        nbr = neighbors.ball_neighbors(dx, dx, dm, dm, 0.025, 52)
+        y = fused.PosPoolFunction.apply(f, dx, dx, dm, nbr, 0.025, 'avg')
+        grads.append(torch.autograd.grad(y, f, g)[0])
+    assert torch.equal(grads[0], grads[1])
