@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py — training points/s of the point U-Net offset-regression step on synthetic PointCleanNet-shaped patches.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference algorithm on the host cores, rank 0 only)
+
+Workload (BASELINE.json configs[1]): cfgs/l1.yaml geometry as train_dist.py imposes it, PosPool aggregation
+(`--operator pseudo_grid` for configs[2]), batch 16 x 8192-point patches per GPU, fp32, Adam, grad-clip 10.
+A step = forward + MaskedL1 loss + backward + clip + optimizer step (train_dist.py:440-451).
+
+One JSON line on rank 0:
+  value        points/s with the batch already resident in HBM (device-timed, max over ranks)
+  e2e          same metric through the public API with HOST batches: pinned H2D copy of every step's inputs and a
+               D2H read of the loss inside the timed region
+  roofline     dominant kernel of the step: algorithmic bytes / CUDA-event duration measured live vs MEASURED_PEAKS.json
+  cpu_baseline the oracle port of the same step (oracle/cpu_model.py) on the host cores, bounded sample
+  kernels      per-op device time inside one instrumented step (explains value; not part of the contract)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_points_per_sec_fwd_bwd"
+UNIT = "points/s"
+BATCH, NUM_POINTS = 16, 8192
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--operator", default="pospool", choices=["pospool", "pseudo_grid"])
+    p.add_argument("--pseudo-grid-precision", default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--batch", type=int, default=BATCH)
+    p.add_argument("--num-points", type=int, default=NUM_POINTS)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def build_model(operator, num_points):
+    from deep3dpointclouddenoising_b200.models import build_offset_regression
+    from deep3dpointclouddenoising_b200.utils import config as cfgmod
+    cfgmod.reset_config()
+    name = "l1.yaml" if operator == "pseudo_grid" else "l1_pospool.yaml"
+    cfgmod.update_config(os.path.join(ROOT, "deep3dpointclouddenoising_b200", "cfgs", name))
+    c = cfgmod.config
+    c.num_points = num_points
+    cfgmod.apply_train_geometry(c)
+    c.input_features_dim = 0
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model, criterion = build_offset_regression(c)
+    model.init_weights()
+    return model, criterion, c
+
+
+def workload_name(operator, batch, num_points):
+    return (f"U-Net offset regression fwd+bwd, cfgs/l1.yaml geometry (train_dist.py:125-137), "
+            f"{'PosPool xyz/avg' if operator == 'pospool' else 'PseudoGrid 15 kernel points'}, "
+            f"batch {batch} x {num_points}-point synthetic noisy patches per GPU")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# algorithmic bytes of one call of each op (compulsory HBM traffic, fp32/int32)
+# ------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(op, s):
+    B, M, N, C, ns = s.get("B", 0), s.get("M", 0), s.get("N", 0), s.get("C", 0), s.get("ns", 0)
+    if op == "ball_query":
+        return 16 * B * (M + N) + 8 * B * M * ns
+    if op == "nearest_query":
+        return 16 * B * (M + N) + 8 * B * M
+    if op == "grid_subsample":
+        return 16 * B * N + 16 * B * M
+    if op == "build_inverse_map":
+        return 4 * B * M * ns * 2 + 4 * B * N
+    if op in ("cm_to_cl", "cl_to_cm"):
+        return 8 * B * C * N
+    if op in ("pospool_fwd", "pseudogrid_fwd", "gather_max_fwd"):
+        return 4 * B * C * N + 4 * B * M * ns + 4 * B * M + 12 * B * (M + N) + 4 * B * C * M
+    if op in ("pospool_bwd", "pseudogrid_bwd", "gather_max_bwd"):
+        return 4 * B * C * M + 4 * B * M * ns + 4 * B * N + 12 * B * (M + N) + 4 * B * C * N
+    if op in ("nearest_gather_fwd", "nearest_gather_bwd"):
+        return 4 * B * C * (M + N) + 4 * B * M
+    return 0
+
+
+class OpTimer:
+    """Wraps the ops module's functions with CUDA-event pairs on the current stream (instrumented pass only)."""
+
+    def __init__(self, ops):
+        self.ops, self.records, self.saved = ops, [], {}
+
+    def _shape(self, name, args):
+        t = [a for a in args if isinstance(a, torch.Tensor)]
+        try:
+            if name == "ball_query":
+                return dict(B=t[0].shape[0], M=t[0].shape[1], N=t[1].shape[1], ns=int(args[5]))
+            if name == "nearest_query":
+                return dict(B=t[0].shape[0], M=t[0].shape[1], N=t[1].shape[1])
+            if name == "grid_subsample":
+                return dict(B=t[0].shape[0], N=t[0].shape[1], M=int(args[2]))
+            if name == "build_inverse_map":
+                i = t[0]
+                return dict(B=i.shape[0], M=i.shape[1], ns=i.shape[2] if i.dim() == 3 else 1, N=int(args[1]))
+            if name == "cm_to_cl":
+                return dict(B=t[0].shape[0], C=t[0].shape[1], N=t[0].shape[2])
+            if name == "cl_to_cm":
+                return dict(B=t[0].shape[0], C=t[0].shape[2], N=t[0].shape[1])
+            if name in ("pospool_fwd", "pseudogrid_fwd"):
+                return dict(B=t[0].shape[0], N=t[0].shape[1], C=t[0].shape[2], M=t[3].shape[1], ns=t[3].shape[2])
+            if name == "gather_max_fwd":
+                return dict(B=t[0].shape[0], N=t[0].shape[1], C=t[0].shape[2], M=t[1].shape[1], ns=t[1].shape[2])
+            if name == "pospool_bwd":
+                return dict(B=t[0].shape[0], M=t[0].shape[1], C=t[0].shape[2], N=int(args[7]), ns=int(args[8]))
+            if name == "pseudogrid_bwd":
+                return dict(B=t[0].shape[0], M=t[0].shape[1], C=t[0].shape[2], N=t[1].shape[1], ns=t[4].shape[2])
+            if name == "gather_max_bwd":
+                return dict(B=t[0].shape[0], M=t[0].shape[1], C=t[0].shape[2], N=int(args[4]), ns=0)
+            if name == "nearest_gather_fwd":
+                return dict(B=t[0].shape[0], N=t[0].shape[1], C=t[0].shape[2], M=t[1].shape[1])
+            if name == "nearest_gather_bwd":
+                return dict(B=t[0].shape[0], M=t[0].shape[1], C=t[0].shape[2], N=int(args[3]))
+        except Exception:
+            pass
+        return {}
+
+    def __enter__(self):
+        names = ["ball_query", "nearest_query", "grid_subsample", "build_inverse_map", "cm_to_cl", "cl_to_cm",
+                 "pospool_fwd", "pospool_bwd", "pseudogrid_fwd", "pseudogrid_bwd", "gather_max_fwd", "gather_max_bwd",
+                 "nearest_gather_fwd", "nearest_gather_bwd", "group_points", "group_points_grad"]
+        for n in names:
+            fn = getattr(self.ops, n)
+            self.saved[n] = fn
+
+            def wrapped(*a, _fn=fn, _n=n, **k):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = _fn(*a, **k)
+                e.record()
+                self.records.append((_n, self._shape(_n, a), s, e))
+                return out
+
+            setattr(self.ops, n, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for n, fn in self.saved.items():
+            setattr(self.ops, n, fn)
+
+    def summary(self, n_steps):
+        torch.cuda.synchronize()
+        per = {}
+        for name, shape, s, e in self.records:
+            key = name + "".join(f" {k}{v}" for k, v in sorted(shape.items()))
+            d = per.setdefault(key, {"op": name, "shape": shape, "ms": 0.0, "calls": 0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+        for d in per.values():
+            d["ms_per_call"] = d["ms"] / d["calls"]
+            d["ms_per_step"] = d["ms"] / n_steps
+            d["bytes_per_call"] = algorithmic_bytes(d["op"], d["shape"])
+        return per
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the same step)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_step_fn(operator, num_points):
+    from oracle import cpu_index_ops
+    from oracle.cpu_model import CpuUNet
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, criterion, cfg = build_model(operator, num_points)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay)
+    # index ops: the reference's own kernels compiled for the host when the prebuilt library travelled, else the port
+    use_ref = cpu_index_ops.reference_available()
+    ix = cpu_index_ops.reference() if use_ref else cpu_index_ops.restated()
+    net = CpuUNet(model, ix)
+
+    def step(batch):
+        pts, mask, feats, offs = [torch.from_numpy(a) for a in batch]
+        opt.zero_grad(set_to_none=True)
+        loss = criterion(net(pts, mask, feats).transpose(1, 2), offs, mask)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10)
+        opt.step()
+        return float(loss)
+
+    kind = "port"  # aggregation math is the oracle restatement even when the index kernels are the reference's
+    return step, kind, ("reference kernels (host build) + " if use_ref else "") + "oracle port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from deep3dpointclouddenoising_b200 import synthetic
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    # one 8192-point patch costs ~13 s on 8 cores; keep the whole run within a few minutes
+    num_points, patches = args.num_points, 1
+    budget_s = 240.0
+    step, kind, how = cpu_step_fn(args.operator, num_points)
+    t0 = time.time()
+    step(synthetic.make_batch(999, patches, num_points))
+    probe = time.time() - t0
+    steps, warm = args.steps, args.warmup
+    if probe * total > budget_s:  # shrink what a "step" executes, never the patch geometry
+        warm = min(warm, 1)
+        steps = max(1, min(steps, int(budget_s / probe) - warm))
+    for w in range(warm):
+        step(synthetic.make_batch(1000 + w, patches, num_points))
+    t0 = time.time()
+    for s in range(steps):
+        step(synthetic.make_batch(2000 + s, patches, num_points))
+    dt = time.time() - t0
+    value = patches * num_points * steps / dt
+    sample = (f"{steps} timed steps (+{warm} warm-up) of {patches} x {num_points}-point patch fwd+bwd+Adam on {cores} host threads "
+              f"({how}); requested steps={args.steps} warmup={args.warmup} bounded to ~{int(budget_s)} s")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.operator, args.batch, args.num_points)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from deep3dpointclouddenoising_b200 import _lib, ops, synthetic
+    from deep3dpointclouddenoising_b200.utils import config as cfgmod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", init_method="env://")
+    lib = _lib.load()
+    cfgmod.runtime.pseudo_grid_precision = args.pseudo_grid_precision
+
+    model, criterion, cfg = build_model(args.operator, args.num_points)
+    model = model.to(dev)
+    if world > 1:  # the reference's data parallelism: DDP, NCCL gradient all-reduce (train_dist.py:375)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
+    else:
+        net = model
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay)
+    B, N = args.batch, args.num_points
+
+    def host_batch(step):  # per-rank shard of the synthetic patch stream
+        arrs = synthetic.make_batch(1234 + 1000 * rank + step, B, N)
+        return [torch.from_numpy(a).pin_memory() for a in arrs]
+
+    def train_step(pts, mask, feats, offs):
+        opt.zero_grad(set_to_none=True)
+        loss = criterion(net(pts, mask, feats).transpose(1, 2), offs, mask)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_host = 4
+    host = [host_batch(s) for s in range(n_host)]
+    resident = [[t.to(dev) for t in hb] for hb in host]
+
+    # ---- device-resident timing -------------------------------------------------------------------------
+    for w in range(max(args.warmup, 3)):
+        train_step(*resident[w % n_host])
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = lib.d3d_kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        train_step(*resident[s % n_host])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.d3d_kernel_launches() - launches0
+    clock_info = clocks.stop()
+
+    # ---- end to end: host batches in, loss out ----------------------------------------------------------
+    def e2e_step(hb):
+        dbatch = [t.to(dev, non_blocking=True) for t in hb]
+        return train_step(*dbatch).item()  # D2H read of the loss
+
+    for w in range(3):
+        e2e_step(host[w % n_host])
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(args.steps):
+        e2e_step(host[s % n_host])
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tt.tolist()
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- instrumented pass: where the step's device time goes, and the roofline of the dominant kernel ----
+    kernels, roofline = None, None
+    if rank == 0:
+        n_inst = 3
+        with OpTimer(ops) as timer:
+            for s in range(n_inst):
+                train_step(*resident[s % n_host])
+            per = timer.summary(n_inst)
+        step_ms = ms / args.steps
+        kernels = {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / n_inst,
+                       "gbs": round(v["bytes_per_call"] / 1e6 / v["ms_per_call"], 1) if v["ms_per_call"] > 0 else None}
+                   for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])[:12]}
+        ours_ms = sum(v["ms_per_step"] for v in per.values())
+        top_key, top = max(per.items(), key=lambda kv: kv[1]["ms"])
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        else:
+            peak, which = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        achieved = top["bytes_per_call"] / 1e6 / top["ms_per_call"]
+        roofline = {"bound": "hbm", "kernel": top_key, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
+                    "algorithmic_bytes_per_launch": top["bytes_per_call"], "ms_per_launch": round(top["ms_per_call"], 4),
+                    "share_of_step": round(top["ms_per_step"] / step_ms, 4),
+                    "our_kernels_share_of_step": round(ours_ms / step_ms, 4)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        step_cpu, kind, how = cpu_step_fn(args.operator, N)
+        batch = synthetic.make_batch(4242, 1, N)
+        t = time.time()
+        step_cpu(batch)
+        dt = time.time() - t
+        cpu_baseline = {"value": N / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"1 step of 1 x {N}-point patch fwd+bwd+Adam ({how}), {dt:.1f} s on {cores} host threads"}
+
+    if rank == 0:
+        pts_per_step = world * B * N
+        line = {"metric": METRIC, "value": pts_per_step * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args.operator, B, N), "global_batch": world * B,
+                           "num_points": N, "operator": args.operator,
+                           "pseudo_grid_precision": args.pseudo_grid_precision if args.operator == "pseudo_grid" else None,
+                           "parallelism": f"dp{world}", "optimizer": "adam", "l2": "per-step working set (activations, "
+                           "several GB) exceeds the 126 MB L2; 4 rotating input batches"},
+                "e2e": {"value": pts_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -267,6 +267,7 @@ int launch_fwd(const float* feat, const float* q, const float* s, const int* idx
       default: D3D_FWD(9); break;
     }
 #undef D3D_FWD
+    d3d_note_launches(1);
   }
   return d3d_launch_status();
 }
@@ -289,6 +290,7 @@ int launch_bwd(const float* gout, const float* q, const float* s, const int* row
       default: D3D_BWD(9); break;
     }
 #undef D3D_BWD
+    d3d_note_launches(1);
   }
   return d3d_launch_status();
 }
@@ -351,6 +353,7 @@ int d3d_nearest_gather_fwd(const float* feat_cl, const int* idx, int B, int M, i
   if (B == 0 || M == 0) return 0;
   dim3 grid(d3d_ceil_div((long long)M * (C / 4), 256), B);
   nearest_gather_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(feat_cl, idx, M, N, C / 4, out_cl);
+  d3d_note_launches(1);
   return d3d_launch_status();
 }
 

@@ -13,6 +13,9 @@
 
 static inline int d3d_launch_status() { return (int)cudaGetLastError(); }
 
+// Process-wide count of kernels this library has launched (d3d_kernel_launches(); bench.py reports it).
+void d3d_note_launches(int n);
+
 static inline int d3d_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Squared distance exactly as the reference kernels compute it on the device.  nvcc contracts

@@ -225,6 +225,7 @@ int d3d_grid_subsample(const float* xyz, const int* mask, int B, int N, int m, f
   }
   grid_subsample_kernel<<<B, kGsThreads, smem, st>>>(xyz, mask, N, m, sample_dl, sub_xyz, sub_mask,
                                                      (unsigned long long*)ws, pow2_at_least((size_t)N), in_smem ? 1 : 0);
+  d3d_note_launches(1);
   return d3d_launch_status();
 }
 

@@ -181,6 +181,7 @@ int d3d_build_inverse_map(const int* idx, int B, int N, int M, int nsample, int*
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(w.long_count, 0, sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
+  d3d_note_launches(total > 0 ? 5 : 1);
   if (total > 0) count_kernel<<<d3d_ceil_div(total, 256), 256, 0, st>>>(idx, total, P, N, w.cursor);
   scan_kernel<<<B, 1024, 0, st>>>(w.cursor, N, P, B, rowptr);
   if (total > 0) {

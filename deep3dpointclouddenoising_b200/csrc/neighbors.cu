@@ -215,6 +215,7 @@ int launch_ball_query(const float* q, const float* s, const int* qm, const int* 
   dim3 grid(d3d_ceil_div(M, kBqWarps * QW), B);
   ball_query_kernel<QW><<<grid, kBqWarps * 32, smem, st>>>(q, s, qm, vlen, M, N, radius, nsample, idx, idx_mask,
                                                           nvalid);
+  d3d_note_launches(1);
   return d3d_launch_status();
 }
 
@@ -227,6 +228,7 @@ size_t bq_smem_bytes(int qw, int nsample) {
 
 void d3d_launch_prefix_len(const int* mask, int B, int N, int* vlen, cudaStream_t st) {
   prefix_len_kernel<<<B, 256, 0, st>>>(mask, N, vlen);
+  d3d_note_launches(1);
 }
 
 extern "C" {
@@ -270,6 +272,7 @@ int d3d_nearest_query(const float* query_xyz, const float* support_xyz, const in
   d3d_launch_prefix_len(support_mask, B, N, vlen, st);
   dim3 grid(d3d_ceil_div(M, kNnThreads), B);
   nearest_query_kernel<<<grid, kNnThreads, 0, st>>>(query_xyz, support_xyz, query_mask, vlen, M, N, idx, idx_mask);
+  d3d_note_launches(1);
   return d3d_launch_status();
 }
 

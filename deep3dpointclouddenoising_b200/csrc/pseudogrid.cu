@@ -300,6 +300,7 @@ int d3d_pseudogrid_fwd(const float* feat_cl, const float* query_xyz, const float
   dim3 grid(d3d_ceil_div(M, kWarps), B);
   pseudogrid_fwd_kernel<<<grid, kWarps * 32, smem, st>>>(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask,
                                                          kpoints, weights, M, N, C, nsample, K, extent, influence, out_cl);
+  d3d_note_launches(1);
   return d3d_launch_status();
 }
 
@@ -327,6 +328,7 @@ int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const flo
     pseudogrid_bwd_feat_kernel<<<grid, kWarps * 32, 0, st>>>(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid,
                                                              query_mask, kpoints, weights, M, N, C, nsample, K, extent,
                                                              influence, grad_feat_cl);
+    d3d_note_launches(1);
   }
   if (grad_weights) {
     if (M == 0) return (int)cudaMemsetAsync(grad_weights, 0, (size_t)K * C * sizeof(float), st);
@@ -342,6 +344,7 @@ int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const flo
                                                                   nvalid, query_mask, kpoints, B, M, N, C, nsample, K,
                                                                   extent, influence, (float*)ws);
     reduce_partials_kernel<<<d3d_ceil_div((long long)K * C, 256), 256, 0, st>>>((const float*)ws, nblk, K, C, grad_weights);
+    d3d_note_launches(2);
   }
   return d3d_launch_status();
 }

@@ -37,6 +37,8 @@ extern "C" {
 int d3d_abi_version(void);
 /* Human-readable description of a return code (static storage). */
 const char* d3d_error_string(int code);
+/* Number of CUDA kernels this library has launched in this process (evidence for bench.py's gpu_launches). */
+long long d3d_kernel_launches(void);
 
 /* ------------------------------------------------------------------------------------------------
  * 1. Neighbourhood construction (bit-exact with the reference kernels)

@@ -102,7 +102,7 @@ def test_full_size_level0_against_oracle_subset_and_properties(cuda_device, orac
         dist = ((nb - pts[b][:, None, :]) ** 2).sum(-1)
         assert (dist[:, 0] == 0).all()
         valid = msk_h[b].astype(bool)
-        asc = (np.diff(dist, axis=1) >= -1e-12) | ~valid[:, 1:]
+        asc = (np.diff(dist, axis=1) >= -1e-9) | ~valid[:, 1:]  # numpy recomputes d2 without the fma: allow its rounding
         assert asc.all()
         assert (dist[valid] < radius * radius * (1 + 1e-5)).all()
     # determinism: a second launch gives the same bits
