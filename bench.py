@@ -284,33 +284,26 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    from deep3dpointclouddenoising_b200 import _lib, ops, synthetic
+    from deep3dpointclouddenoising_b200 import _lib, distributed, ops, synthetic
     from deep3dpointclouddenoising_b200.utils import config as cfgmod
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend="nccl", init_method="env://")
+    rank, world, local_rank = distributed.init("nccl")
     lib = _lib.load()
     cfgmod.runtime.pseudo_grid_precision = args.pseudo_grid_precision
 
     model, criterion, cfg = build_model(args.operator, args.num_points)
     model = model.to(dev)
-    if world > 1:  # the reference's data parallelism: DDP, NCCL gradient all-reduce (train_dist.py:375)
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
-    else:
-        net = model
+    net = distributed.wrap(model, local_rank)  # DDP + NCCL gradient all-reduce when world > 1 (train_dist.py:375)
     opt = torch.optim.Adam(model.parameters(), lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay)
     B, N = args.batch, args.num_points
 
     def host_batch(step):  # per-rank shard of the synthetic patch stream
-        arrs = synthetic.make_batch(1234 + 1000 * rank + step, B, N)
+        arrs = synthetic.make_batch(distributed.shard_seed(rank, step), B, N)
         return [torch.from_numpy(a).pin_memory() for a in arrs]
 
     def train_step(pts, mask, feats, offs):
@@ -322,9 +315,7 @@ def main():
         return loss
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        distributed.barrier(dev)
 
     n_host = 4
     host = [host_batch(s) for s in range(n_host)]
@@ -363,10 +354,7 @@ def main():
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
-    if world > 1:
-        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = tt.tolist()
+    ms, ms_e2e = distributed.max_over_ranks([ms, ms_e2e], dev)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
     # ---- instrumented pass: where the step's device time goes, and the roofline of the dominant kernel ----
@@ -399,12 +387,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         step_cpu, kind, how = cpu_step_fn(args.operator, N)
-        batch = synthetic.make_batch(4242, 1, N)
-        t = time.time()
-        step_cpu(batch)
+        t, n_cpu = time.time(), 0
+        while n_cpu < 64 and (time.time() - t < 12.0 or n_cpu < 2):  # ~10-30 s of CPU work
+            step_cpu(synthetic.make_batch(4242 + n_cpu, 1, N))
+            n_cpu += 1
         dt = time.time() - t
-        cpu_baseline = {"value": N / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": f"1 step of 1 x {N}-point patch fwd+bwd+Adam ({how}), {dt:.1f} s on {cores} host threads"}
+        cpu_baseline = {"value": n_cpu * N / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{n_cpu} steps of 1 x {N}-point patch fwd+bwd+Adam ({how}), {dt:.1f} s on {cores} host threads"}
 
     if rank == 0:
         pts_per_step = world * B * N

@@ -1,0 +1,54 @@
+"""Data parallelism of the training step: one process per GPU, patches sharded by rank, gradient all-reduce only.
+
+Mirrors what the reference does with torch.distributed.launch + DistributedDataParallel
+(u_net_arch/train_dist.py:375 `DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)`,
+:244 DistributedSampler, :502 init_process_group('nccl', 'env://')): BatchNorm statistics stay local, the only
+collective per step is the bucketed sum all-reduce of ~18.4 M fp32 gradients (73.7 MB), which NCCL runs over
+NVLink 5 / NVSwitch.  Patches are independent units, so there is no data-path collective.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend=None):
+    """env:// rendezvous (RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT); returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        dist.init_process_group(backend=backend, init_method="env://")
+    return rank, world, local_rank
+
+
+def shard_seed(rank, step, base=1234):
+    """Seed of the synthetic batch a rank draws at a step: disjoint streams per rank."""
+    return base + 1000 * rank + step
+
+
+def wrap(model, local_rank=None):
+    """DDP exactly as the reference configures it (no buffer broadcast: plain, per-rank BatchNorm)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return model
+    ids = [local_rank] if (local_rank is not None and next(model.parameters()).is_cuda) else None
+    return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False)
+
+
+def max_over_ranks(values, device):
+    """Element-wise maximum of a list of floats over all ranks (timings are reported as the slowest rank's)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(values)
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def barrier(device=None):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+    if device is not None and torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)

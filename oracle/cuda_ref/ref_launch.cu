@@ -4,6 +4,10 @@
  * masked_nearest_query_gpu.cu:71, group_points_gpu.cu:40,76).  All pointers are device pointers;
  * scratch must be zero-filled by the caller like the reference's torch::zeros. */
 extern "C" {
+/* The reference's in-kernel thrust::sort_by_key allocates its merge buffer from the device malloc heap; at the
+ * BASELINE size (16 x 8192 queries, 3*52 candidates each) the default 8 MB heap is exhausted and the reference
+ * kernel dies with "get_temporary_buffer failed".  The arbiter raises the limit before its first launch. */
+int ref_cuda_set_malloc_heap(size_t bytes) { return (int)cudaDeviceSetLimit(cudaLimitMallocHeapSize, bytes); }
 int ref_cuda_ball_query(int b, int n, int m, float radius, int nsample, const float* q, const float* s,
                         const int* qm, const int* sm, int* idx, int* idx_mask, float* dists, int* tempidxs,
                         cudaStream_t st) {

@@ -1,0 +1,58 @@
+"""CPU suite, part 4: the N>1 path on world_size-2 gloo — rendezvous, per-rank shards of the patch stream,
+DDP gradient averaging configured like the reference, max-over-ranks timing reduction."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from deep3dpointclouddenoising_b200 import distributed, synthetic
+    from deep3dpointclouddenoising_b200.models.heads import MultiDimHeadResNet
+    from deep3dpointclouddenoising_b200.models.losses import MaskedL1Loss
+    r, w, _ = distributed.init("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)  # same initial weights on every rank, like DDP's initial broadcast would give
+    head = MultiDimHeadResNet(3, 8, 0.025, [4, 4, 4, 4, 4])
+    block = torch.nn.Sequential(head.up_conv3, head.head)  # the CPU-runnable tail of the U-Net: conv/BN/ReLU -> 3 dims
+    net = distributed.wrap(block)
+    assert isinstance(net, torch.nn.parallel.DistributedDataParallel) and not net.broadcast_buffers
+    pts, mask, feats, offs = synthetic.make_batch(distributed.shard_seed(rank, 0), 2, 64)
+    x = torch.from_numpy(np.tile(feats, (1, 6, 1))[:, :16])  # (B, 2*width, N) stand-in for the concatenated features
+    loss = MaskedL1Loss()(net(x).transpose(1, 2), torch.from_numpy(offs), torch.from_numpy(mask))
+    loss.backward()
+    grads = torch.cat([p.grad.flatten() for p in block.parameters()])
+    # the same computation without DDP gives this rank's local gradient
+    torch.manual_seed(0)
+    head2 = MultiDimHeadResNet(3, 8, 0.025, [4, 4, 4, 4, 4])
+    block2 = torch.nn.Sequential(head2.up_conv3, head2.head)
+    MaskedL1Loss()(block2(x).transpose(1, 2), torch.from_numpy(offs), torch.from_numpy(mask)).backward()
+    local = torch.cat([p.grad.flatten() for p in block2.parameters()])
+    times = distributed.max_over_ranks([10.0 + rank, 5.0 - rank], "cpu")
+    distributed.barrier()
+    torch.save({"ddp": grads, "local": local, "times": times, "seed": distributed.shard_seed(rank, 0),
+                "points": torch.from_numpy(pts)}, os.path.join(out_dir, f"rank{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_and_sharding(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
+    assert torch.equal(r0["ddp"], r1["ddp"])  # every rank holds the same averaged gradient after the all-reduce
+    torch.testing.assert_close(r0["ddp"], (r0["local"] + r1["local"]) / 2, rtol=1e-5, atol=1e-7)
+    assert not torch.equal(r0["local"], r1["local"])  # the ranks really worked on different shards
+    assert r0["seed"] != r1["seed"] and not torch.equal(r0["points"], r1["points"])
+    assert r0["times"] == r1["times"] == [11.0, 5.0]  # max over ranks, element-wise
