@@ -15,12 +15,15 @@
 //     order (ties -> lower index first);
 //   * the <= 3*nsample candidates are ordered by warp-cooperative rank counting and written as
 //     coalesced rows.  No (B, M, 3*nsample) global scratch, no zero-fill.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int kBqWarps = 8;
-constexpr int kBqTile = 1024;  // supports per shared-memory tile
+// tuning knobs (overridable through the environment for experiments: D3D_BQ_WARPS in {4,8,16}, D3D_BQ_TILE)
+constexpr int kBqDefaultWarps = 16;  // measured on B200 (tools/bq_sweep.py): 16 warps x 2048-support tiles is the fastest of the sweep
+constexpr int kBqDefaultTile = 2048;  // supports staged per shared-memory tile
 
 __global__ void prefix_len_kernel(const int* __restrict__ mask, int N, int* __restrict__ vlen) {
   __shared__ int first_zero;
@@ -40,19 +43,30 @@ __device__ __forceinline__ unsigned long long make_key(float d2, int k) {
   return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)k;
 }
 
-template <int QW>
+// far-away filler for the unused tail of a tile: its squared distance overflows to +inf, which fails
+// every "d2 < something" test, so the scan loops need no bounds predicate
+constexpr float kFar = 1.0e30f;
+
+// Per query the scan is split in two passes over the shared-memory tile:
+//   fill pass : 32 supports per step, ballot + prefix popcount append the in-radius ones to the candidate list in
+//               ascending index order; stops as soon as the list holds 3*nsample entries (on the BASELINE patches
+//               after ~1/4 of the supports on average);
+//   min pass  : the reference's running (min_dist, min_idx) over ALL in-radius supports (:59-62), 4 queries at a
+//               time so that each support is read once per 4 queries: 6 FP ops + compare + 2 selects per pair.
+template <int QW, int kBqWarps>
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__ support_xyz,
-                  const int* __restrict__ query_mask, const int* __restrict__ vlen, int M, int N,
+                  const int* __restrict__ query_mask, const int* __restrict__ vlen, int M, int N, int tile,
                   float radius, int nsample, int* __restrict__ idx, int* __restrict__ idx_mask,
                   int* __restrict__ nvalid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = 3 * nsample;
   float* sx = reinterpret_cast<float*>(smem_raw);
-  float* sy = sx + kBqTile;
-  float* sz = sy + kBqTile;
-  unsigned long long* lists = reinterpret_cast<unsigned long long*>(sz + kBqTile);
+  float* sy = sx + tile;
+  float* sz = sy + tile;
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(sz + tile);
   int* sorted_all = reinterpret_cast<int*>(lists + (size_t)kBqWarps * QW * cap);
+  int* hist_all = sorted_all + (size_t)kBqWarps * QW * nsample;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -65,6 +79,7 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
   const float* S = support_xyz + (size_t)b * N * 3;
   unsigned long long* my_list = lists + (size_t)warp * QW * cap;
   int* my_sorted = sorted_all + (size_t)warp * QW * nsample;
+  int* my_hist = hist_all + warp * 32;
 
   float qx[QW], qy[QW], qz[QW], best[QW];
   int bestk[QW], cnt[QW];
@@ -72,37 +87,47 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
   for (int u = 0; u < QW; ++u) {
     const int j = min(q0 + u, M - 1);
     qx[u] = Q[3 * j + 0]; qy[u] = Q[3 * j + 1]; qz[u] = Q[3 * j + 2];
-    best[u] = r2; bestk[u] = 0; cnt[u] = 0;
+    best[u] = r2; bestk[u] = 0; cnt[u] = 0;  // :45-47
   }
 
-  for (int base = 0; base < v; base += kBqTile) {
+  for (int base = 0; base < v; base += tile) {
     __syncthreads();  // everyone is done with the previous tile
-    const int tile_n = min(kBqTile, v - base);
-    // coalesced flat copy of 3*tile_n floats, de-interleaved into SoA
-    for (int f = threadIdx.x; f < 3 * tile_n; f += blockDim.x) {
-      const float val = S[(size_t)base * 3 + f];
-      const int i = f / 3, c = f - 3 * i;
-      (c == 0 ? sx : (c == 1 ? sy : sz))[i] = val;
+    const int tile_n = min(tile, v - base);
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
+      float x = kFar, y = kFar, z = kFar;
+      if (i < tile_n) {
+        const float* p = S + (size_t)(base + i) * 3;
+        x = p[0]; y = p[1]; z = p[2];
+      }
+      sx[i] = x; sy[i] = y; sz[i] = z;
     }
     __syncthreads();
-    for (int i0 = 0; i0 < tile_n; i0 += 32) {
-      const int i = i0 + lane;
-      const bool in_tile = i < tile_n;
+    const int steps = (tile_n + 31) >> 5;
+    // ---- fill pass, one query at a time, until its list is full
+#pragma unroll
+    for (int u = 0; u < QW; ++u) {
+      for (int st = 0; st < steps && cnt[u] < cap; ++st) {
+        const int i = (st << 5) + lane;
+        const float d2 = d3d_dist2(qx[u], qy[u], qz[u], sx[i], sy[i], sz[i]);
+        const bool inr = d2 < r2;
+        const unsigned ball = __ballot_sync(D3D_FULL_MASK, inr);
+        if (ball) {
+          const int pos = cnt[u] + __popc(ball & lt_mask);
+          if (inr && pos < cap) my_list[u * cap + pos] = make_key(d2, base + i);
+          cnt[u] += __popc(ball);
+        }
+      }
+    }
+    // ---- min pass over the whole tile for all QW queries (strict <: earliest index per lane)
+#pragma unroll 2
+    for (int st = 0; st < steps; ++st) {
+      const int i = (st << 5) + lane;
       const int k = base + i;
-      const float x = sx[i], y = sy[i], z = sz[i];  // i < kBqTile always (tile is a multiple of 32)
+      const float x = sx[i], y = sy[i], z = sz[i];
 #pragma unroll
       for (int u = 0; u < QW; ++u) {
         const float d2 = d3d_dist2(qx[u], qy[u], qz[u], x, y, z);
-        const bool inr = in_tile && (d2 < r2);
-        if (inr && d2 < best[u]) { best[u] = d2; bestk[u] = k; }  // strict: earliest index per lane
-        const unsigned ball = __ballot_sync(D3D_FULL_MASK, inr);
-        if (ball) {
-          if (cnt[u] < cap) {
-            const int pos = cnt[u] + __popc(ball & lt_mask);
-            if (inr && pos < cap) my_list[u * cap + pos] = make_key(d2, k);
-          }
-          cnt[u] += __popc(ball);
-        }
+        if (d2 < best[u]) { best[u] = d2; bestk[u] = k; }  // best starts at r2: implies in-radius
       }
     }
   }
@@ -111,45 +136,77 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
   for (int u = 0; u < QW; ++u) {
     const int j = q0 + u;
     if (j >= M) break;  // warp-uniform
-    // global nearest in-radius support: min d2, lowest index among equal d2 (:59-62)
-    float bd = best[u];
-    int bk = bestk[u];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float od = __shfl_xor_sync(D3D_FULL_MASK, bd, off);
-      const int ok = __shfl_xor_sync(D3D_FULL_MASK, bk, off);
-      if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
-    }
     unsigned long long* list = my_list + u * cap;
     int* sorted = my_sorted + u * nsample;
     const int c = min(cnt[u], cap);
     __syncwarp();
-    if (lane == 0 && cnt[u] >= cap && cap > 0) {  // :72-75 nearest-swap into the last slot
-      const int last_k = (int)(unsigned)(list[cap - 1] & 0xffffffffull);
-      if (bk > last_k) list[cap - 1] = make_key(bd, bk);
+    if (cnt[u] >= cap) {
+      // global nearest in-radius support: min d2, lowest index among equal d2
+      float bd = best[u];
+      int bk = bestk[u];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float od = __shfl_xor_sync(D3D_FULL_MASK, bd, off);
+        const int ok = __shfl_xor_sync(D3D_FULL_MASK, bk, off);
+        if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+      }
+      // :72-75  it lies beyond the last slot -> it replaces the last slot
+      if (lane == 0 && bk > (int)(unsigned)(list[cap - 1] & 0xffffffffull)) list[cap - 1] = make_key(bd, bk);
+      __syncwarp();
     }
-    __syncwarp();
-    // rank counting: keys are unique, rank = number of smaller keys = position after the stable sort
-    for (int t0 = 0; t0 < c; t0 += 128) {
-      unsigned long long own[4];
-      int rank[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int t = t0 + e * 32 + lane;
-        own[e] = t < c ? list[t] : ~0ull;
-        rank[e] = 0;
+    // Pre-selection: only the nsample smallest keys are emitted.  d2 -> bin is monotone, so every key in a
+    // bin below B* is smaller than every key above it: rank only the keys of bins <= B*.
+    int n_rank = c;
+    if (c > nsample) {
+      my_hist[lane] = 0;
+      __syncwarp();
+      const float scale = 32.0f / r2;
+      for (int t = lane; t < c; t += 32) {
+        const int bin = min(31, (int)(__uint_as_float((unsigned)(list[t] >> 32)) * scale));
+        atomicAdd(&my_hist[bin], 1);
       }
+      __syncwarp();
+      int incl = my_hist[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const unsigned reach = __ballot_sync(D3D_FULL_MASK, incl >= nsample);
+      const int bstar = __ffs(reach) - 1;  // exists: incl[31] == c > nsample
+      n_rank = __shfl_sync(D3D_FULL_MASK, incl, bstar);
+      if (n_rank < c) {  // in-place left compaction, round by round (reads of a round precede its writes)
+        int kept = 0;
+        for (int t0 = 0; t0 < c; t0 += 32) {
+          const int t = t0 + lane;
+          unsigned long long key = 0;
+          bool keep = false;
+          if (t < c) {
+            key = list[t];
+            keep = min(31, (int)(__uint_as_float((unsigned)(key >> 32)) * scale)) <= bstar;
+          }
+          const unsigned kb = __ballot_sync(D3D_FULL_MASK, keep);
+          __syncwarp();
+          if (keep) list[kept + __popc(kb & lt_mask)] = key;
+          kept += __popc(kb);
+          __syncwarp();
+        }
+      }
+    }
+    // rank counting among the n_rank selected keys (unique): rank = number of smaller keys
+    for (int t0 = 0; t0 < n_rank; t0 += 64) {
+      const int ta = t0 + lane, tb = t0 + 32 + lane;
+      const unsigned long long own_a = ta < n_rank ? list[ta] : ~0ull;
+      const unsigned long long own_b = tb < n_rank ? list[tb] : ~0ull;
+      int ra = 0, rb = 0;
 #pragma unroll 4
-      for (int jj = 0; jj < c; ++jj) {
+      for (int jj = 0; jj < n_rank; ++jj) {
         const unsigned long long kj = list[jj];  // broadcast
-#pragma unroll
-        for (int e = 0; e < 4; ++e) rank[e] += (kj < own[e]) ? 1 : 0;
+        ra += (kj < own_a) ? 1 : 0;
+        rb += (kj < own_b) ? 1 : 0;
       }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int t = t0 + e * 32 + lane;
-        if (t < c && rank[e] < nsample) sorted[rank[e]] = (int)(unsigned)(own[e] & 0xffffffffull);
-      }
+      if (ta < n_rank && ra < nsample) sorted[ra] = (int)(unsigned)(own_a & 0xffffffffull);
+      if (tb < n_rank && rb < nsample) sorted[rb] = (int)(unsigned)(own_b & 0xffffffffull);
     }
     __syncwarp();
     const int qm = query_mask[(size_t)b * M + j];
@@ -206,22 +263,48 @@ nearest_query_kernel(const float* __restrict__ query_xyz, const float* __restric
   }
 }
 
-template <int QW>
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int bq_tile(int N) {
+  const int t = (N + 31) & ~31;
+  const int mx = (env_int("D3D_BQ_TILE", kBqDefaultTile) + 31) & ~31;
+  return t < mx ? t : mx;
+}
+
+size_t bq_smem_bytes(int warps, int qw, int nsample, int tile) {
+  return (size_t)3 * tile * sizeof(float) + (size_t)warps * qw * 3 * nsample * sizeof(unsigned long long) +
+         (size_t)warps * qw * nsample * sizeof(int) + (size_t)warps * 32 * sizeof(int);
+}
+
+template <int QW, int WARPS>
 int launch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, int B, int M, int N,
-                      float radius, int nsample, int* idx, int* idx_mask, int* nvalid, size_t smem,
-                      cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<QW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                      float radius, int nsample, int* idx, int* idx_mask, int* nvalid, cudaStream_t st) {
+  const int tile = bq_tile(N);
+  const size_t smem = bq_smem_bytes(WARPS, QW, nsample, tile);
+  cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<QW, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(d3d_ceil_div(M, kBqWarps * QW), B);
-  ball_query_kernel<QW><<<grid, kBqWarps * 32, smem, st>>>(q, s, qm, vlen, M, N, radius, nsample, idx, idx_mask,
-                                                          nvalid);
+  dim3 grid(d3d_ceil_div(M, WARPS * QW), B);
+  ball_query_kernel<QW, WARPS><<<grid, WARPS * 32, smem, st>>>(q, s, qm, vlen, M, N, tile, radius, nsample, idx,
+                                                             idx_mask, nvalid);
   d3d_note_launches(1);
   return d3d_launch_status();
 }
 
-size_t bq_smem_bytes(int qw, int nsample) {
-  return (size_t)3 * kBqTile * sizeof(float) + (size_t)kBqWarps * qw * 3 * nsample * sizeof(unsigned long long) +
-         (size_t)kBqWarps * qw * nsample * sizeof(int);
+template <int WARPS>
+int dispatch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, int B, int M, int N,
+                        float radius, int nsample, int* idx, int* idx_mask, int* nvalid, cudaStream_t st) {
+  const size_t budget = 220 * 1024;  // opt-in shared memory per block on sm_100a is 227 KB
+  const int tile = bq_tile(N);
+  if (bq_smem_bytes(WARPS, 4, nsample, tile) <= budget / 2)
+    return launch_ball_query<4, WARPS>(q, s, qm, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+  if (bq_smem_bytes(WARPS, 2, nsample, tile) <= budget / 2)
+    return launch_ball_query<2, WARPS>(q, s, qm, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+  if (bq_smem_bytes(WARPS, 1, nsample, tile) <= budget)
+    return launch_ball_query<1, WARPS>(q, s, qm, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+  return D3D_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -245,17 +328,11 @@ int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* 
   cudaStream_t st = (cudaStream_t)stream;
   int* vlen = (int*)ws;
   d3d_launch_prefix_len(support_mask, B, N, vlen, st);
-  const size_t budget = 100 * 1024;  // keep >= 2 blocks per SM
-  if (bq_smem_bytes(4, nsample) <= budget)
-    return launch_ball_query<4>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask,
-                                nvalid, bq_smem_bytes(4, nsample), st);
-  if (bq_smem_bytes(2, nsample) <= budget)
-    return launch_ball_query<2>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask,
-                                nvalid, bq_smem_bytes(2, nsample), st);
-  if (bq_smem_bytes(1, nsample) <= 200 * 1024)
-    return launch_ball_query<1>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask,
-                                nvalid, bq_smem_bytes(1, nsample), st);
-  return D3D_ERR_UNSUPPORTED;
+  switch (env_int("D3D_BQ_WARPS", kBqDefaultWarps)) {
+    case 4: return dispatch_ball_query<4>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    case 16: return dispatch_ball_query<16>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    default: return dispatch_ball_query<8>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+  }
 }
 
 size_t d3d_nearest_query_workspace_bytes(int B) { return (size_t)(B > 0 ? B : 0) * sizeof(int); }
