@@ -358,13 +358,15 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
     # ---- instrumented pass: where the step's device time goes, and the roofline of the dominant kernel ----
+    # (every rank runs these steps — they contain the gradient all-reduce — only rank 0 reports them)
     kernels, roofline = None, None
+    n_inst = 3
+    with OpTimer(ops) as timer:
+        for s in range(n_inst):
+            train_step(*resident[s % n_host])
+        per = timer.summary(n_inst)
+    barrier()
     if rank == 0:
-        n_inst = 3
-        with OpTimer(ops) as timer:
-            for s in range(n_inst):
-                train_step(*resident[s % n_host])
-            per = timer.summary(n_inst)
         step_ms = ms / args.steps
         kernels = {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / n_inst,
                        "gbs": round(v["bytes_per_call"] / 1e6 / v["ms_per_call"], 1) if v["ms_per_call"] > 0 else None}

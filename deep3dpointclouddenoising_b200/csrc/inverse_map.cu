@@ -7,9 +7,14 @@
 // (query, slot) order, and every backward kernel reduces its segment sequentially: no float atomics,
 // bit-reproducible gradients.
 //
-// Build: integer histogram -> per-cloud exclusive scan -> cursor fill (integer atomics; the order
-// inside a segment is arbitrary at this point) -> per-segment sort (a warp for short segments, a
-// block-wide bitonic network for long ones).  Entries are (query << 8) | slot.
+// Entries are (query << 8) | slot.  Two builders:
+//   chunked (default, N <= kChunkMaxN): every cloud's entry list is cut into <= 16 chunks; a block
+//     histograms its chunk in SHARED memory and writes one row of a (cloud, chunk, support) count matrix;
+//     a scan turns the matrix into rowptr and per-(chunk, support) write cursors; the fill pass hands out
+//     slots with shared-memory atomics.  No global atomics; a segment comes out as <= 16 pieces in chunk
+//     order, each piece (a few entries) is then rank-sorted by a warp.
+//   global (fallback for very large N): global integer histogram -> scan -> cursor fill -> per-segment
+//     sort (a warp for short segments, a block-wide bitonic network for long ones).
 #include "common.cuh"
 
 namespace {
@@ -138,6 +143,133 @@ sort_long_kernel(const int* __restrict__ rowptr, const int* __restrict__ long_ro
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// chunked builder
+// ---------------------------------------------------------------------------------------------------
+constexpr int kChunkMaxN = 49152;  // N ints of shared memory per block (192 KB)
+constexpr int kMaxChunks = 16;
+
+// block = (chunk, cloud): histogram of idx[b, chunk range] over supports, written as one matrix row
+__global__ void __launch_bounds__(512)
+chunk_count_kernel(const int* __restrict__ idx, int P, int N, int n_chunks, int chunk_len, int* __restrict__ matrix) {
+  extern __shared__ int hist[];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int beg = chunk * chunk_len, end = min(beg + chunk_len, P);
+  const int* src = idx + (size_t)b * P;
+  for (int e = beg + threadIdx.x; e < end; e += blockDim.x) atomicAdd(&hist[d3d_clamp_index(src[e], N)], 1);
+  __syncthreads();
+  int* row = matrix + ((size_t)b * n_chunks + chunk) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) row[i] = hist[i];
+}
+
+// block per cloud: counts -> rowptr, and the matrix is rewritten in place as write cursors
+__global__ void __launch_bounds__(1024)
+chunk_scan_kernel(int* __restrict__ matrix, int N, int P, int B, int n_chunks, int* __restrict__ rowptr) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* mat = matrix + (size_t)b * n_chunks * N;
+  int* rp = rowptr + (size_t)b * N;
+  if (tid == 0) carry = b * P;
+  __syncthreads();
+  for (int base = 0; base < N; base += 1024) {
+    const int i = base + tid;
+    int c = 0;
+    if (i < N)
+      for (int ch = 0; ch < n_chunks; ++ch) c += mat[(size_t)ch * N + i];
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_tot[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(D3D_FULL_MASK, wi, o);
+        if (lane >= o) wi += up;
+      }
+      warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const int excl = carry + warp_tot[warp] + incl - c;
+    if (i < N) {
+      rp[i] = excl;
+      int run = excl;
+      for (int ch = 0; ch < n_chunks; ++ch) {  // chunk ch writes its entries of support i from here on
+        const int k = mat[(size_t)ch * N + i];
+        mat[(size_t)ch * N + i] = run;
+        run += k;
+      }
+    }
+    __syncthreads();
+    if (tid == 1023) carry = excl + c;
+    __syncthreads();
+  }
+  if (b == B - 1 && tid == 0) rowptr[(size_t)B * N] = B * P;
+}
+
+__global__ void __launch_bounds__(512)
+chunk_fill_kernel(const int* __restrict__ idx, int P, int N, int nsample, int n_chunks, int chunk_len,
+                  const int* __restrict__ matrix, int* __restrict__ unsorted) {
+  extern __shared__ int cursor[];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int* row = matrix + ((size_t)b * n_chunks + chunk) * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) cursor[i] = row[i];
+  __syncthreads();
+  const int beg = chunk * chunk_len, end = min(beg + chunk_len, P);
+  const int* src = idx + (size_t)b * P;
+  for (int e = beg + threadIdx.x; e < end; e += blockDim.x) {
+    const int pos = atomicAdd(&cursor[d3d_clamp_index(src[e], N)], 1);
+    const int j = e / nsample;
+    unsorted[pos] = (j << 8) | (e - j * nsample);
+  }
+}
+
+// warp per support: its segment is n_chunks pieces (already in chunk order); rank-sort each piece
+__global__ void __launch_bounds__(256)
+chunk_sort_kernel(const int* __restrict__ rowptr, const int* __restrict__ matrix, int B, int N, int n_chunks,
+                  const int* __restrict__ unsorted, int* __restrict__ entries) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= (long long)B * N) return;
+  const int b = (int)(row / N), i = (int)(row - (long long)b * N);
+  const int seg_end = rowptr[row + 1];
+  const int* mat = matrix + (size_t)b * n_chunks * N + i;
+  int beg = rowptr[row];
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int end = ch + 1 < n_chunks ? mat[(size_t)(ch + 1) * N] : seg_end;  // cursor start of the next piece
+    const int len = end - beg;
+    if (len <= 64) {
+      const int own0 = lane < len ? unsorted[beg + lane] : 0x7fffffff;
+      const int own1 = lane + 32 < len ? unsorted[beg + lane + 32] : 0x7fffffff;
+      int r0 = 0, r1 = 0;
+      for (int t = 0; t < len; ++t) {  // entries are unique -> rank = number of smaller entries
+        const int other = t < 32 ? __shfl_sync(D3D_FULL_MASK, own0, t) : __shfl_sync(D3D_FULL_MASK, own1, t - 32);
+        r0 += other < own0 ? 1 : 0;
+        r1 += other < own1 ? 1 : 0;
+      }
+      if (lane < len) entries[beg + r0] = own0;
+      if (lane + 32 < len) entries[beg + r1] = own1;
+    } else {
+      for (int t = lane; t < len; t += 32) {  // rare: out-of-place rank counting straight from L1/L2
+        const int own = unsorted[beg + t];
+        int r = 0;
+        for (int u = 0; u < len; ++u) r += unsorted[beg + u] < own ? 1 : 0;
+        entries[beg + r] = own;
+      }
+    }
+    beg = end;
+  }
+}
+
 struct InvWs {
   int* cursor;
   int* unsorted;
@@ -163,7 +295,9 @@ extern "C" {
 
 size_t d3d_inverse_map_workspace_bytes(int B, int N, int M, int nsample) {
   if (B <= 0 || N <= 0 || M <= 0 || nsample <= 0) return 0;
-  return 2 * align256((size_t)B * N * sizeof(int)) + align256((size_t)B * M * nsample * sizeof(int)) + 256;
+  const size_t global_path = 2 * align256((size_t)B * N * sizeof(int)) + align256((size_t)B * M * nsample * sizeof(int)) + 256;
+  const size_t chunk_path = align256((size_t)B * kMaxChunks * N * sizeof(int)) + align256((size_t)B * M * nsample * sizeof(int));
+  return global_path > chunk_path ? global_path : chunk_path;
 }
 
 int d3d_build_inverse_map(const int* idx, int B, int N, int M, int nsample, int* rowptr, int* entries, void* ws,
@@ -175,8 +309,26 @@ int d3d_build_inverse_map(const int* idx, int B, int N, int M, int nsample, int*
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0) return 0;
   if (!ws || ws_bytes < d3d_inverse_map_workspace_bytes(B, N, M, nsample)) return D3D_ERR_WORKSPACE;
-  InvWs w = carve(ws, B, N, M, nsample);
   const int P = M * nsample;
+  if (N <= kChunkMaxN && total > 0) {
+    int n_chunks = (P + 8191) / 8192;
+    if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
+    const int chunk_len = (P + n_chunks - 1) / n_chunks;
+    int* matrix = (int*)ws;
+    int* unsorted = (int*)((unsigned char*)ws + align256((size_t)B * kMaxChunks * N * sizeof(int)));
+    const size_t smem = (size_t)N * sizeof(int);
+    cudaError_t e1 = cudaFuncSetAttribute(chunk_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(chunk_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess) return (int)e1;
+    dim3 grid(n_chunks, B);
+    chunk_count_kernel<<<grid, 512, smem, st>>>(idx, P, N, n_chunks, chunk_len, matrix);
+    chunk_scan_kernel<<<B, 1024, 0, st>>>(matrix, N, P, B, n_chunks, rowptr);
+    chunk_fill_kernel<<<grid, 512, smem, st>>>(idx, P, N, nsample, n_chunks, chunk_len, matrix, unsorted);
+    chunk_sort_kernel<<<d3d_ceil_div((long long)B * N * 32, 256), 256, 0, st>>>(rowptr, matrix, B, N, n_chunks, unsorted, entries);
+    d3d_note_launches(4);
+    return d3d_launch_status();
+  }
+  InvWs w = carve(ws, B, N, M, nsample);
   cudaError_t e = cudaMemsetAsync(w.cursor, 0, (size_t)B * N * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(w.long_count, 0, sizeof(int), st);

@@ -159,3 +159,34 @@ def test_backward_is_deterministic(cuda_device):
         y = fused.PosPoolFunction.apply(f, dx, dx, dm, nbr, 0.025, 'avg')
         grads.append(torch.autograd.grad(y, f, g)[0])
     assert torch.equal(grads[0], grads[1])
+
+
+@pytest.mark.parametrize("C,N,M,ns,radius", [(72, 2048, 2048, 52, 0.025), (144, 2048, 512, 39, 0.03), (288, 512, 512, 32, 0.05),
+                                             (1152, 64, 64, 26, 0.4), (12, 300, 300, 7, 0.02), (72, 512, 512, 16, 0.02)])
+def test_pseudogrid_tensor_core_path(cuda_device, oracle, C, N, M, ns, radius):
+    """tcgen05 bf16 contraction (precision=1): W and the influence weights are rounded to bf16 (relative 2^-9),
+    features and accumulation stay fp32.  Stated tolerance: max abs error <= 2e-2 * max|out|, relative Frobenius
+    error <= 5e-3 — checked against the fp32 CUDA-core path, itself pinned to the reference within 1e-5."""
+    from deep3dpointclouddenoising_b200 import neighbors, ops
+    B = 2
+    pts, mask, _, _ = synthetic.make_batch(600 + C + ns, B, N, ragged=True)
+    if M == N:
+        q, qm = pts, mask
+    else:
+        q, qm = oracle.grid_subsampling(pts, mask, M, 0.05 / 32 * (N / M) ** 0.5)
+    rng = np.random.default_rng(C + ns)
+    f = dev(rng.standard_normal((B, N, C)).astype(np.float32), cuda_device)  # channel-last
+    kp = dev((rng.standard_normal((15, 3)) * 0.4 * radius).astype(np.float32), cuda_device)
+    w = dev((rng.standard_normal((15, C)) * 0.2).astype(np.float32), cuda_device)
+    dq, ds, dqm, dsm = dev(q, cuda_device), dev(pts, cuda_device), dev(qm, cuda_device), dev(mask, cuda_device)
+    neighbors.cache.clear()
+    nbr = neighbors.ball_neighbors(dq, ds, dqm, dsm, radius, ns)
+    ref = ops.pseudogrid_fwd(f, dq, ds, nbr.idx, nbr.nvalid, dqm, kp, w, 0.4 * radius, 'linear', 0)
+    out = ops.pseudogrid_fwd(f, dq, ds, nbr.idx, nbr.nvalid, dqm, kp, w, 0.4 * radius, 'linear', 1)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    rel_fro = ((out - ref).norm() / ref.norm()).item()
+    assert err <= 2e-2 * scale, (err, scale)
+    assert rel_fro <= 5e-3, rel_fro
+    assert torch.equal(out, ops.pseudogrid_fwd(f, dq, ds, nbr.idx, nbr.nvalid, dqm, kp, w, 0.4 * radius, 'linear', 1))
