@@ -35,7 +35,7 @@ SIGNATURES = {
     "d3d_pospool_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "d3d_pseudogrid_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _i, _vp, _vp]),
     "d3d_pseudogrid_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "d3d_pseudogrid_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_f, _i, _vp, _vp, _vp, _sz, _vp]),
+    "d3d_pseudogrid_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "d3d_gather_max_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "d3d_gather_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "d3d_nearest_gather_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

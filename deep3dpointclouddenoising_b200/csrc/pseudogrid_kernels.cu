@@ -1,0 +1,486 @@
+// PseudoGrid (depthwise KPConv-style) aggregation kernels: forward, gradient w.r.t. features, gradient w.r.t.
+// kernel weights — each with the kernel-point contraction either on CUDA cores (fp32) or on the 5th-generation
+// tensor cores (tcgen05 + TMEM, bf16 operands, fp32 accumulate).
+//
+//   ref: u_net_arch/models/local_aggregation_operators.py:467-503
+//   w[j,m,k]    = influence(|| (S[idx[j,m]] - Q[j]) - K[k] ||) * fm[j,m]
+//   out[j,c]    = sum_m F[idx[j,m], c] * E[c,(j,m)],          E[c,(j,m)] = sum_k W[k,c] * w[j,m,k]
+//   dF[i,c]     = sum_{(j,m) in inverse map of i} g[j,c] * E[c,(j,m)]
+//   dW[k,c]     = sum_{j,m} w[j,m,k] * F[idx[j,m], c] * g[j,c]
+//
+// One thread owns ONE channel: the 32 lanes of a warp read 32 consecutive channels of the same gathered row (one
+// coalesced 128-byte request per neighbour, many requests in flight per thread), and every reduction over
+// neighbours happens in that thread's registers — no cross-thread reduction anywhere.
+//
+// E is a dense GEMM  E^T[C x items] = W^T[C x 16] . w^T[16 x items]  (K = 15 kernel points padded to 16 = exactly one
+// tcgen05.mma K-step for bf16).  Tensor-core mapping: MMA M (TMEM lanes) = 128 channels (A operand = W^T tile,
+// staged once per CTA), MMA N (TMEM columns) = up to 64.. 256 items (B operand = influence weights), accumulator
+// lane = channel, column = item — so after tcgen05.ld a thread holds E for its own channel and all items.
+// Operand layout: K-major, no swizzle (8-row x 16-byte core matrices, K chunks LBO = 128 B apart, row groups
+// SBO = 256 B apart).  Features/gradients stay fp32; only W and the influence weights are rounded to bf16.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;     // 4 warps = the 4 TMEM lane quarters; 128 channels per channel tile
+constexpr int kRowsPerCta = 8;    // rows (queries / supports) processed one after the other by a CTA
+constexpr int kMaxCTiles = 9;     // 9 x 128 = 1152 channels
+constexpr int kTileBytes = 128 * 32;
+constexpr unsigned kLbo = 128, kSbo = 256;
+constexpr int kK = 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ unsigned operand_offset(int row, int k) {
+  return (unsigned)((row >> 3) * kSbo + (k >> 3) * kLbo + (row & 7) * 16 + (k & 7) * 2);
+}
+
+__device__ __forceinline__ unsigned long long make_smem_desc(unsigned addr) {
+  return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)(kLbo >> 4) << 16) |
+         ((unsigned long long)(kSbo >> 4) << 32) | (1ull << 46);  // version 1 (sm_100), layout type 0 = no swizzle
+}
+
+// coef = 1/extent (linear) or -1/(2 sigma^2 + 1e-9), sigma = 0.3 extent (gaussian); multiplying by the reciprocal
+// instead of dividing moves the result by <= 1 ulp of the quotient, far inside the stated fp32 tolerance
+template <int kInfluence>
+__device__ __forceinline__ float influence_weight(float dx, float dy, float dz, float coef) {
+  const float sq = dx * dx + dy * dy + dz * dz;
+  if (kInfluence == D3D_KP_LINEAR) return fmaxf(1.0f - sqrtf(sq) * coef, 0.0f);  // :480
+  if (kInfluence == D3D_KP_GAUSSIAN) return __expf(sq * coef);                   // :484, models/utlis.py:287-294
+  return 1.0f;                                                                   // constant (:476)
+}
+
+__host__ __device__ inline float influence_coef(float extent, int influence) {
+  if (influence == D3D_KP_GAUSSIAN) {
+    const float sigma = extent * 0.3f;
+    return -1.0f / (2.0f * sigma * sigma + 1e-9f);
+  }
+  return 1.0f / extent;
+}
+
+// stage 2 of a piece: influence weight of every (item, kernel point); srow < 0 marks a masked item
+template <int kInfluence, bool kTensorCore>
+__device__ __forceinline__ void stage_weights(int tid, int pmax, int K, const int* srow, const float* srel,
+                                              const float* kp, float coef, unsigned char* b_tile, float* w_f32) {
+  const int k = tid & 15;  // 128 threads: the kernel point of a thread never changes
+  const float kx = kp[3 * k], ky = kp[3 * k + 1], kz = kp[3 * k + 2];
+  for (int t = tid; t < pmax * 16; t += 128) {
+    const int p = t >> 4;
+    float w = 0.0f;
+    if (k < K && srow[p] >= 0) w = influence_weight<kInfluence>(srel[3 * p] - kx, srel[3 * p + 1] - ky, srel[3 * p + 2] - kz, coef);
+    if (kTensorCore)
+      *reinterpret_cast<__nv_bfloat16*>(b_tile + operand_offset(p, k)) = __float2bfloat16_rn(w);
+    else
+      w_f32[t] = w;
+  }
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+struct Args {
+  const float* src;          // rows that are gathered: features (forward) or grad_out (backward), channel-last
+  const float* query_xyz;    // (B, M, 3)
+  const float* support_xyz;  // (B, N, 3)
+  const int* idx;            // (B, M, ns)          forward
+  const int* rowptr;         // inverse map         backward
+  const int* entries;
+  const int* nvalid;         // (B, M)
+  const int* query_mask;     // (B, M)
+  const float* kpoints;      // (K, 3)
+  const float* weights;      // (K, C)
+  float* out;                // (B, rows, C)
+  int M, N, C, nsample, K, influence;
+  float extent;
+  int n_items_max;  // items staged per piece (multiple of 16, <= 256)
+  int tmem_cols;
+};
+
+// kBackward: rows are support points and items are inverse-map entries; else rows are queries, items are slots.
+// kTensorCore: E from tcgen05.mma into TMEM; else 16 fp32 FMAs per (item, channel) against W in registers.
+// Per-row latency chain (stage -> MMA -> TMEM load -> gathers) is what bounds this kernel, so it is tuned for many
+// resident CTAs (8 per SM: <= 64 registers, 64 TMEM columns) and the next row's index/coordinate loads are issued
+// before the current row's gathers are consumed.
+template <bool kBackward, bool kTensorCore>
+__global__ void __launch_bounds__(kThreads, 8)
+pseudogrid_rows_kernel(const Args a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ unsigned tmem_base_slot;
+  __shared__ float kp[48];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const int C = a.C, K = a.K;
+  const int n_ctile = (C + 127) >> 7;
+  const int n_rows = kBackward ? a.N : a.M;
+  const int pmax = a.n_items_max;
+  // shared-memory carve-up
+  unsigned char* a_tiles = smem;                                                      // tensor core: n_ctile x 4 KB
+  unsigned char* b_tile = a_tiles + (kTensorCore ? (size_t)n_ctile * kTileBytes : 0);  // tc: pmax x 32 B bf16
+  float* w_f32 = reinterpret_cast<float*>(b_tile);                                    // fp32: pmax x 16 floats
+  int* srow = reinterpret_cast<int*>(b_tile + (kTensorCore ? (size_t)pmax * 32 : (size_t)pmax * 64));
+  float* srel = reinterpret_cast<float*>(srow + pmax);  // pmax x 3
+
+  unsigned tmem_base = 0, bar = 0, phase = 0, idesc = 0;
+  unsigned long long b_desc = 0;
+  if (kTensorCore) {
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"((unsigned)a.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int e = tid; e < n_ctile * 128 * 16; e += kThreads) {
+      const int ct = e >> 11, k = (e >> 7) & 15, cl = e & 127;  // consecutive threads -> consecutive channels
+      const int c = ct * 128 + cl;
+      const float w = (c < C && k < K) ? a.weights[(size_t)k * C + c] : 0.0f;
+      *reinterpret_cast<__nv_bfloat16*>(a_tiles + (size_t)ct * kTileBytes + operand_offset(cl, k)) = __float2bfloat16_rn(w);
+    }
+  }
+  if (tid < K * 3) kp[tid] = a.kpoints[tid];
+  if (kTensorCore) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (kTensorCore) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = tmem_base_slot;
+    bar = smem_u32(&mbar);
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = pmax, M = 128
+    idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(pmax >> 3) << 17) | ((128u >> 4) << 24);
+    b_desc = make_smem_desc(smem_u32(b_tile));
+  }
+  const float* src_b = a.src + (size_t)b * (kBackward ? a.M : a.N) * C;
+  const float coef = influence_coef(a.extent, a.influence);
+
+  for (int ri = 0; ri < kRowsPerCta; ++ri) {
+    const int row = blockIdx.x * kRowsPerCta + ri;
+    if (row >= n_rows) break;  // block-uniform
+    const size_t grow = (size_t)b * n_rows + row;
+    int item_beg = 0, n_items = 0;
+    float rx, ry, rz;  // the row's own coordinates
+    if (kBackward) {
+      item_beg = a.rowptr[grow];
+      n_items = a.rowptr[grow + 1] - item_beg;
+      rx = a.support_xyz[grow * 3]; ry = a.support_xyz[grow * 3 + 1]; rz = a.support_xyz[grow * 3 + 2];
+    } else {
+      n_items = a.query_mask[grow] != 0 ? a.nvalid[grow] : a.nsample;  // fm: padded query uses every slot (:490)
+      rx = a.query_xyz[grow * 3]; ry = a.query_xyz[grow * 3 + 1]; rz = a.query_xyz[grow * 3 + 2];
+    }
+    float acc[kMaxCTiles];
+#pragma unroll
+    for (int ct = 0; ct < kMaxCTiles; ++ct) acc[ct] = 0.0f;
+
+    for (int p0 = 0; p0 < n_items; p0 += pmax) {
+      const int np = min(pmax, n_items - p0);
+      // ---- stage 1: which row each item gathers, and its relative position
+      for (int p = tid; p < pmax; p += kThreads) {
+        int g = -1;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (p < np) {
+          if (kBackward) {
+            const int e = a.entries[item_beg + p0 + p];
+            const int j = e >> 8, m = e & 255;
+            const size_t qrow = (size_t)b * a.M + j;
+            const int n_eff = a.query_mask[qrow] != 0 ? a.nvalid[qrow] : a.nsample;
+            if (m < n_eff) {
+              g = j;
+              dx = rx - a.query_xyz[qrow * 3]; dy = ry - a.query_xyz[qrow * 3 + 1]; dz = rz - a.query_xyz[qrow * 3 + 2];
+            }
+          } else {
+            g = d3d_clamp_index(a.idx[grow * a.nsample + p0 + p], a.N);
+            const float* s = a.support_xyz + ((size_t)b * a.N + g) * 3;
+            dx = s[0] - rx; dy = s[1] - ry; dz = s[2] - rz;
+          }
+        }
+        srow[p] = g;
+        srel[3 * p] = dx; srel[3 * p + 1] = dy; srel[3 * p + 2] = dz;
+      }
+      __syncthreads();
+      // ---- stage 2: influence weights of (item, kernel point)
+      if (a.influence == D3D_KP_LINEAR) stage_weights<D3D_KP_LINEAR, kTensorCore>(tid, pmax, K, srow, srel, kp, coef, b_tile, w_f32);
+      else if (a.influence == D3D_KP_GAUSSIAN) stage_weights<D3D_KP_GAUSSIAN, kTensorCore>(tid, pmax, K, srow, srel, kp, coef, b_tile, w_f32);
+      else stage_weights<D3D_KP_CONSTANT, kTensorCore>(tid, pmax, K, srow, srel, kp, coef, b_tile, w_f32);
+      __syncthreads();
+      // gather offsets replace the row numbers (masked items read row 0 with weight 0)
+      for (int p = tid; p < pmax; p += kThreads) srow[p] = srow[p] >= 0 ? srow[p] * C : 0;
+      if (kTensorCore) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      }
+      __syncthreads();
+
+#pragma unroll
+      for (int ct = 0; ct < kMaxCTiles; ++ct) {
+        if (ct >= n_ctile) break;
+        const int c = ct * 128 + tid;
+        const bool active = c < C;
+        const float* sc = src_b + (active ? c : 0);
+        float sum = 0.0f;
+        if (kTensorCore) {
+          if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned long long a_desc = make_smem_desc(smem_u32(a_tiles + (size_t)ct * kTileBytes));
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                "}\n" ::"r"(tmem_base), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(0u) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+          }
+          mbar_wait(bar, phase);
+          phase ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int col0 = 0; col0 < np; col0 += 16) {
+            unsigned r[16];
+            const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)col0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            // (tcgen05.ld / wait::ld are .sync.aligned: every lane of the warp executes them, outside any
+            //  lane-divergent branch; only the gathers are predicated on the lane's channel being real)
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)  // all gathers of the chunk are issued before the first use; columns >= np
+              x[i] = active ? __ldg(sc + srow[col0 + i]) : 0.0f;  // have E = 0 and offset 0 (chunk stays inside pmax)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum += x[i] * __uint_as_float(r[i]);
+          }
+          // every warp is done reading TMEM before the next MMA overwrites it
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncthreads();
+        } else if (active) {
+          float W[kK];
+#pragma unroll
+          for (int k = 0; k < kK; ++k) W[k] = k < K ? __ldg(a.weights + (size_t)k * C + c) : 0.0f;
+          for (int q0 = 0; q0 < np; q0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __ldg(sc + srow[q0 + i]);  // q0 + i < pmax: offset 0 / weight 0 beyond np
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              {
+                const float4* wp = reinterpret_cast<const float4*>(w_f32 + (q0 + i) * kK);  // broadcast reads
+                float e = 0.0f;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  const float4 w = wp[k4];
+                  e += w.x * W[4 * k4] + w.y * W[4 * k4 + 1] + w.z * W[4 * k4 + 2] + w.w * W[4 * k4 + 3];
+                }
+                sum += x[i] * e;
+              }
+            }
+          }
+        }
+        acc[ct] += sum;
+      }
+      if (!kTensorCore) __syncthreads();  // the staging buffers are rewritten by the next piece / row
+    }
+#pragma unroll
+    for (int ct = 0; ct < kMaxCTiles; ++ct) {
+      const int c = ct * 128 + tid;
+      if (ct < n_ctile && c < C) a.out[grow * C + c] = acc[ct];
+    }
+  }
+
+  if (kTensorCore) {
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)a.tmem_cols) : "memory");
+  }
+}
+
+// dW partials (fp32, CUDA cores): grid (channel tiles, nblk); thread = channel, 16 accumulators in registers.
+__global__ void __launch_bounds__(kThreads)
+pseudogrid_weight_grad_kernel(const float* __restrict__ grad_out, const float* __restrict__ feat,
+                              const float* __restrict__ query_xyz, const float* __restrict__ support_xyz,
+                              const int* __restrict__ idx, const int* __restrict__ nvalid,
+                              const int* __restrict__ query_mask, const float* __restrict__ kpoints, int B, int M, int N,
+                              int C, int nsample, int K, float extent, int influence,
+                              float* __restrict__ partial /* (gridDim.y, 16, C) */) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ float kp[48];
+  const int pm = (nsample + 7) & ~7;
+  float* w_f32 = reinterpret_cast<float*>(smem);        // pm x 16
+  int* srow = reinterpret_cast<int*>(w_f32 + pm * kK);  // pm
+  float* srel = reinterpret_cast<float*>(srow + pm);    // pm x 3
+  const int tid = threadIdx.x;
+  if (tid < K * 3) kp[tid] = kpoints[tid];
+  const int c = blockIdx.x * 128 + tid;
+  const bool active = c < C;
+  float acc[kK];
+#pragma unroll
+  for (int k = 0; k < kK; ++k) acc[k] = 0.0f;
+  const long long total = (long long)B * M;
+  const float coef = influence_coef(extent, influence);
+  const int pmax = (nsample + 7) & ~7;
+  for (long long qi = blockIdx.y; qi < total; qi += gridDim.y) {
+    const int b = (int)(qi / M);
+    const int n_eff = query_mask[qi] != 0 ? nvalid[qi] : nsample;
+    const float qx = query_xyz[qi * 3], qy = query_xyz[qi * 3 + 1], qz = query_xyz[qi * 3 + 2];
+    __syncthreads();  // previous query fully consumed
+    for (int p = tid; p < pmax; p += kThreads) {
+      int g = -1;
+      float dx = 0.f, dy = 0.f, dz = 0.f;
+      if (p < n_eff) {
+        g = d3d_clamp_index(idx[qi * nsample + p], N);
+        const float* s = support_xyz + ((size_t)b * N + g) * 3;
+        dx = s[0] - qx; dy = s[1] - qy; dz = s[2] - qz;
+      }
+      srow[p] = g;
+      srel[3 * p] = dx; srel[3 * p + 1] = dy; srel[3 * p + 2] = dz;
+    }
+    __syncthreads();
+    if (influence == D3D_KP_LINEAR) stage_weights<D3D_KP_LINEAR, false>(tid, pmax, K, srow, srel, kp, coef, nullptr, w_f32);
+    else if (influence == D3D_KP_GAUSSIAN) stage_weights<D3D_KP_GAUSSIAN, false>(tid, pmax, K, srow, srel, kp, coef, nullptr, w_f32);
+    else stage_weights<D3D_KP_CONSTANT, false>(tid, pmax, K, srow, srel, kp, coef, nullptr, w_f32);
+    __syncthreads();
+    for (int p = tid; p < pmax; p += kThreads) srow[p] = srow[p] >= 0 ? srow[p] * C : 0;
+    __syncthreads();
+    if (active) {
+      const float g = __ldg(grad_out + (size_t)qi * C + c);
+      const float* fc = feat + (size_t)b * N * C + c;
+      for (int q0 = 0; q0 < n_eff; q0 += 8) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ldg(fc + srow[q0 + i]) * g;  // masked tail: weight 0, offset 0
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4* wp = reinterpret_cast<const float4*>(w_f32 + (q0 + i) * kK);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 w = wp[k4];
+            acc[4 * k4] += w.x * x[i]; acc[4 * k4 + 1] += w.y * x[i]; acc[4 * k4 + 2] += w.z * x[i]; acc[4 * k4 + 3] += w.w * x[i];
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kK; ++k) partial[((size_t)blockIdx.y * kK + k) * C + c] = acc[k];
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblk, int K, int C,
+                                       float* __restrict__ grad_weights) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= K * C) return;
+  const int k = t / C, c = t - k * C;
+  float s = 0.0f;
+  for (int blk = 0; blk < nblk; ++blk) s += partial[((size_t)blk * kK + k) * C + c];  // fixed order: deterministic
+  grad_weights[t] = s;
+}
+
+int weight_blocks(int B, int M, int C) {
+  const long long q = (long long)B * M;
+  const int n_ctile = (C + 127) / 128;
+  long long blk = (148 * 12) / n_ctile;
+  if (blk > q) blk = q;
+  return (int)(blk < 1 ? 1 : blk);
+}
+
+template <bool kBackward, bool kTensorCore>
+int launch_rows(Args a, int B, cudaStream_t st) {
+  const int n_ctile = (a.C + 127) / 128;
+  if (n_ctile > kMaxCTiles) return D3D_ERR_UNSUPPORTED;
+  // items per piece: the whole slot list in the forward pass, 64 inverse-map entries in the backward pass
+  a.n_items_max = kBackward ? 64 : ((a.nsample + 15) & ~15);
+  if (a.n_items_max > 256) return D3D_ERR_UNSUPPORTED;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < ((a.n_items_max + 31) & ~31)) a.tmem_cols <<= 1;
+  const size_t smem = (kTensorCore ? (size_t)n_ctile * kTileBytes + (size_t)a.n_items_max * 32 : (size_t)a.n_items_max * 64) +
+                      (size_t)a.n_items_max * 16 + 16;
+  auto kernel = pseudogrid_rows_kernel<kBackward, kTensorCore>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int n_rows = kBackward ? a.N : a.M;
+  dim3 grid(d3d_ceil_div(n_rows, kRowsPerCta), B);
+  kernel<<<grid, kThreads, smem, st>>>(a);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int d3d_pseudogrid_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+                       const int* nvalid, const int* query_mask, const float* kpoints, const float* weights, int B,
+                       int M, int N, int C, int nsample, int K, float extent, int influence, int precision,
+                       float* out_cl, void* stream) {
+  D3D_REQUIRE(feat_cl && query_xyz && support_xyz && idx && nvalid && query_mask && kpoints && weights && out_cl);
+  D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE);
+  D3D_REQUIRE(K > 0 && K <= kK && extent > 0.f && influence >= 0 && influence <= 2 && (precision == 0 || precision == 1));
+  if (B == 0 || M == 0) return 0;
+  Args a{};
+  a.src = feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx; a.nvalid = nvalid;
+  a.query_mask = query_mask; a.kpoints = kpoints; a.weights = weights; a.out = out_cl;
+  a.M = M; a.N = N; a.C = C; a.nsample = nsample; a.K = K; a.influence = influence; a.extent = extent;
+  return precision == 1 ? launch_rows<false, true>(a, B, (cudaStream_t)stream)
+                        : launch_rows<false, false>(a, B, (cudaStream_t)stream);
+}
+
+size_t d3d_pseudogrid_bwd_workspace_bytes(int B, int M, int C, int K) {
+  (void)K;
+  if (B <= 0 || M <= 0 || C <= 0) return 0;
+  return (size_t)weight_blocks(B, M, C) * kK * C * sizeof(float);
+}
+
+int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const float* query_xyz,
+                       const float* support_xyz, const int* idx, const int* rowptr, const int* entries,
+                       const int* nvalid, const int* query_mask, const float* kpoints, const float* weights, int B,
+                       int M, int N, int C, int nsample, int K, float extent, int influence, int precision,
+                       float* grad_feat_cl, float* grad_weights, void* ws, size_t ws_bytes, void* stream) {
+  D3D_REQUIRE(grad_out_cl && feat_cl && query_xyz && support_xyz && idx && rowptr && entries && nvalid && query_mask);
+  D3D_REQUIRE(kpoints && weights && (grad_feat_cl || grad_weights));
+  D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE);
+  D3D_REQUIRE(K > 0 && K <= kK && extent > 0.f && influence >= 0 && influence <= 2 && (precision == 0 || precision == 1));
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (grad_feat_cl) {
+    Args a{};
+    a.src = grad_out_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.rowptr = rowptr; a.entries = entries;
+    a.nvalid = nvalid; a.query_mask = query_mask; a.kpoints = kpoints; a.weights = weights; a.out = grad_feat_cl;
+    a.M = M; a.N = N; a.C = C; a.nsample = nsample; a.K = K; a.influence = influence; a.extent = extent;
+    const int rc = precision == 1 ? launch_rows<true, true>(a, B, st) : launch_rows<true, false>(a, B, st);
+    if (rc != 0) return rc;
+  }
+  if (grad_weights) {
+    if (M == 0) return (int)cudaMemsetAsync(grad_weights, 0, (size_t)K * C * sizeof(float), st);
+    if (!ws || ws_bytes < d3d_pseudogrid_bwd_workspace_bytes(B, M, C, K)) return D3D_ERR_WORKSPACE;
+    const int nblk = weight_blocks(B, M, C);
+    const size_t smem = (size_t)((nsample + 7) & ~7) * (kK * sizeof(float) + sizeof(int) + 3 * sizeof(float)) + 16;
+    cudaError_t e = cudaFuncSetAttribute(pseudogrid_weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((C + 127) / 128, nblk);
+    pseudogrid_weight_grad_kernel<<<grid, kThreads, smem, st>>>(grad_out_cl, feat_cl, query_xyz, support_xyz, idx, nvalid,
+                                                                query_mask, kpoints, B, M, N, C, nsample, K, extent,
+                                                                influence, (float*)ws);
+    reduce_partials_kernel<<<d3d_ceil_div((long long)K * C, 256), 256, 0, st>>>((const float*)ws, nblk, K, C, grad_weights);
+    d3d_note_launches(2);
+  }
+  return d3d_launch_status();
+}
+
+}  // extern "C"

@@ -44,7 +44,7 @@ class PseudoGridFunction(Function):
         w = kernel_weights.contiguous()
         out_cl = ops.pseudogrid_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, k_points, w,
                                     extent, influence, precision)
-        ctx.nbr, ctx.extent, ctx.influence = nbr, extent, influence
+        ctx.nbr, ctx.extent, ctx.influence, ctx.precision = nbr, extent, influence, precision
         ctx.save_for_backward(feat_cl, w, query_xyz, support_xyz, query_mask, k_points)
         return ops.cl_to_cm(out_cl)
 
@@ -55,7 +55,7 @@ class PseudoGridFunction(Function):
         rowptr, entries = nbr.csr()
         g_cl = ops.cm_to_cl(grad_out.contiguous())
         gf_cl, gw = ops.pseudogrid_bwd(g_cl, feat_cl, query_xyz, support_xyz, nbr.idx, rowptr, entries, nbr.nvalid,
-                                       query_mask, k_points, w, ctx.extent, ctx.influence,
+                                       query_mask, k_points, w, ctx.extent, ctx.influence, ctx.precision,
                                        need_feat=ctx.needs_input_grad[0], need_weights=ctx.needs_input_grad[1])
         gf = ops.cl_to_cm(gf_cl) if gf_cl is not None else None
         return gf, gw, None, None, None, None, None, None, None, None

@@ -225,7 +225,7 @@ def pseudogrid_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, kpo
 
 
 def pseudogrid_bwd(grad_out_cl, feat_cl, query_xyz, support_xyz, idx, rowptr, entries, nvalid, query_mask, kpoints,
-                   weights, extent, influence, need_feat=True, need_weights=True):
+                   weights, extent, influence, precision=0, need_feat=True, need_weights=True):
     L = _lib.load()
     g, f = _f32(grad_out_cl, "grad_out"), _f32(feat_cl, "features")
     B, M, C = g.shape
@@ -238,7 +238,7 @@ def pseudogrid_bwd(grad_out_cl, feat_cl, query_xyz, support_xyz, idx, rowptr, en
         ws = _ws(L.d3d_pseudogrid_bwd_workspace_bytes(B, M, C, K), g.device)
         _lib.check(L.d3d_pseudogrid_bwd(_p(g), _p(f), _p(query_xyz), _p(support_xyz), _p(idx), _p(rowptr), _p(entries),
                                         _p(nvalid), _p(query_mask), _p(kpoints), _p(weights), B, M, N, C, ns, K,
-                                        float(extent), INFLUENCES[influence], _p(gf), _p(gw), _p(ws), ws.numel(),
+                                        float(extent), INFLUENCES[influence], int(precision), _p(gf), _p(gw), _p(ws), ws.numel(),
                                         _stream()), "d3d_pseudogrid_bwd")
     _count()
     return gf, gw

@@ -140,13 +140,14 @@ int d3d_pseudogrid_fwd(const float* feat_cl, const float* query_xyz, const float
                        const int* idx, const int* nvalid, const int* query_mask, const float* kpoints,
                        const float* weights, int B, int M, int N, int C, int nsample, int K, float extent,
                        int influence, int precision, float* out_cl, void* stream);
-/* grad wrt features (via the inverse map) and wrt weights (deterministic two-pass reduction).
+/* grad wrt features (via the inverse map; `precision` selects fp32 or the tcgen05 contraction like the forward)
+ * and wrt weights (fp32, deterministic two-pass reduction).  Either output pointer may be NULL.
  * Workspace: d3d_pseudogrid_bwd_workspace_bytes. */
 size_t d3d_pseudogrid_bwd_workspace_bytes(int B, int M, int C, int K);
 int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const float* query_xyz,
                        const float* support_xyz, const int* idx, const int* rowptr, const int* entries,
                        const int* nvalid, const int* query_mask, const float* kpoints, const float* weights,
-                       int B, int M, int N, int C, int nsample, int K, float extent, int influence,
+                       int B, int M, int N, int C, int nsample, int K, float extent, int influence, int precision,
                        float* grad_feat_cl, float* grad_weights, void* ws, size_t ws_bytes, void* stream);
 
 /* MaskedMaxPool's gather + max over all nsample slots   ref: pt_custom_ops/pt_utils.py:199-205

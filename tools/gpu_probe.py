@@ -38,8 +38,14 @@ for C in (72, 144):
     kp = torch.randn(15, 3, device=dev) * 0.01; w = torch.randn(15, C, device=dev)
     t = timeit(lambda: ops.pseudogrid_fwd(fcl, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 0))
     print("C=%d pseudogrid_fwd fp32: %.3f ms" % (C, t))
-    t = timeit(lambda: ops.pseudogrid_bwd(g, fcl, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear'))
-    print("C=%d pseudogrid_bwd fp32: %.3f ms" % (C, t))
+    t = timeit(lambda: ops.pseudogrid_fwd(fcl, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 1))
+    print("C=%d pseudogrid_fwd tcgen05: %.3f ms" % (C, t))
+    t = timeit(lambda: ops.pseudogrid_bwd(g, fcl, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 0, True, False))
+    print("C=%d pseudogrid_bwd feat fp32: %.3f ms" % (C, t))
+    t = timeit(lambda: ops.pseudogrid_bwd(g, fcl, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 1, True, False))
+    print("C=%d pseudogrid_bwd feat tcgen05: %.3f ms" % (C, t))
+    t = timeit(lambda: ops.pseudogrid_bwd(g, fcl, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 0, False, True))
+    print("C=%d pseudogrid_bwd weights: %.3f ms" % (C, t))
     t = timeit(lambda: ops.gather_max_fwd(fcl, idx))
     print("C=%d gather_max_fwd: %.3f ms" % (C, t))
 f = torch.randn(B, 72, N, device=dev)

@@ -21,6 +21,7 @@ for _ in range(n):
     elif op == "pospool_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg')
     elif op == "pseudogrid_fwd": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 0)
     elif op == "pseudogrid_fwd_tc": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 1)
-    elif op == "pseudogrid_bwd": ops.pseudogrid_bwd(f, f, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear')
+    elif op == "pseudogrid_bwd": ops.pseudogrid_bwd(f, f, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 0)
+    elif op == "pseudogrid_bwd_tc": ops.pseudogrid_bwd(f, f, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 1)
 torch.cuda.synchronize()
 print("ok", op)
