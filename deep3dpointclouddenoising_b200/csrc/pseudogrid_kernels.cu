@@ -47,7 +47,11 @@ __device__ __forceinline__ unsigned long long make_smem_desc(unsigned addr) {
 template <int kInfluence>
 __device__ __forceinline__ float influence_weight(float dx, float dy, float dz, float coef) {
   const float sq = dx * dx + dy * dy + dz * dz;
-  if (kInfluence == D3D_KP_LINEAR) return fmaxf(1.0f - sqrtf(sq) * coef, 0.0f);  // :480
+  if (kInfluence == D3D_KP_LINEAR) {  // :480   (sqrt.approx: <= 1 ulp, no slow-path call)
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(sq));
+    return fmaxf(1.0f - r * coef, 0.0f);
+  }
   if (kInfluence == D3D_KP_GAUSSIAN) return __expf(sq * coef);                   // :484, models/utlis.py:287-294
   return 1.0f;                                                                   // constant (:476)
 }
@@ -60,20 +64,27 @@ __host__ __device__ inline float influence_coef(float extent, int influence) {
   return 1.0f / extent;
 }
 
-// stage 2 of a piece: influence weight of every (item, kernel point); srow < 0 marks a masked item
+// stage 2 of a piece: influence weight of every (item, kernel point); srow < 0 marks a masked item.
+// thread = (item, pair of adjacent kernel points): the relative position is read once per two weights and the two
+// bf16 go out as one 32-bit store (adjacent k are adjacent in the K-major operand layout).
 template <int kInfluence, bool kTensorCore>
 __device__ __forceinline__ void stage_weights(int tid, int pmax, int K, const int* srow, const float* srel,
                                               const float* kp, float coef, unsigned char* b_tile, float* w_f32) {
-  const int k = tid & 15;  // 128 threads: the kernel point of a thread never changes
-  const float kx = kp[3 * k], ky = kp[3 * k + 1], kz = kp[3 * k + 2];
-  for (int t = tid; t < pmax * 16; t += 128) {
-    const int p = t >> 4;
-    float w = 0.0f;
-    if (k < K && srow[p] >= 0) w = influence_weight<kInfluence>(srel[3 * p] - kx, srel[3 * p + 1] - ky, srel[3 * p + 2] - kz, coef);
+  const int k0 = (tid & 7) * 2;  // 128 threads: a thread's kernel-point pair never changes
+  const float ax = kp[3 * k0], ay = kp[3 * k0 + 1], az = kp[3 * k0 + 2];
+  const float bx = kp[3 * k0 + 3], by = kp[3 * k0 + 4], bz = kp[3 * k0 + 5];
+  for (int t = tid; t < pmax * 8; t += 128) {
+    const int p = t >> 3;
+    float w0 = 0.0f, w1 = 0.0f;
+    if (srow[p] >= 0) {
+      const float dx = srel[3 * p], dy = srel[3 * p + 1], dz = srel[3 * p + 2];
+      if (k0 < K) w0 = influence_weight<kInfluence>(dx - ax, dy - ay, dz - az, coef);
+      if (k0 + 1 < K) w1 = influence_weight<kInfluence>(dx - bx, dy - by, dz - bz, coef);
+    }
     if (kTensorCore)
-      *reinterpret_cast<__nv_bfloat16*>(b_tile + operand_offset(p, k)) = __float2bfloat16_rn(w);
+      *reinterpret_cast<__nv_bfloat162*>(b_tile + operand_offset(p, k0)) = __floats2bfloat162_rn(w0, w1);
     else
-      w_f32[t] = w;
+      *reinterpret_cast<float2*>(w_f32 + p * 16 + k0) = make_float2(w0, w1);
   }
 }
 
@@ -113,12 +124,12 @@ struct Args {
 // resident CTAs (8 per SM: <= 64 registers, 64 TMEM columns) and the next row's index/coordinate loads are issued
 // before the current row's gathers are consumed.
 template <bool kBackward, bool kTensorCore>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, 6)
 pseudogrid_rows_kernel(const Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ unsigned tmem_base_slot;
-  __shared__ float kp[48];
+  __shared__ float kp[52];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -152,7 +163,7 @@ pseudogrid_rows_kernel(const Args a) {
       *reinterpret_cast<__nv_bfloat16*>(a_tiles + (size_t)ct * kTileBytes + operand_offset(cl, k)) = __float2bfloat16_rn(w);
     }
   }
-  if (tid < K * 3) kp[tid] = a.kpoints[tid];
+  if (tid < 52) kp[tid] = tid < K * 3 ? a.kpoints[tid] : 0.0f;
   if (kTensorCore) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (kTensorCore) {
@@ -245,48 +256,52 @@ pseudogrid_rows_kernel(const Args a) {
           mbar_wait(bar, phase);
           phase ^= 1u;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int col0 = 0; col0 < np; col0 += 16) {
-            unsigned r[16];
-            const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)col0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
-            // (tcgen05.ld / wait::ld are .sync.aligned: every lane of the warp executes them, outside any
-            //  lane-divergent branch; only the gathers are predicated on the lane's channel being real)
-            float x[16];
+          if (ct * 128 + warp * 32 < C) {  // warp-uniform: a warp whose 32 channels are all padding skips the epilogue
+            for (int col0 = 0; col0 < np; col0 += 16) {
+              unsigned r[16];
+              const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)col0;
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                  : "r"(taddr));
+              // gathers: unconditional (a padding lane re-reads channel 0, a masked / padding item reads row 0 with
+              // E = 0), all 16 issued before the first use; offsets come as 4 x int4 broadcast reads
+              float x[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i)  // all gathers of the chunk are issued before the first use; columns >= np
-              x[i] = active ? __ldg(sc + srow[col0 + i]) : 0.0f;  // have E = 0 and offset 0 (chunk stays inside pmax)
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const int4 o = *reinterpret_cast<const int4*>(srow + col0 + 4 * i4);
+                x[4 * i4] = __ldg(sc + o.x); x[4 * i4 + 1] = __ldg(sc + o.y);
+                x[4 * i4 + 2] = __ldg(sc + o.z); x[4 * i4 + 3] = __ldg(sc + o.w);
+              }
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sum += x[i] * __uint_as_float(r[i]);
+              for (int i = 0; i < 16; ++i) sum += x[i] * __uint_as_float(r[i]);
+            }
           }
           // every warp is done reading TMEM before the next MMA overwrites it
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncthreads();
-        } else if (active) {
+        } else if (ct * 128 + warp * 32 < C) {  // warp-uniform
           float W[kK];
 #pragma unroll
-          for (int k = 0; k < kK; ++k) W[k] = k < K ? __ldg(a.weights + (size_t)k * C + c) : 0.0f;
-          for (int q0 = 0; q0 < np; q0 += 8) {
+          for (int k = 0; k < kK; ++k) W[k] = (active && k < K) ? __ldg(a.weights + (size_t)k * C + c) : 0.0f;
+          for (int q0 = 0; q0 < np; q0 += 8) {  // q0 + 8 <= pmax: offset 0 / weight 0 beyond np
             float x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = __ldg(sc + srow[q0 + i]);  // q0 + i < pmax: offset 0 / weight 0 beyond np
+            const int4 o0 = *reinterpret_cast<const int4*>(srow + q0), o1 = *reinterpret_cast<const int4*>(srow + q0 + 4);
+            x[0] = __ldg(sc + o0.x); x[1] = __ldg(sc + o0.y); x[2] = __ldg(sc + o0.z); x[3] = __ldg(sc + o0.w);
+            x[4] = __ldg(sc + o1.x); x[5] = __ldg(sc + o1.y); x[6] = __ldg(sc + o1.z); x[7] = __ldg(sc + o1.w);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              {
-                const float4* wp = reinterpret_cast<const float4*>(w_f32 + (q0 + i) * kK);  // broadcast reads
-                float e = 0.0f;
+              const float4* wp = reinterpret_cast<const float4*>(w_f32 + (q0 + i) * kK);  // broadcast reads
+              float e = 0.0f;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  const float4 w = wp[k4];
-                  e += w.x * W[4 * k4] + w.y * W[4 * k4 + 1] + w.z * W[4 * k4 + 2] + w.w * W[4 * k4 + 3];
-                }
-                sum += x[i] * e;
+              for (int k4 = 0; k4 < 4; ++k4) {
+                const float4 w = wp[k4];
+                e += w.x * W[4 * k4] + w.y * W[4 * k4 + 1] + w.z * W[4 * k4 + 2] + w.w * W[4 * k4 + 3];
               }
+              sum += x[i] * e;
             }
           }
         }
@@ -317,13 +332,13 @@ pseudogrid_weight_grad_kernel(const float* __restrict__ grad_out, const float* _
                               int C, int nsample, int K, float extent, int influence,
                               float* __restrict__ partial /* (gridDim.y, 16, C) */) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ float kp[48];
+  __shared__ float kp[52];
   const int pm = (nsample + 7) & ~7;
   float* w_f32 = reinterpret_cast<float*>(smem);        // pm x 16
   int* srow = reinterpret_cast<int*>(w_f32 + pm * kK);  // pm
   float* srel = reinterpret_cast<float*>(srow + pm);    // pm x 3
   const int tid = threadIdx.x;
-  if (tid < K * 3) kp[tid] = kpoints[tid];
+  if (tid < 52) kp[tid] = tid < K * 3 ? kpoints[tid] : 0.0f;
   const int c = blockIdx.x * 128 + tid;
   const bool active = c < C;
   float acc[kK];
@@ -355,13 +370,15 @@ pseudogrid_weight_grad_kernel(const float* __restrict__ grad_out, const float* _
     __syncthreads();
     for (int p = tid; p < pmax; p += kThreads) srow[p] = srow[p] >= 0 ? srow[p] * C : 0;
     __syncthreads();
-    if (active) {
-      const float g = __ldg(grad_out + (size_t)qi * C + c);
-      const float* fc = feat + (size_t)b * N * C + c;
-      for (int q0 = 0; q0 < n_eff; q0 += 8) {
+    if (blockIdx.x * 128 + (tid & ~31) < C) {  // warp-uniform: skip warps made of padding channels only
+      const int cc = active ? c : 0;
+      const float g = active ? __ldg(grad_out + (size_t)qi * C + cc) : 0.0f;
+      const float* fc = feat + (size_t)b * N * C + cc;
+      for (int q0 = 0; q0 < n_eff; q0 += 8) {  // masked tail: weight 0, offset 0
         float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __ldg(fc + srow[q0 + i]) * g;  // masked tail: weight 0, offset 0
+        const int4 o0 = *reinterpret_cast<const int4*>(srow + q0), o1 = *reinterpret_cast<const int4*>(srow + q0 + 4);
+        x[0] = __ldg(fc + o0.x) * g; x[1] = __ldg(fc + o0.y) * g; x[2] = __ldg(fc + o0.z) * g; x[3] = __ldg(fc + o0.w) * g;
+        x[4] = __ldg(fc + o1.x) * g; x[5] = __ldg(fc + o1.y) * g; x[6] = __ldg(fc + o1.z) * g; x[7] = __ldg(fc + o1.w) * g;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4* wp = reinterpret_cast<const float4*>(w_f32 + (q0 + i) * kK);
