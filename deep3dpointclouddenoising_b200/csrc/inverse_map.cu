@@ -241,13 +241,39 @@ chunk_sort_kernel(const int* __restrict__ rowptr, const int* __restrict__ matrix
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= (long long)B * N) return;
   const int b = (int)(row / N), i = (int)(row - (long long)b * N);
-  const int seg_end = rowptr[row + 1];
+  const int seg_beg = rowptr[row], seg_end = rowptr[row + 1];
+  const int seg_len = seg_end - seg_beg;
+  if (seg_len <= 1) {
+    if (seg_len == 1 && lane == 0) entries[seg_beg] = unsorted[seg_beg];
+    return;
+  }
+  // piece boundaries: lane ch holds where piece ch starts (the fill cursors' initial values)
   const int* mat = matrix + (size_t)b * n_chunks * N + i;
-  int beg = rowptr[row];
+  const int my_start = lane < n_chunks ? (lane == 0 ? seg_beg : mat[(size_t)lane * N]) : seg_end;
+  if (seg_len <= 32) {
+    // whole segment in one pass: rank among the entries of the same piece, offset by the piece start
+    const int pos = seg_beg + lane;
+    const int own = lane < seg_len ? unsorted[pos] : 0x7fffffff;
+    // piece of this lane's entry = number of piece starts <= pos, minus 1
+    int piece = 0;
+    for (int ch = 1; ch < n_chunks; ++ch) piece += __shfl_sync(D3D_FULL_MASK, my_start, ch) <= pos ? 1 : 0;
+    const int pstart = __shfl_sync(D3D_FULL_MASK, my_start, piece);
+    int r = 0;
+    for (int t = 0; t < seg_len; ++t) {
+      const int other = __shfl_sync(D3D_FULL_MASK, own, t);
+      const int opiece = __shfl_sync(D3D_FULL_MASK, piece, t);
+      r += (opiece == piece && other < own) ? 1 : 0;
+    }
+    if (lane < seg_len) entries[pstart + r] = own;
+    return;
+  }
+  int beg = seg_beg;
   for (int ch = 0; ch < n_chunks; ++ch) {
-    const int end = ch + 1 < n_chunks ? mat[(size_t)(ch + 1) * N] : seg_end;  // cursor start of the next piece
+    const int end = __shfl_sync(D3D_FULL_MASK, my_start, ch + 1 < 32 ? ch + 1 : 31);  // lanes >= n_chunks hold seg_end
     const int len = end - beg;
-    if (len <= 64) {
+    if (len == 1) {
+      if (lane == 0) entries[beg] = unsorted[beg];
+    } else if (len > 1 && len <= 64) {
       const int own0 = lane < len ? unsorted[beg + lane] : 0x7fffffff;
       const int own1 = lane + 32 < len ? unsorted[beg + lane + 32] : 0x7fffffff;
       int r0 = 0, r1 = 0;
@@ -258,7 +284,7 @@ chunk_sort_kernel(const int* __restrict__ rowptr, const int* __restrict__ matrix
       }
       if (lane < len) entries[beg + r0] = own0;
       if (lane + 32 < len) entries[beg + r1] = own1;
-    } else {
+    } else if (len > 64) {
       for (int t = lane; t < len; t += 32) {  // rare: out-of-place rank counting straight from L1/L2
         const int own = unsorted[beg + t];
         int r = 0;

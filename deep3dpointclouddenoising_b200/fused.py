@@ -97,3 +97,34 @@ class NearestGatherFunction(Function):
         g_cl = ops.cm_to_cl(grad_out.contiguous())
         gf_cl = ops.nearest_gather_bwd(g_cl, rowptr, entries, ctx.nbr.n_support)
         return ops.cl_to_cm(gf_cl), None
+
+
+class BatchNormActFunction(Function):
+    """y = act(BatchNorm1d(x) [+ residual]) in one statistics pass and one apply pass (csrc/batchnorm.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu):
+        x = x.contiguous()
+        res = residual.contiguous() if residual is not None else None
+        y, mean, invstd = ops.bn_act_fwd(x, res, weight, bias, running_mean, running_var, eps, momentum, training, relu)
+        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
+        ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, y, weight, mean, invstd = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, mean, invstd, ctx.training, ctx.relu,
+                                                 ctx.has_res and ctx.needs_input_grad[1])
+        return (dx, dres, dgamma if weight is not None else None, dbeta if weight is not None else None, None, None, None,
+                None, None, None)
+
+
+def batch_norm_act(bn, x, relu, residual=None):
+    """Applies nn.BatchNorm1d module `bn` (its parameters, buffers, momentum, eps, training flag) with the fused kernel."""
+    training = bn.training or bn.running_mean is None
+    if bn.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = bn.momentum if bn.momentum is not None else 1.0 / float(max(int(bn.num_batches_tracked), 1))
+    return BatchNormActFunction.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, momentum,
+                                      training, relu)

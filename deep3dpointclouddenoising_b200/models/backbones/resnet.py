@@ -11,14 +11,12 @@ import torch.nn as nn
 
 from ... import neighbors as _neighbors
 from ...pt_custom_ops.pt_utils import MaskedMaxPool
+from ..blocks import conv_bn
 from ..local_aggregation_operators import LocalAggregation
 
 
 def _conv_bn(cin, cout, momentum, relu):
-    layers = [nn.Conv1d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm1d(cout, momentum=momentum)]
-    if relu:
-        layers.append(nn.ReLU(inplace=True))
-    return nn.Sequential(*layers)
+    return conv_bn(cin, cout, momentum, relu)
 
 
 class MultiInputSequential(nn.Sequential):
@@ -50,10 +48,10 @@ class Bottleneck(nn.Module):
             query_xyz, query_mask, identity = xyz, mask, features
         out = self.conv1(features)
         out = self.local_aggregation(query_xyz, xyz, query_mask, mask, out)
-        out = self.conv2(out)
         if self.in_channels != self.out_channels:
             identity = self.shortcut(identity)
-        return query_xyz, query_mask, self.relu(out + identity)
+        # conv2 -> BN, + identity, ReLU (resnet.py:58-66): the add and the ReLU ride on the BN apply pass
+        return query_xyz, query_mask, self.conv2(out, residual=identity, final_relu=True)
 
 
 class ResNet(nn.Module):

@@ -1,0 +1,41 @@
+"""Conv1d / BatchNorm1d / ReLU stacks with the reference's module layout (nn.Sequential children '0', '1', '2', so
+state-dict keys are identical: ref u_net_arch/models/backbones/resnet.py:32-45, local_aggregation_operators.py:117-123,
+heads/multi_dimensional_head.py:40-59) whose forward runs every BatchNorm1d (+ following ReLU, + optional residual
+add) through the fused kernel (csrc/batchnorm.cu).  The 1x1 convolutions stay cuDNN/cuBLAS."""
+import torch.nn as nn
+
+from ..fused import batch_norm_act
+from ..utils.config import runtime
+
+
+class FusedSequential(nn.Sequential):
+    def forward(self, x, residual=None, final_relu=False):
+        mods = list(self._modules.values())
+        use_fused = x.is_cuda and runtime.fused_batchnorm
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.BatchNorm1d) and use_fused and x.dim() == 3:
+                next_is_relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                is_last = i + (2 if next_is_relu else 1) == len(mods)
+                res = residual if is_last else None
+                x = batch_norm_act(m, x, relu=next_is_relu or (is_last and final_relu), residual=res)
+                if is_last:
+                    residual, final_relu = None, False
+                i += 2 if next_is_relu else 1
+                continue
+            x = m(x)
+            i += 1
+        if residual is not None:
+            x = x + residual
+        if final_relu:
+            x = x.relu()
+        return x
+
+
+def conv_bn(cin, cout, momentum=0.1, relu=True, conv=True):
+    layers = [nn.Conv1d(cin, cout, kernel_size=1, bias=False)] if conv else []
+    layers.append(nn.BatchNorm1d(cout, momentum=momentum))
+    if relu:
+        layers.append(nn.ReLU(inplace=True))
+    return FusedSequential(*layers)

@@ -5,10 +5,11 @@ import torch
 import torch.nn as nn
 
 from ...pt_custom_ops.pt_utils import MaskedUpsample
+from ..blocks import FusedSequential, conv_bn
 
 
 def _block(cin, cout):
-    return nn.Sequential(nn.Conv1d(cin, cout, kernel_size=1, bias=False), nn.BatchNorm1d(cout), nn.ReLU(inplace=True))
+    return conv_bn(cin, cout)
 
 
 class MultiDimHeadResNet(nn.Module):
@@ -22,9 +23,9 @@ class MultiDimHeadResNet(nn.Module):
         self.up_conv1 = _block(8 * width, 2 * width)
         self.up_conv2 = _block(4 * width, width)
         self.up_conv3 = _block(2 * width, width // 2)
-        self.head = nn.Sequential(nn.Conv1d(width // 2, width // 2, kernel_size=1, bias=False),
-                                  nn.BatchNorm1d(width // 2), nn.ReLU(inplace=True),
-                                  nn.Conv1d(width // 2, num_classes, kernel_size=1, bias=True))
+        self.head = FusedSequential(nn.Conv1d(width // 2, width // 2, kernel_size=1, bias=False),
+                                    nn.BatchNorm1d(width // 2), nn.ReLU(inplace=True),
+                                    nn.Conv1d(width // 2, num_classes, kernel_size=1, bias=True))
 
     def forward(self, end_points):
         features = end_points['res5_features']

@@ -15,14 +15,14 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..fused import PosPoolFunction, PseudoGridFunction
+from .blocks import conv_bn
 from ..pt_custom_ops.pt_utils import MaskedQueryAndGroup
 from ..utils.config import runtime
 from .utlis import create_kernel_points, weight_variable
 
 
 def _output_block(in_channels, out_channels, momentum, with_conv):
-    layers = [nn.Conv1d(in_channels, out_channels, kernel_size=1, bias=False)] if with_conv else []
-    return nn.Sequential(*layers, nn.BatchNorm1d(out_channels, momentum=momentum), nn.ReLU(inplace=True))
+    return conv_bn(in_channels, out_channels, momentum, relu=True, conv=with_conv)
 
 
 class PosPool(nn.Module):

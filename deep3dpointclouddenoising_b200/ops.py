@@ -291,3 +291,38 @@ def nearest_gather_bwd(grad_out_cl, rowptr, entries, n_support):
                    "d3d_nearest_gather_bwd")
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused BatchNorm1d (+ residual) (+ ReLU), channel-major tensors
+# ------------------------------------------------------------------------------------------------
+def bn_act_fwd(x, residual, gamma, beta, running_mean, running_var, eps, momentum, training, relu):
+    L = _lib.load()
+    x = _f32(x, "input")
+    B, C, N = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty_like(x)
+        mean = torch.empty((C,), dtype=torch.float32, device=x.device)
+        invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
+        _lib.check(L.d3d_bn_act_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(running_mean), _p(running_var), B, C, N,
+                                    float(eps), float(momentum), int(bool(training)), int(bool(relu)), _p(y), _p(mean),
+                                    _p(invstd), _stream()), "d3d_bn_act_fwd")
+    _count()
+    return y, mean, invstd
+
+
+def bn_act_bwd(dy, x, y, gamma, mean, invstd, training, relu, need_res):
+    L = _lib.load()
+    dy = _f32(dy, "grad_out")
+    B, C, N = dy.shape
+    with torch.cuda.device(dy.device):
+        dx = torch.empty_like(dy)
+        dres = torch.empty_like(dy) if need_res else None
+        dgamma = torch.empty((C,), dtype=torch.float32, device=dy.device)
+        dbeta = torch.empty((C,), dtype=torch.float32, device=dy.device)
+        ws = _ws(L.d3d_bn_act_bwd_workspace_bytes(C), dy.device)
+        _lib.check(L.d3d_bn_act_bwd(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(invstd), B, C, N, int(bool(training)),
+                                    int(bool(relu)), _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()),
+                   "d3d_bn_act_bwd")
+    _count()
+    return dx, dres, dgamma, dbeta

@@ -75,7 +75,8 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 # Not in the reference: selects the arithmetic of the PseudoGrid contraction.
 #   'fp32' CUDA cores (parity tolerance 1e-5) | 'bf16' tcgen05 tensor cores (separate tolerance)
 # Kept outside the yaml-checked key set so that reference yaml files stay valid and unknown keys still raise.
-runtime = AttrDict({"pseudo_grid_precision": "fp32"})
+#   fused_batchnorm: BatchNorm1d (+ReLU, +residual) through csrc/batchnorm.cu instead of cuDNN/ATen (row f4)
+runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True})
 
 
 def reset_config():

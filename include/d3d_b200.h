@@ -164,6 +164,22 @@ int d3d_nearest_gather_fwd(const float* feat_cl, const int* idx, int B, int M, i
 int d3d_nearest_gather_bwd(const float* grad_out_cl, const int* rowptr, const int* entries, int B, int M,
                            int N, int C, float* grad_feat_cl, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 4. Fused BatchNorm1d (+ residual add) (+ ReLU) on channel-major (B, C, N) activations (SURVEY.md §8 row f4:
+ *    the conv / BN / ReLU sandwich around each aggregation; ref: models/backbones/resnet.py:32-45,58-66,
+ *    models/local_aggregation_operators.py:121-123).  torch.nn.BatchNorm1d semantics; training != 0 uses batch
+ *    statistics and updates running_mean / running_var in place, else the running statistics are used.
+ *    y = act(bn(x) [+ residual]).  save_mean / save_invstd (C) are outputs the backward pass needs.
+ * ---------------------------------------------------------------------------------------------- */
+int d3d_bn_act_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
+                   float* running_var, int B, int C, int N, float eps, float momentum, int training, int relu,
+                   float* y, float* save_mean, float* save_invstd, void* stream);
+/* dx (and dres = gradient w.r.t. residual, may be NULL; dgamma / dbeta (C), may be NULL).  y is needed when relu. */
+size_t d3d_bn_act_bwd_workspace_bytes(int C);
+int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* save_mean,
+                   const float* save_invstd, int B, int C, int N, int training, int relu, float* dx, float* dres,
+                   float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
