@@ -397,6 +397,180 @@ pseudogrid_weight_grad_kernel(const float* __restrict__ grad_out, const float* _
   }
 }
 
+// dW partials on the tensor cores (bf16 mode).  dW^T[c, k] = sum_items P[c, item] * w[item, k] with
+// P[c, item] = F[idx_item, c] * g[row, c]:  MMA M = 128 channels (TMEM lanes), N = 16 kernel points, K = items
+// (16 per K-step, up to 64 per row), accumulated in ONE TMEM tile over every row the CTA visits.  A thread owns a
+// channel: it gathers its 16 features per K-step, multiplies by g, rounds to bf16 and writes them as two 16-byte
+// stores into the K-major A tile (its own row of the tile); the B tile holds the influence weights transposed.
+// Two staging buffers: while the tensor core consumes one, the threads fill the other.
+constexpr int kDwItems = 64;                         // items staged per buffer (4 K-steps)
+constexpr int kDwABytes = (kDwItems / 16) * 4096;    // 4 x [128 x 16] bf16
+constexpr int kDwBBytes = (kDwItems / 16) * 512;     // 4 x [16 x 16] bf16
+constexpr int kDwBufBytes = kDwABytes + kDwBBytes;
+
+__global__ void __launch_bounds__(kThreads)
+pseudogrid_weight_grad_tc_kernel(const float* __restrict__ grad_out, const float* __restrict__ feat,
+                                 const float* __restrict__ query_xyz, const float* __restrict__ support_xyz,
+                                 const int* __restrict__ idx, const int* __restrict__ nvalid,
+                                 const int* __restrict__ query_mask, const float* __restrict__ kpoints, int B, int M,
+                                 int N, int C, int nsample, int K, float extent, int influence,
+                                 float* __restrict__ partial /* (gridDim.y, 16, C) */) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long mbar[2];
+  __shared__ unsigned tmem_base_slot;
+  __shared__ float kp[52];
+  unsigned char* bufs = smem;                                           // 2 x (A | B)
+  int* srow = reinterpret_cast<int*>(smem + 2 * kDwBufBytes);           // kDwItems offsets
+  float* srel = reinterpret_cast<float*>(srow + kDwItems);              // kDwItems x 3
+  float* w_f32 = srel + 3 * kDwItems;                                   // kDwItems x 16 (fp32 staging of the weights)
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int c = blockIdx.x * 128 + tid;
+  const bool active = c < C;
+  const bool warp_active = blockIdx.x * 128 + warp * 32 < C;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(32u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 52) kp[tid] = tid < K * 3 ? kpoints[tid] : 0.0f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_base = tmem_base_slot;
+  // D = f32, A = B = bf16, K-major, N = 16, M = 128
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+  const float coef = influence_coef(extent, influence);
+  unsigned phase[2] = {0u, 0u};
+  int pending[2] = {0, 0};  // an MMA group that reads this buffer has been committed and not yet waited for
+  int n_issued = 0;         // MMAs issued so far (the first one overwrites the accumulator)
+  int buf = 0;
+
+  const long long total = (long long)B * M;
+  for (long long qi = blockIdx.y; qi < total; qi += gridDim.y) {
+    const int b = (int)(qi / M);
+    const int n_eff = query_mask[qi] != 0 ? nvalid[qi] : nsample;
+    const float qx = query_xyz[qi * 3], qy = query_xyz[qi * 3 + 1], qz = query_xyz[qi * 3 + 2];
+    const float g = active ? __ldg(grad_out + (size_t)qi * C + c) : 0.0f;
+    const float* fc = feat + (size_t)b * N * C + (active ? c : 0);
+    for (int p0 = 0; p0 < n_eff; p0 += kDwItems) {
+      const int np = min(kDwItems, n_eff - p0);
+      const int ksteps = (np + 15) >> 4;
+      unsigned char* a_tile = bufs + (size_t)buf * kDwBufBytes;
+      unsigned char* b_tile = a_tile + kDwABytes;
+      // the tensor core must be done with this buffer (the MMA group committed two pieces ago)
+      if (pending[buf]) {
+        mbar_wait(smem_u32(&mbar[buf]), phase[buf]);
+        phase[buf] ^= 1u;
+        pending[buf] = 0;
+      }
+      __syncthreads();  // srow / srel / w_f32 of the previous piece fully consumed
+      if (tid < kDwItems) {
+        int gi = -1;
+        float dx = 0.f, dy = 0.f, dz = 0.f;
+        if (tid < np) {
+          gi = d3d_clamp_index(idx[qi * nsample + p0 + tid], N);
+          const float* sp = support_xyz + ((size_t)b * N + gi) * 3;
+          dx = sp[0] - qx; dy = sp[1] - qy; dz = sp[2] - qz;
+        }
+        srow[tid] = gi;
+        srel[3 * tid] = dx; srel[3 * tid + 1] = dy; srel[3 * tid + 2] = dz;
+      }
+      __syncthreads();
+      if (influence == D3D_KP_LINEAR) stage_weights<D3D_KP_LINEAR, false>(tid, ksteps * 16, K, srow, srel, kp, coef, nullptr, w_f32);
+      else if (influence == D3D_KP_GAUSSIAN) stage_weights<D3D_KP_GAUSSIAN, false>(tid, ksteps * 16, K, srow, srel, kp, coef, nullptr, w_f32);
+      else stage_weights<D3D_KP_CONSTANT, false>(tid, ksteps * 16, K, srow, srel, kp, coef, nullptr, w_f32);
+      __syncthreads();
+      // B tiles: w^T, row = kernel point, column = item of the K-step;  gather offsets replace the row numbers
+      for (int t = tid; t < ksteps * 256; t += kThreads) {
+        const int p = t >> 4, k = t & 15;
+        *reinterpret_cast<__nv_bfloat16*>(b_tile + (p >> 4) * 512 + operand_offset(k, p & 15)) = __float2bfloat16_rn(w_f32[t]);
+      }
+      if (tid < kDwItems) srow[tid] = srow[tid] >= 0 ? srow[tid] * C : 0;
+      __syncthreads();
+      // A tiles: this thread's row (channel) of every K-step: 16 products -> 16 bf16 -> two 16-byte stores
+      if (warp_active) {
+        for (int s = 0; s < ksteps; ++s) {
+          float x[16];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int4 o = *reinterpret_cast<const int4*>(srow + s * 16 + 4 * i4);
+            x[4 * i4] = __ldg(fc + o.x); x[4 * i4 + 1] = __ldg(fc + o.y); x[4 * i4 + 2] = __ldg(fc + o.z); x[4 * i4 + 3] = __ldg(fc + o.w);
+          }
+          __nv_bfloat162 h[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(x[2 * i] * g, x[2 * i + 1] * g);
+          unsigned char* dst = a_tile + s * 4096 + (tid >> 3) * kSbo + (tid & 7) * 16;
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&h[0]);         // items 0..7  of the K-step
+          *reinterpret_cast<uint4*>(dst + kLbo) = *reinterpret_cast<const uint4*>(&h[4]);  // items 8..15
+        }
+      } else {
+        for (int s = 0; s < ksteps; ++s) {  // padding channels: zero rows (the tile is read in full by the MMA)
+          unsigned char* dst = a_tile + s * 4096 + (tid >> 3) * kSbo + (tid & 7) * 16;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + kLbo) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int s = 0; s < ksteps; ++s) {
+          const unsigned long long a_desc = make_smem_desc(smem_u32(a_tile + s * 4096));
+          const unsigned long long b_desc = make_smem_desc(smem_u32(b_tile + s * 512));
+          const unsigned accumulate = (n_issued + s) > 0 ? 1u : 0u;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+              "}\n" ::"r"(tmem_base), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[buf])) : "memory");
+      }
+      n_issued += ksteps;
+      pending[buf] = 1;
+      buf ^= 1;
+    }
+  }
+  // drain: both buffers' MMA groups complete (in issue order), then read the accumulator
+  for (int k = 0; k < 2; ++k) {
+    if (pending[buf]) {
+      mbar_wait(smem_u32(&mbar[buf]), phase[buf]);
+      phase[buf] ^= 1u;
+      pending[buf] = 0;
+    }
+    buf ^= 1;
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  unsigned r[16];
+  if (n_issued > 0) {
+    const unsigned taddr = tmem_base + ((unsigned)(warp * 32) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  } else {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r[k] = 0u;
+  }
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kK; ++k) partial[((size_t)blockIdx.y * kK + k) * C + c] = __uint_as_float(r[k]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblk, int K, int C,
                                        float* __restrict__ grad_weights) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,9 +665,18 @@ int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const flo
     cudaError_t e = cudaFuncSetAttribute(pseudogrid_weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((C + 127) / 128, nblk);
-    pseudogrid_weight_grad_kernel<<<grid, kThreads, smem, st>>>(grad_out_cl, feat_cl, query_xyz, support_xyz, idx, nvalid,
-                                                                query_mask, kpoints, B, M, N, C, nsample, K, extent,
-                                                                influence, (float*)ws);
+    if (precision == 1) {
+      const size_t smem_tc = 2 * kDwBufBytes + (size_t)kDwItems * (sizeof(int) + 3 * sizeof(float) + kK * sizeof(float)) + 16;
+      e = cudaFuncSetAttribute(pseudogrid_weight_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+      if (e != cudaSuccess) return (int)e;
+      pseudogrid_weight_grad_tc_kernel<<<grid, kThreads, smem_tc, st>>>(grad_out_cl, feat_cl, query_xyz, support_xyz, idx,
+                                                                       nvalid, query_mask, kpoints, B, M, N, C, nsample, K,
+                                                                       extent, influence, (float*)ws);
+    } else {
+      pseudogrid_weight_grad_kernel<<<grid, kThreads, smem, st>>>(grad_out_cl, feat_cl, query_xyz, support_xyz, idx, nvalid,
+                                                                  query_mask, kpoints, B, M, N, C, nsample, K, extent,
+                                                                  influence, (float*)ws);
+    }
     reduce_partials_kernel<<<d3d_ceil_div((long long)K * C, 256), 256, 0, st>>>((const float*)ws, nblk, K, C, grad_weights);
     d3d_note_launches(2);
   }

