@@ -379,11 +379,24 @@ def main():
         else:
             peak, which = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
         achieved = top["bytes_per_call"] / 1e6 / top["ms_per_call"]
+        # dram bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/), if there is one
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top_key)
+        sh = top["shape"]
+        gather = None
+        if top["op"] in ("pospool_fwd", "pospool_bwd", "pseudogrid_fwd", "pseudogrid_bwd", "gather_max_fwd", "gather_max_bwd"):
+            gb = 4 * sh["B"] * sh["M"] * max(sh.get("ns", 0), 1) * sh["C"]  # rows gathered through L2 (never materialised)
+            gather = {"l2_gather_bytes_per_launch": gb, "l2_gather_gbs": round(gb / 1e6 / top["ms_per_call"], 1)}
         roofline = {"bound": "hbm", "kernel": top_key, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": which,
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": which,
                     "algorithmic_bytes_per_launch": top["bytes_per_call"], "ms_per_launch": round(top["ms_per_call"], 4),
                     "share_of_step": round(top["ms_per_step"] / step_ms, 4),
-                    "our_kernels_share_of_step": round(ours_ms / step_ms, 4)}
+                    "our_kernels_share_of_step": round(ours_ms / step_ms, 4), "gather": gather,
+                    "note": "algorithmic bytes = compulsory HBM traffic (features + idx + xyz in, result out, DESIGN.md §3); "
+                            "the aggregation kernels are bound by the L2->SM gather of B*M*ns*C*4 bytes (reported under "
+                            "'gather'), the ball query by instruction issue (brute-force pair scan)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

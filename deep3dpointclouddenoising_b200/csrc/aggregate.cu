@@ -26,15 +26,17 @@ enum { kModePosPool = 0, kModeMax = 1, kModePlain = 2 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// weights of the 4 channels c..c+3 of a vector whose first channel has (c mod 3) == r
-__device__ __forceinline__ void rot3(const float4 w, int r, float& a, float& b, float& c) {
-  a = r == 0 ? w.x : (r == 1 ? w.y : w.z);
-  b = r == 0 ? w.y : (r == 1 ? w.z : w.x);
-  c = r == 0 ? w.z : (r == 1 ? w.x : w.y);
+// PosPool weight of channel c is (relative position)[c mod 3].  A float4 of channels starting at 4q needs the
+// components in the order r, r+1, r+2, r with r = (c_begin + 4q) mod 3 = (c_begin + q) mod 3: the staging code
+// writes the three rotations of every slot's weight once, a lane reads the one it needs with a single LDS.128.
+__device__ __forceinline__ void store_rotations(float4* dst, float x, float y, float z) {
+  dst[0] = make_float4(x, y, z, x);
+  dst[1] = make_float4(y, z, x, y);
+  dst[2] = make_float4(z, x, y, z);
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: warp per query
+// forward: warp per query.  Inner loop per (slot, float4 of channels): LDS.128 weight, LDG.128 row, 4 FFMA.
 // ------------------------------------------------------------------------------------------------
 template <int NV, int MODE>
 __global__ void __launch_bounds__(kWarps * 32)
@@ -43,12 +45,15 @@ aggregate_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ q
                      const int* __restrict__ nvalid, const int* __restrict__ query_mask, int M, int N, int C,
                      int c_begin, int nsample, float inv_radius, int reduction, float* __restrict__ out,
                      uint8_t* __restrict__ argslot) {
-  extern __shared__ __align__(16) float4 slot_smem[];
+  extern __shared__ __align__(16) unsigned char slot_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int j = blockIdx.x * kWarps + warp;
   if (j >= M) return;  // warp-uniform; no block-level barrier below
-  float4* sw = slot_smem + (size_t)warp * nsample;
+  // per warp: nsample row offsets (+ 3 weight rotations per slot for PosPool)
+  const size_t per_warp = (size_t)nsample * (MODE == kModePosPool ? 3 * sizeof(float4) : 0) + (((size_t)nsample * 4 + 15) & ~(size_t)15);
+  float4* sw = reinterpret_cast<float4*>(slot_smem + warp * per_warp);
+  int* soff = reinterpret_cast<int*>(slot_smem + warp * per_warp + (MODE == kModePosPool ? (size_t)nsample * 3 * sizeof(float4) : 0));
   const size_t qrow = (size_t)b * M + j;
   const int* irow = idx + qrow * nsample;
 
@@ -57,56 +62,45 @@ aggregate_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ q
     const float qx = query_xyz[qrow * 3], qy = query_xyz[qrow * 3 + 1], qz = query_xyz[qrow * 3 + 2];
     // feature_mask = idx_mask + (1 - query_mask): a padded query uses all nsample slots (:171)
     n_eff = query_mask[qrow] != 0 ? nvalid[qrow] : nsample;
-    for (int m = lane; m < nsample; m += 32) {
+    for (int m = lane; m < n_eff; m += 32) {
       const int i = d3d_clamp_index(irow[m], N);
       const float* s = support_xyz + ((size_t)b * N + i) * 3;
-      float4 w;
-      w.x = (s[0] - qx) * inv_radius;  // pt_utils.py:131-133 (the CUDA reference divides by multiplying with 1/radius)
-      w.y = (s[1] - qy) * inv_radius;
-      w.z = (s[2] - qz) * inv_radius;
-      w.w = __int_as_float(i);
-      sw[m] = w;
+      // pt_utils.py:131-133 (the CUDA reference divides by multiplying with 1/radius)
+      store_rotations(sw + 3 * m, (s[0] - qx) * inv_radius, (s[1] - qy) * inv_radius, (s[2] - qz) * inv_radius);
+      soff[m] = i * C;
     }
   } else {
-    for (int m = lane; m < nsample; m += 32) {
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      w.w = __int_as_float(d3d_clamp_index(irow[m], N));
-      sw[m] = w;
-    }
+    for (int m = lane; m < nsample; m += 32) soff[m] = d3d_clamp_index(irow[m], N) * C;
   }
   __syncwarp();
 
   const int cv = (C - c_begin) >> 2;  // vectors left in this pass
   float4 acc[NV];
   int arg[NV][4];
-  int rot[NV];
+  int qv[NV], rot[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float init = MODE == kModeMax ? -INFINITY : 0.0f;
     acc[v] = make_float4(init, init, init, init);
     arg[v][0] = arg[v][1] = arg[v][2] = arg[v][3] = 0;
-    rot[v] = (c_begin + 4 * (lane + 32 * v)) % 3;
+    qv[v] = min(lane + 32 * v, cv - 1);  // a lane beyond the last vector re-reads the last one; its result is dropped
+    rot[v] = (c_begin + qv[v]) % 3;
   }
   const float* fb = feat + (size_t)b * N * C + c_begin;
 #pragma unroll 4
   for (int m = 0; m < n_eff; ++m) {
-    const float4 w = sw[m];
-    const float* row = fb + (size_t)__float_as_int(w.w) * C;
+    const float* row = fb + soff[m];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int q = lane + 32 * v;
-      if (q < cv) {
-        const float4 x = ld4(row + 4 * q);
-        if (MODE == kModePosPool) {
-          float wa, wb, wc;
-          rot3(w, rot[v], wa, wb, wc);
-          acc[v].x += x.x * wa; acc[v].y += x.y * wb; acc[v].z += x.z * wc; acc[v].w += x.w * wa;
-        } else {  // max over all slots, first maximum wins (F.max_pool2d, pt_utils.py:202-205)
-          if (x.x > acc[v].x) { acc[v].x = x.x; arg[v][0] = m; }
-          if (x.y > acc[v].y) { acc[v].y = x.y; arg[v][1] = m; }
-          if (x.z > acc[v].z) { acc[v].z = x.z; arg[v][2] = m; }
-          if (x.w > acc[v].w) { acc[v].w = x.w; arg[v][3] = m; }
-        }
+      const float4 x = ld4(row + 4 * qv[v]);
+      if (MODE == kModePosPool) {
+        const float4 w = sw[3 * m + rot[v]];
+        acc[v].x += x.x * w.x; acc[v].y += x.y * w.y; acc[v].z += x.z * w.z; acc[v].w += x.w * w.w;
+      } else {  // max over all slots, first maximum wins (F.max_pool2d, pt_utils.py:202-205)
+        if (x.x > acc[v].x) { acc[v].x = x.x; arg[v][0] = m; }
+        if (x.y > acc[v].y) { acc[v].y = x.y; arg[v][1] = m; }
+        if (x.z > acc[v].z) { acc[v].z = x.z; arg[v][2] = m; }
+        if (x.w > acc[v].w) { acc[v].w = x.w; arg[v][3] = m; }
       }
     }
   }
@@ -131,19 +125,24 @@ aggregate_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ q
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: warp per support point, segment of the inverse map
+// backward: warp per support point, segment of the inverse map.  Segment lengths vary a lot (mean nsample, max
+// several hundred), so blocks are only kBwdWarps = 2 warps: a short segment does not hold a slot hostage.
 // ------------------------------------------------------------------------------------------------
+constexpr int kBwdWarps = 2;
+
 template <int NV, int MODE>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32)
 aggregate_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict__ query_xyz,
                      const float* __restrict__ support_xyz, const int* __restrict__ rowptr,
                      const int* __restrict__ entries, const int* __restrict__ nvalid,
                      const int* __restrict__ query_mask, const uint8_t* __restrict__ argslot, int M, int N, int C,
                      int c_begin, int nsample, float inv_radius, int reduction, float* __restrict__ grad_feat) {
-  __shared__ __align__(16) float4 stage[kWarps][32];
+  __shared__ __align__(16) float4 stage_w[kBwdWarps][32 * 3];
+  __shared__ int stage_off[kBwdWarps][32];
+  __shared__ int stage_k[kBwdWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int i = blockIdx.x * kWarps + warp;
+  const int i = blockIdx.x * kBwdWarps + warp;
   if (i >= N) return;
   const size_t srow = (size_t)b * N + i;
   const int beg = rowptr[srow], end = rowptr[srow + 1];
@@ -152,11 +151,12 @@ aggregate_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict
 
   const int cv = (C - c_begin) >> 2;
   float4 acc[NV];
-  int rot[NV];
+  int qv[NV], rot[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    rot[v] = (c_begin + 4 * (lane + 32 * v)) % 3;
+    qv[v] = min(lane + 32 * v, cv - 1);
+    rot[v] = (c_begin + qv[v]) % 3;
   }
   const float* gb = grad_out + (size_t)b * M * C + c_begin;
   const uint8_t* ab = MODE == kModeMax ? argslot + (size_t)b * M * C + c_begin : nullptr;
@@ -166,54 +166,41 @@ aggregate_bwd_kernel(const float* __restrict__ grad_out, const float* __restrict
     __syncwarp();
     if (lane < n_here) {
       const int packed = entries[e0 + lane];
-      int j = packed >> 8;
-      const int k = packed & 255;
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int j = packed >> 8, k = packed & 255;
       if (MODE == kModePosPool) {
         const size_t qrow = (size_t)b * M + j;
         const int n_eff = query_mask[qrow] != 0 ? nvalid[qrow] : nsample;
-        if (k < n_eff) {
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if (k < n_eff) {  // a masked slot keeps weight 0 (its row is still read: no branch in the inner loop)
           float scale = inv_radius;
-          w.x = (sx - query_xyz[qrow * 3]) * scale;
-          w.y = (sy - query_xyz[qrow * 3 + 1]) * scale;
-          w.z = (sz - query_xyz[qrow * 3 + 2]) * scale;
-          if (reduction == D3D_REDUCE_AVG) {
-            const float den = (float)n_eff;
-            w.x /= den; w.y /= den; w.z /= den;
-          }
-        } else {
-          j = -1;  // masked slot: contributes nothing
+          if (reduction == D3D_REDUCE_AVG) scale /= (float)n_eff;
+          wx = (sx - query_xyz[qrow * 3]) * scale;
+          wy = (sy - query_xyz[qrow * 3 + 1]) * scale;
+          wz = (sz - query_xyz[qrow * 3 + 2]) * scale;
         }
+        store_rotations(&stage_w[warp][3 * lane], wx, wy, wz);
       } else if (MODE == kModeMax) {
-        w.x = __int_as_float(k);
+        stage_k[warp][lane] = k;
       }
-      w.w = __int_as_float(j);
-      stage[warp][lane] = w;
+      stage_off[warp][lane] = j * C;
     }
     __syncwarp();
 #pragma unroll 4
     for (int t = 0; t < n_here; ++t) {
-      const float4 w = stage[warp][t];
-      const int j = __float_as_int(w.w);
-      if (j < 0) continue;  // warp-uniform
-      const float* row = gb + (size_t)j * C;
+      const float* row = gb + stage_off[warp][t];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        const int q = lane + 32 * v;
-        if (q < cv) {
-          const float4 g = ld4(row + 4 * q);
-          if (MODE == kModePosPool) {
-            float wa, wb, wc;
-            rot3(w, rot[v], wa, wb, wc);
-            acc[v].x += g.x * wa; acc[v].y += g.y * wb; acc[v].z += g.z * wc; acc[v].w += g.w * wa;
-          } else if (MODE == kModeMax) {
-            const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(ab + (size_t)j * C + 4 * q));
-            const int k = __float_as_int(w.x);
-            acc[v].x += a.x == k ? g.x : 0.f; acc[v].y += a.y == k ? g.y : 0.f;
-            acc[v].z += a.z == k ? g.z : 0.f; acc[v].w += a.w == k ? g.w : 0.f;
-          } else {
-            acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
-          }
+        const float4 g = ld4(row + 4 * qv[v]);
+        if (MODE == kModePosPool) {
+          const float4 w = stage_w[warp][3 * t + rot[v]];
+          acc[v].x += g.x * w.x; acc[v].y += g.y * w.y; acc[v].z += g.z * w.z; acc[v].w += g.w * w.w;
+        } else if (MODE == kModeMax) {
+          const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(ab + stage_off[warp][t] + 4 * qv[v]));
+          const int k = stage_k[warp][t];
+          acc[v].x += a.x == k ? g.x : 0.f; acc[v].y += a.y == k ? g.y : 0.f;
+          acc[v].z += a.z == k ? g.z : 0.f; acc[v].w += a.w == k ? g.w : 0.f;
+        } else {
+          acc[v].x += g.x; acc[v].y += g.y; acc[v].z += g.z; acc[v].w += g.w;
         }
       }
     }
@@ -252,7 +239,8 @@ template <int MODE>
 int launch_fwd(const float* feat, const float* q, const float* s, const int* idx, const int* nvalid, const int* qm,
                int B, int M, int N, int C, int ns, float inv_r, int reduction, float* out, uint8_t* arg,
                cudaStream_t st) {
-  const size_t smem = (size_t)kWarps * ns * sizeof(float4);
+  const size_t per_warp = (size_t)ns * (MODE == kModePosPool ? 3 * sizeof(float4) : 0) + (((size_t)ns * 4 + 15) & ~(size_t)15);
+  const size_t smem = (size_t)kWarps * per_warp;
   dim3 grid(d3d_ceil_div(M, kWarps), B);
   for (int c0 = 0; c0 < C; c0 += kMaxNV * 128) {
     const int cv = (C - c0) / 4;
@@ -276,11 +264,11 @@ template <int MODE>
 int launch_bwd(const float* gout, const float* q, const float* s, const int* rowptr, const int* entries,
                const int* nvalid, const int* qm, const uint8_t* arg, int B, int M, int N, int C, int ns, float inv_r,
                int reduction, float* gfeat, cudaStream_t st) {
-  dim3 grid(d3d_ceil_div(N, kWarps), B);
+  dim3 grid(d3d_ceil_div(N, kBwdWarps), B);
   for (int c0 = 0; c0 < C; c0 += kMaxNV * 128) {
     const int cv = (C - c0) / 4;
 #define D3D_BWD(NVV)                                                                                              \
-  aggregate_bwd_kernel<NVV, MODE><<<grid, kWarps * 32, 0, st>>>(gout, q, s, rowptr, entries, nvalid, qm, arg, M, N, C, \
+  aggregate_bwd_kernel<NVV, MODE><<<grid, kBwdWarps * 32, 0, st>>>(gout, q, s, rowptr, entries, nvalid, qm, arg, M, N, C, \
                                                                 c0, ns, inv_r, reduction, gfeat)
     switch (pick_nv(cv)) {
       case 1: D3D_BWD(1); break;

@@ -51,22 +51,34 @@ def test_fused_bn_matches_torch(cuda_device, B, C, N, relu, residual):
 
 
 def test_model_with_and_without_fused_bn_agree(cuda_device):
-    import numpy as np
+    """Whole U-Net, fused BN kernels vs torch/cuDNN BatchNorm+ReLU.  TF32 is switched off for the convolutions so
+    that only BN rounding differs; the deepest level still normalises over few samples (B*N/128), which amplifies
+    1e-7 differences, hence the comparison in relative Frobenius norm."""
     from deep3dpointclouddenoising_b200 import synthetic
     from deep3dpointclouddenoising_b200.utils.config import runtime
     import bench
-    model, criterion, cfg = bench.build_model("pospool", 1024)
-    model = model.to(cuda_device)
-    batch = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(3, 2, 1024, ragged=True)]
-    outs = []
-    state = {k: v.clone() for k, v in model.state_dict().items()}
-    for flag in (True, False):
-        runtime.fused_batchnorm = flag
-        model.load_state_dict(state)
-        model.zero_grad(set_to_none=True)
-        pred = model(batch[0], batch[1], batch[2])
-        loss = criterion(pred.transpose(1, 2), batch[3], batch[1])
-        loss.backward()
-        outs.append((pred.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}))
-    runtime.fused_batchnorm = True
-    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=2e-3, atol=2e-3)  # 30+ stacked layers, TF32 convolutions
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model, criterion, cfg = bench.build_model("pospool", 4096)
+        model = model.to(cuda_device)
+        batch = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(3, 4, 4096, ragged=True)]
+        outs = []
+        state = {k: v.clone() for k, v in model.state_dict().items()}
+        for flag in (True, False):
+            runtime.fused_batchnorm = flag
+            model.load_state_dict(state)
+            model.zero_grad(set_to_none=True)
+            pred = model(batch[0], batch[1], batch[2])
+            loss = criterion(pred.transpose(1, 2), batch[3], batch[1])
+            loss.backward()
+            outs.append((pred.detach().clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    finally:
+        runtime.fused_batchnorm = True
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    rel = ((outs[0][0] - outs[1][0]).norm() / outs[1][0].norm()).item()
+    assert rel < 1e-3, rel
+    assert abs(outs[0][1] - outs[1][1]) < 1e-4 * max(1.0, abs(outs[1][1]))
+    g0 = torch.cat([g.flatten() for g in outs[0][2].values()])
+    g1 = torch.cat([g.flatten() for g in outs[1][2].values()])
+    assert ((g0 - g1).norm() / g1.norm()).item() < 1e-2
