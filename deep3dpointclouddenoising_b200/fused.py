@@ -107,16 +107,18 @@ class BatchNormActFunction(Function):
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
         y, mean, invstd = ops.bn_act_fwd(x, res, weight, bias, running_mean, running_var, eps, momentum, training, relu)
-        ctx.training, ctx.relu, ctx.has_res = training, relu, residual is not None
-        ctx.save_for_backward(x, y if relu else None, weight, mean, invstd)
+        ctx.training, ctx.has_res = training, residual is not None
+        # the ReLU mask is recomputed from x in backward unless a residual was added (then y itself is needed)
+        ctx.relu_mode = 0 if not relu else (2 if residual is not None else 1)
+        ctx.save_for_backward(x, y if ctx.relu_mode == 2 else None, weight, bias, mean, invstd)
         return y
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, y, weight, mean, invstd = ctx.saved_tensors
-        dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, mean, invstd, ctx.training, ctx.relu,
-                                                 ctx.has_res and ctx.needs_input_grad[1])
-        return (dx, dres, dgamma if weight is not None else None, dbeta if weight is not None else None, None, None, None,
+        x, y, weight, bias, mean, invstd = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, bias, mean, invstd, ctx.training,
+                                                 ctx.relu_mode, ctx.has_res and ctx.needs_input_grad[1])
+        return (dx, dres, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
                 None, None, None)
 
 

@@ -296,6 +296,20 @@ def nearest_gather_bwd(grad_out_cl, rowptr, entries, n_support):
 # ------------------------------------------------------------------------------------------------
 # fused BatchNorm1d (+ residual) (+ ReLU), channel-major tensors
 # ------------------------------------------------------------------------------------------------
+_bn_workspaces = {}
+
+
+def _bn_ws(device, C):
+    """Zero-initialised, reused workspace of the split channel reductions (one per device and channel count; the
+    kernels leave the ticket counters zero; all launches of this process go to the current stream)."""
+    key = (device, C)
+    ws = _bn_workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(_lib.load().d3d_bn_act_workspace_bytes(C), dtype=torch.uint8, device=device)
+        _bn_workspaces[key] = ws
+    return ws
+
+
 def bn_act_fwd(x, residual, gamma, beta, running_mean, running_var, eps, momentum, training, relu):
     L = _lib.load()
     x = _f32(x, "input")
@@ -304,14 +318,16 @@ def bn_act_fwd(x, residual, gamma, beta, running_mean, running_var, eps, momentu
         y = torch.empty_like(x)
         mean = torch.empty((C,), dtype=torch.float32, device=x.device)
         invstd = torch.empty((C,), dtype=torch.float32, device=x.device)
+        ws = _bn_ws(x.device, C)
         _lib.check(L.d3d_bn_act_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(running_mean), _p(running_var), B, C, N,
                                     float(eps), float(momentum), int(bool(training)), int(bool(relu)), _p(y), _p(mean),
-                                    _p(invstd), _stream()), "d3d_bn_act_fwd")
+                                    _p(invstd), _p(ws), ws.numel(), _stream()), "d3d_bn_act_fwd")
     _count()
     return y, mean, invstd
 
 
-def bn_act_bwd(dy, x, y, gamma, mean, invstd, training, relu, need_res):
+def bn_act_bwd(dy, x, y, gamma, beta, mean, invstd, training, relu_mode, need_res):
+    """relu_mode: 0 none, 1 ReLU mask recomputed from x (no residual), 2 mask from y."""
     L = _lib.load()
     dy = _f32(dy, "grad_out")
     B, C, N = dy.shape
@@ -320,9 +336,9 @@ def bn_act_bwd(dy, x, y, gamma, mean, invstd, training, relu, need_res):
         dres = torch.empty_like(dy) if need_res else None
         dgamma = torch.empty((C,), dtype=torch.float32, device=dy.device)
         dbeta = torch.empty((C,), dtype=torch.float32, device=dy.device)
-        ws = _ws(L.d3d_bn_act_bwd_workspace_bytes(C), dy.device)
-        _lib.check(L.d3d_bn_act_bwd(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(invstd), B, C, N, int(bool(training)),
-                                    int(bool(relu)), _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()),
-                   "d3d_bn_act_bwd")
+        ws = _bn_ws(dy.device, C)
+        _lib.check(L.d3d_bn_act_bwd(_p(dy), _p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(invstd), B, C, N,
+                                    int(bool(training)), int(relu_mode), _p(dx), _p(dres), _p(dgamma), _p(dbeta), _p(ws),
+                                    ws.numel(), _stream()), "d3d_bn_act_bwd")
     _count()
     return dx, dres, dgamma, dbeta

@@ -171,14 +171,17 @@ int d3d_nearest_gather_bwd(const float* grad_out_cl, const int* rowptr, const in
  *    statistics and updates running_mean / running_var in place, else the running statistics are used.
  *    y = act(bn(x) [+ residual]).  save_mean / save_invstd (C) are outputs the backward pass needs.
  * ---------------------------------------------------------------------------------------------- */
+/* Workspace shared by both directions: d3d_bn_act_workspace_bytes(C) bytes that are ZERO before the first use
+ * (ticket counters of the split channel reductions; the kernels leave them zero).  One workspace per stream. */
+size_t d3d_bn_act_workspace_bytes(int C);
 int d3d_bn_act_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
                    float* running_var, int B, int C, int N, float eps, float momentum, int training, int relu,
-                   float* y, float* save_mean, float* save_invstd, void* stream);
-/* dx (and dres = gradient w.r.t. residual, may be NULL; dgamma / dbeta (C), may be NULL).  y is needed when relu. */
-size_t d3d_bn_act_bwd_workspace_bytes(int C);
-int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* save_mean,
-                   const float* save_invstd, int B, int C, int N, int training, int relu, float* dx, float* dres,
-                   float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+                   float* y, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, void* stream);
+/* dx (and dres = gradient w.r.t. residual, may be NULL; dgamma / dbeta (C), may be NULL).
+ * relu: 0 = none, 1 = ReLU without residual (mask recomputed from x, y may be NULL), 2 = ReLU mask read from y. */
+int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* beta,
+                   const float* save_mean, const float* save_invstd, int B, int C, int N, int training, int relu,
+                   float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }
