@@ -40,6 +40,10 @@ SIGNATURES = {
     "d3d_gather_max_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "d3d_nearest_gather_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "d3d_nearest_gather_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "d3d_nn_workspace_bytes": (_sz, [_i]),
+    "d3d_nn_sqdist": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "d3d_chamfer_workspace_bytes": (_sz, [_i, _i]),
+    "d3d_chamfer_l2": (_i, [_vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     "d3d_bn_act_workspace_bytes": (_sz, [_i]),
     "d3d_bn_act_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_bn_act_bwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),

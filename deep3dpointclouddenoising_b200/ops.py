@@ -342,3 +342,33 @@ def bn_act_bwd(dy, x, y, gamma, beta, mean, invstd, training, relu_mode, need_re
                                     ws.numel(), _stream()), "d3d_bn_act_bwd")
     _count()
     return dx, dres, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------
+# exact nearest neighbours / Chamfer distance on large clouds
+# ------------------------------------------------------------------------------------------------
+def nn_sqdist(query_xyz, support_xyz, want_idx=False):
+    """(M,3),(N,3) -> squared distance to the nearest support (M,), optionally its index."""
+    L = _lib.load()
+    q, s = _f32(query_xyz, "query_xyz"), _f32(support_xyz, "support_xyz")
+    M, N = q.shape[0], s.shape[0]
+    with torch.cuda.device(q.device):
+        d2 = torch.empty((M,), dtype=torch.float32, device=q.device)
+        idx = torch.empty((M,), dtype=torch.int32, device=q.device) if want_idx else None
+        ws = _ws(L.d3d_nn_workspace_bytes(N), q.device)
+        _lib.check(L.d3d_nn_sqdist(_p(q), _p(s), M, N, _p(d2), _p(idx), _p(ws), ws.numel(), _stream()), "d3d_nn_sqdist")
+    _count()
+    return (d2, idx) if want_idx else d2
+
+
+def chamfer_l2(x, y):
+    """(Nx,3),(Ny,3) -> tensor [cham_x + cham_y, cham_x, cham_y] (chamfer_distance_aux.py, L2, mean reductions)."""
+    L = _lib.load()
+    x, y = _f32(x, "x"), _f32(y, "y")
+    with torch.cuda.device(x.device):
+        out = torch.empty((3,), dtype=torch.float32, device=x.device)
+        ws = _ws(L.d3d_chamfer_workspace_bytes(x.shape[0], y.shape[0]), x.device)
+        _lib.check(L.d3d_chamfer_l2(_p(x), _p(y), x.shape[0], y.shape[0], _p(out), _p(ws), ws.numel(), _stream()),
+                   "d3d_chamfer_l2")
+    _count()
+    return out

@@ -183,6 +183,18 @@ int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float*
                    const float* save_mean, const float* save_invstd, int B, int C, int N, int training, int relu,
                    float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * 5. Exact nearest neighbours on large clouds and the Chamfer distance
+ *    ref: compute_cd.py:74-75; models/losses/chamfer_distance_aux.py:154-155,216-246 (pytorch3d knn_points, K = 1)
+ * ---------------------------------------------------------------------------------------------- */
+/* out_d2[j] = min_i |q_j - s_i|^2 (and out_idx[j], may be NULL: lowest index among equal distances); clouds (M,3), (N,3). */
+size_t d3d_nn_workspace_bytes(int N);
+int d3d_nn_sqdist(const float* query_xyz, const float* support_xyz, int M, int N, float* out_d2, int* out_idx,
+                  void* ws, size_t ws_bytes, void* stream);
+/* out3 = { mean_x min_y |x-y|^2 + mean_y min_x |x-y|^2,  first term,  second term }  (L2, point reduction mean) */
+size_t d3d_chamfer_workspace_bytes(int Nx, int Ny);
+int d3d_chamfer_l2(const float* x, const float* y, int Nx, int Ny, float* out3, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
