@@ -165,7 +165,9 @@ __global__ void cell_fill_kernel(const float* __restrict__ s, int N, const int* 
   sorted[pos] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __int_as_float(i));
 }
 
-// thread per query: expanding cube shells of cells
+// thread per query: expanding cube shells of cells.  kDouble: distances in fp64 (what a KD-tree on float64 copies of
+// the data decides, used where the INDEX must match the reference's sklearn search; fp32 otherwise).
+template <bool kDouble>
 __global__ void __launch_bounds__(128)
 nn_query_kernel(const float* __restrict__ q, int M, const GridParams* __restrict__ gp, const int* __restrict__ cell_start,
                 int n_cells, int N, const float4* __restrict__ sorted, float* __restrict__ out_d2, int* __restrict__ out_idx) {
@@ -176,16 +178,23 @@ nn_query_kernel(const float* __restrict__ q, int M, const GridParams* __restrict
   const float qx = q[3 * (size_t)j], qy = q[3 * (size_t)j + 1], qz = q[3 * (size_t)j + 2];
   const int cx = cell_coord(qx, p.min_x, p.inv_cell, G), cy = cell_coord(qy, p.min_y, p.inv_cell, G), cz = cell_coord(qz, p.min_z, p.inv_cell, G);
   float best = INFINITY;
+  double best_d = INFINITY;
   int best_i = -1;
   auto visit = [&](int x, int y, int z) {
     const int c = (z * G + y) * G + x;
     const int beg = cell_start[c], end = c + 1 < n_cells ? cell_start[c + 1] : N;
     for (int t = beg; t < end; ++t) {
       const float4 s = __ldg(sorted + t);
-      const float dx = qx - s.x, dy = qy - s.y, dz = qz - s.z;
-      const float d2 = dx * dx + dy * dy + dz * dz;
       const int si = __float_as_int(s.w);
-      if (d2 < best || (d2 == best && si < best_i)) { best = d2; best_i = si; }
+      if (kDouble) {
+        const double dx = (double)qx - (double)s.x, dy = (double)qy - (double)s.y, dz = (double)qz - (double)s.z;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < best_d || (d2 == best_d && si < best_i)) { best_d = d2; best = (float)d2; best_i = si; }
+      } else {
+        const float dx = qx - s.x, dy = qy - s.y, dz = qz - s.z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < best || (d2 == best && si < best_i)) { best = d2; best_i = si; }
+      }
     }
   };
   for (int r = 0; r < G; ++r) {
@@ -275,7 +284,7 @@ NnWs carve_nn(void* ws, int N) {
   return w;
 }
 
-int nn_search(const float* q, const float* s, int M, int N, float* out_d2, int* out_idx, void* ws, cudaStream_t st) {
+int build_grid(const float* s, int N, void* ws, cudaStream_t st, NnWs* out) {
   NnWs w = carve_nn(ws, N);
   const int G = grid_size_for(N);
   const int cells = G * G * G;
@@ -288,14 +297,42 @@ int nn_search(const float* q, const float* s, int M, int N, float* out_d2, int* 
   scan_totals_kernel<<<1, 1024, 0, st>>>(w.block_tot, nblk);
   scan_add_kernel<<<nblk, 1024, 0, st>>>(w.cell_start, cells, w.block_tot, w.cursor);
   cell_fill_kernel<<<d3d_ceil_div(N, 256), 256, 0, st>>>(s, N, w.cell_of, w.cursor, w.sorted);
-  nn_query_kernel<<<d3d_ceil_div(M, 128), 128, 0, st>>>(q, M, w.gp, w.cell_start, cells, N, w.sorted, out_d2, out_idx);
-  d3d_note_launches(7);
+  d3d_note_launches(6);
+  *out = w;
+  return d3d_launch_status();
+}
+
+int nn_search(const float* q, const float* s, int M, int N, float* out_d2, int* out_idx, void* ws, cudaStream_t st,
+              bool precise = false) {
+  NnWs w;
+  const int rc = build_grid(s, N, ws, st, &w);
+  if (rc != 0) return rc;
+  const int G = grid_size_for(N);
+  if (precise)
+    nn_query_kernel<true><<<d3d_ceil_div(M, 128), 128, 0, st>>>(q, M, w.gp, w.cell_start, G * G * G, N, w.sorted, out_d2, out_idx);
+  else
+    nn_query_kernel<false><<<d3d_ceil_div(M, 128), 128, 0, st>>>(q, M, w.gp, w.cell_start, G * G * G, N, w.sorted, out_d2, out_idx);
+  d3d_note_launches(1);
   return d3d_launch_status();
 }
 
 constexpr int kSumBlocks = 512;
 
 }  // namespace
+
+// shared with patches.cu (radius patches walk the same grid)
+int d3d_internal_build_grid(const float* s, int N, int G_override, void* ws, cudaStream_t st, void** gp_dev, int** cell_start,
+                            float4** sorted, int* G_out) {
+  (void)G_override;
+  NnWs w;
+  const int rc = build_grid(s, N, ws, st, &w);
+  *gp_dev = w.gp; *cell_start = w.cell_start; *sorted = w.sorted; *G_out = grid_size_for(N);
+  return rc;
+}
+size_t d3d_internal_grid_bytes(int N, int G_override) {
+  (void)G_override;
+  return carve_nn(nullptr, N).bytes;
+}
 
 extern "C" {
 
@@ -304,13 +341,13 @@ size_t d3d_nn_workspace_bytes(int N) {
   return carve_nn(nullptr, N).bytes;
 }
 
-int d3d_nn_sqdist(const float* query_xyz, const float* support_xyz, int M, int N, float* out_d2, int* out_idx, void* ws,
-                  size_t ws_bytes, void* stream) {
+int d3d_nn_sqdist(const float* query_xyz, const float* support_xyz, int M, int N, int precise, float* out_d2, int* out_idx,
+                  void* ws, size_t ws_bytes, void* stream) {
   D3D_REQUIRE(query_xyz && support_xyz && out_d2);
   D3D_REQUIRE(M >= 0 && N > 0);
   if (M == 0) return 0;
   if (!ws || ws_bytes < d3d_nn_workspace_bytes(N)) return D3D_ERR_WORKSPACE;
-  return nn_search(query_xyz, support_xyz, M, N, out_d2, out_idx, ws, (cudaStream_t)stream);
+  return nn_search(query_xyz, support_xyz, M, N, out_d2, out_idx, ws, (cudaStream_t)stream, precise != 0);
 }
 
 size_t d3d_chamfer_workspace_bytes(int Nx, int Ny) {

@@ -347,7 +347,7 @@ def bn_act_bwd(dy, x, y, gamma, beta, mean, invstd, training, relu_mode, need_re
 # ------------------------------------------------------------------------------------------------
 # exact nearest neighbours / Chamfer distance on large clouds
 # ------------------------------------------------------------------------------------------------
-def nn_sqdist(query_xyz, support_xyz, want_idx=False):
+def nn_sqdist(query_xyz, support_xyz, want_idx=False, precise=False):
     """(M,3),(N,3) -> squared distance to the nearest support (M,), optionally its index."""
     L = _lib.load()
     q, s = _f32(query_xyz, "query_xyz"), _f32(support_xyz, "support_xyz")
@@ -356,7 +356,8 @@ def nn_sqdist(query_xyz, support_xyz, want_idx=False):
         d2 = torch.empty((M,), dtype=torch.float32, device=q.device)
         idx = torch.empty((M,), dtype=torch.int32, device=q.device) if want_idx else None
         ws = _ws(L.d3d_nn_workspace_bytes(N), q.device)
-        _lib.check(L.d3d_nn_sqdist(_p(q), _p(s), M, N, _p(d2), _p(idx), _p(ws), ws.numel(), _stream()), "d3d_nn_sqdist")
+        _lib.check(L.d3d_nn_sqdist(_p(q), _p(s), M, N, int(bool(precise)), _p(d2), _p(idx), _p(ws), ws.numel(), _stream()),
+                   "d3d_nn_sqdist")
     _count()
     return (d2, idx) if want_idx else d2
 
@@ -372,3 +373,55 @@ def chamfer_l2(x, y):
                    "d3d_chamfer_l2")
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# full-shape inference support
+# ------------------------------------------------------------------------------------------------
+def voxel_ids(points, origin, dl, nx, ny, n_cells):
+    L = _lib.load()
+    p = _f32(points, "points")
+    with torch.cuda.device(p.device):
+        ids = torch.empty((p.shape[0],), dtype=torch.int32, device=p.device)
+        _lib.check(L.d3d_voxel_ids(_p(p), p.shape[0], float(origin[0]), float(origin[1]), float(origin[2]), float(dl), int(nx),
+                                   int(ny), int(n_cells), _p(ids), _stream()), "d3d_voxel_ids")
+    _count()
+    return ids
+
+
+def voxel_barycentres(points, rowptr, entries, n_cells):
+    L = _lib.load()
+    p = _f32(points, "points")
+    with torch.cuda.device(p.device):
+        bary = torch.zeros((n_cells, 3), dtype=torch.float32, device=p.device)
+        counts = torch.empty((n_cells,), dtype=torch.int32, device=p.device)
+        _lib.check(L.d3d_voxel_barycentres(_p(p), _p(rowptr), _p(entries), int(n_cells), _p(bary), _p(counts), _stream()),
+                   "d3d_voxel_barycentres")
+    _count()
+    return bary, counts
+
+
+def radius_patches(points, centres, radius, num_points, overflow_stride=0):
+    L = _lib.load()
+    p, c = _f32(points, "points"), _f32(centres, "centres")
+    N, P = p.shape[0], c.shape[0]
+    with torch.cuda.device(p.device):
+        idx = torch.empty((P, num_points), dtype=torch.int32, device=p.device)
+        cnt = torch.empty((P,), dtype=torch.int32, device=p.device)
+        ws = _ws(L.d3d_radius_patches_workspace_bytes(N, P, int(overflow_stride)), p.device)
+        _lib.check(L.d3d_radius_patches(_p(p), N, _p(c), P, float(radius), int(num_points), int(overflow_stride), _p(idx),
+                                        _p(cnt), _p(ws), ws.numel(), _stream()), "d3d_radius_patches")
+    _count()
+    return idx, cnt
+
+
+def vote_mean(pred, rowptr, entries, n_points, num_points):
+    L = _lib.load()
+    pr = _f32(pred, "pred")
+    with torch.cuda.device(pr.device):
+        mean = torch.empty((n_points, 3), dtype=torch.float32, device=pr.device)
+        votes = torch.empty((n_points,), dtype=torch.float32, device=pr.device)
+        _lib.check(L.d3d_vote_mean(_p(pr), _p(rowptr), _p(entries), int(n_points), int(num_points), _p(mean), _p(votes),
+                                   _stream()), "d3d_vote_mean")
+    _count()
+    return mean, votes

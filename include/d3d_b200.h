@@ -187,13 +187,37 @@ int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float*
  * 5. Exact nearest neighbours on large clouds and the Chamfer distance
  *    ref: compute_cd.py:74-75; models/losses/chamfer_distance_aux.py:154-155,216-246 (pytorch3d knn_points, K = 1)
  * ---------------------------------------------------------------------------------------------- */
-/* out_d2[j] = min_i |q_j - s_i|^2 (and out_idx[j], may be NULL: lowest index among equal distances); clouds (M,3), (N,3). */
+/* out_d2[j] = min_i |q_j - s_i|^2 (and out_idx[j], may be NULL: lowest index among equal distances); clouds (M,3), (N,3).
+ * precise != 0 compares distances in fp64 (the decision a float64 KD-tree takes: used for patch-centre indices). */
 size_t d3d_nn_workspace_bytes(int N);
-int d3d_nn_sqdist(const float* query_xyz, const float* support_xyz, int M, int N, float* out_d2, int* out_idx,
+int d3d_nn_sqdist(const float* query_xyz, const float* support_xyz, int M, int N, int precise, float* out_d2, int* out_idx,
                   void* ws, size_t ws_bytes, void* stream);
 /* out3 = { mean_x min_y |x-y|^2 + mean_y min_x |x-y|^2,  first term,  second term }  (L2, point reduction mean) */
 size_t d3d_chamfer_workspace_bytes(int Nx, int Ny);
 int d3d_chamfer_l2(const float* x, const float* y, int Nx, int Ny, float* out3, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 6. Full-shape inference support
+ *    ref: offset_dataset.py:540-561 (patch centres), :630-656 (radius patches, sorted by distance, first num_points),
+ *         qualitative_inference_test.py:325-342 (vote averaging), cpp_subsampling/grid_subsampling/grid_subsampling.cpp:25-103
+ * ---------------------------------------------------------------------------------------------- */
+/* voxel id of every point (ids (N,) int32, clamped to [0, n_cells)): iX + NX*iY + NX*NY*iZ with
+ * i? = floor((p.? - origin.?) / dl) — the reference's CPU expressions; origin / NX / NY come from the caller. */
+int d3d_voxel_ids(const float* points, int N, float origin_x, float origin_y, float origin_z, float dl, int NX, int NY,
+                  int n_cells, int* ids, void* stream);
+/* per-voxel barycentre from the inverse map of the voxel ids (d3d_build_inverse_map with B = 1, nsample = 1):
+ * members added in ascending point index in fp32, times (float)(1.0 / count).  bary (n_cells, 3), counts (n_cells). */
+int d3d_voxel_barycentres(const float* points, const int* rowptr, const int* entries, int n_cells, float* bary,
+                          int* counts, void* stream);
+/* radius patches: out_idx (P, num_points) = indices of the points within `radius` of each centre in ascending
+ * distance (ties: lower index), -1 padded; out_count (P) = points in the ball.  See patches.cu for overflow_stride. */
+size_t d3d_radius_patches_workspace_bytes(int N, int P, int overflow_stride);
+int d3d_radius_patches(const float* points, int N, const float* centres, int P, float radius, int num_points,
+                       int overflow_stride, int* out_idx, int* out_count, void* ws, size_t ws_bytes, void* stream);
+/* per-point mean of the predictions that voted for it: pred (P, 3, num_points), inverse map of the (flattened,
+ * 128-slot rows) patch indices; mean_offset (N, 3) = sum / (count + 1e-7); votes (N) may be NULL. */
+int d3d_vote_mean(const float* pred, const int* rowptr, const int* entries, int N, int num_points, float* mean_offset,
+                  float* votes, void* stream);
 
 #ifdef __cplusplus
 }

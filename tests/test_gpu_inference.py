@@ -1,0 +1,117 @@
+"""GPU parity, row f2: patch centres, radius patches and vote averaging against the reference's own building blocks
+(its CPU grid_subsampling.cpp through oracle/_ref/libref_gridsub.so when present, sklearn's KDTree — the class the
+reference dataset uses — and numpy vote accumulation as in qualitative_inference_test.py:325-342)."""
+import numpy as np
+import pytest
+import torch
+from sklearn.neighbors import KDTree
+
+from deep3dpointclouddenoising_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(n, seed):
+    return synthetic.make_cloud(seed, n, sigma=0.004)
+
+
+def _numpy_barycentres(pts, dl):
+    """grid_subsampling.cpp:25-103 restated (float32), voxels in ascending id."""
+    dl32 = np.float32(dl)
+    inv = np.float32(1.0) / dl32
+    origin = (np.floor(pts.min(0) * inv) * dl32).astype(np.float32)
+    mx = pts.max(0)
+    nx = int(np.floor((mx[0] - origin[0]) / dl32)) + 1
+    ny = int(np.floor((mx[1] - origin[1]) / dl32)) + 1
+    ijk = np.floor((pts - origin) / dl32).astype(np.int64)
+    ids = ijk[:, 0] + nx * ijk[:, 1] + nx * ny * ijk[:, 2]
+    out = []
+    for v in np.unique(ids):
+        s = np.zeros(3, np.float32)
+        members = np.nonzero(ids == v)[0]
+        for i in members:  # ascending point index, fp32 accumulation like SampledData::update_points
+            s = (s + pts[i]).astype(np.float32)
+        out.append(s * np.float32(1.0 / len(members)))
+    return np.stack(out)
+
+
+def test_voxel_barycentres_match_reference_cpu(cuda_device):
+    from deep3dpointclouddenoising_b200 import inference
+    from oracle import cpu_index_ops
+    pts = _cloud(6000, 1)
+    bary, counts = inference.voxel_barycentres(torch.from_numpy(pts).to(cuda_device), 0.05)
+    got = bary.cpu().numpy()
+    assert np.array_equal(got, _numpy_barycentres(pts, 0.05))
+    assert int(counts.sum()) == 6000
+    try:
+        ref = cpu_index_ops.ref_gridsub_cpu().compute(pts, 0.05)  # the reference's own C++ (hash-map order)
+    except (FileNotFoundError, OSError):
+        return
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(got), key(ref))
+
+
+def test_radius_patches_match_kdtree(cuda_device):
+    from deep3dpointclouddenoising_b200 import inference, ops
+    pts = _cloud(30000, 2)
+    dpts = torch.from_numpy(pts).to(cuda_device)
+    centre_idx = inference.patch_centres(dpts, 0.05)
+    tree = KDTree(pts)
+    # centres: the nearest real point to every barycentre (offset_dataset.py:553 tree.query(sub_pc, k=1))
+    bary = inference.voxel_barycentres(dpts, 0.05)[0].cpu().numpy()
+    ref_centres = tree.query(bary, k=1, return_distance=False)[:, 0]
+    mine = centre_idx.cpu().numpy()
+    differ = np.nonzero(mine != ref_centres)[0]  # only exact distance ties (duplicate points) may resolve differently:
+    assert len(differ) < 0.01 * len(mine)        # ours -> lowest index, sklearn -> unspecified
+    d_mine = np.linalg.norm(pts[mine[differ]].astype(np.float64) - bary[differ], axis=1)
+    d_ref = np.linalg.norm(pts[ref_centres[differ]].astype(np.float64) - bary[differ], axis=1)
+    assert np.array_equal(d_mine, d_ref) and (mine[differ] < ref_centres[differ]).all()
+    for num_points in (512, 4096):
+        idx, cnt = ops.radius_patches(dpts, dpts[centre_idx].contiguous(), 0.05, num_points)
+        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+        ref_idx, ref_d = tree.query_radius(pts[centre_idx.cpu().numpy()], r=0.05, return_distance=True, sort_results=True)
+        for p in range(0, len(ref_idx), 7):
+            assert cnt[p] == len(ref_idx[p])
+            take = min(cnt[p], num_points)
+            got = idx[p, :take]
+            if not np.array_equal(got, ref_idx[p][:take]):  # only the order inside groups of equal distance may differ
+                d_got = np.linalg.norm(pts[got].astype(np.float64) - pts[centre_idx[p].item()], axis=1)
+                np.testing.assert_allclose(d_got, ref_d[p][:take], rtol=1e-12, atol=1e-12)
+            assert (idx[p, take:] == -1).all()
+
+
+def test_extract_and_vote(cuda_device):
+    from deep3dpointclouddenoising_b200 import inference, ops
+    pts = _cloud(20000, 3)
+    dpts = torch.from_numpy(pts).to(cuda_device)
+    centre_idx = inference.patch_centres(dpts, 0.05)
+    n_pts = 1024
+    p, mask, feats, inds = inference.extract_patches(dpts, centre_idx, 0.05, n_pts, seed=1)
+    P = p.shape[0]
+    assert torch.equal(inds[:, 0], centre_idx) and (p[:, 0].abs().max() == 0)
+    assert torch.equal(feats, p.transpose(1, 2)) and bool((mask.sum(1) >= 1).all())
+    # every valid slot is a distinct in-radius point, every padded slot repeats a valid one
+    d = (dpts[inds] - dpts[centre_idx][:, None]).norm(dim=2)
+    assert bool((d <= 0.05 + 1e-6).all())
+    for r in range(0, P, 11):
+        v = inds[r][mask[r].bool()]
+        assert v.unique().numel() == v.numel()
+        assert set(inds[r][~mask[r].bool()].tolist()) <= set(v.tolist())
+    # vote averaging with a fake "prediction" = patch id in x, slot in y, 1 in z
+    pred = torch.zeros(P, 3, n_pts, device=cuda_device)
+    pred[:, 0] = torch.arange(P, device=cuda_device)[:, None].float()
+    pred[:, 1] = torch.arange(n_pts, device=cuda_device)[None, :].float()
+    pred[:, 2] = 1.0
+    flat = torch.arange(P * n_pts, device=cuda_device).view(P, n_pts)
+    pool = 1 << 20
+    vote_idx = torch.where(mask.bool(), inds, 20000 + (flat & (pool - 1))).int().view(1, P * n_pts // 128, 128).contiguous()
+    rowptr, entries = ops.build_inverse_map(vote_idx, 20000 + pool)
+    mean, votes = ops.vote_mean(pred, rowptr, entries, 20000, n_pts)
+    s = np.zeros((20000, 3), np.float32)
+    c = np.zeros((20000, 1), np.float32) + 1e-7
+    inds_h, mask_h, pred_h = inds.cpu().numpy(), mask.cpu().numpy().astype(bool), pred.cpu().numpy()
+    for b in range(P):  # qualitative_inference_test.py:325-337
+        s[inds_h[b][mask_h[b]]] += pred_h[b][:, mask_h[b]].T
+        c[inds_h[b][mask_h[b]]] += 1
+    np.testing.assert_allclose(mean.cpu().numpy(), s / c, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(votes.cpu().numpy(), np.round(c[:, 0]))
