@@ -72,12 +72,13 @@ radius_patch_kernel(const float* __restrict__ centres, int P, float radius, int 
   const int y0 = pcoord(cy - radius, g.min_y, g.inv_cell, g.G), y1 = pcoord(cy + radius, g.min_y, g.inv_cell, g.G);
   const int z0 = pcoord(cz - radius, g.min_z, g.inv_cell, g.G), z1 = pcoord(cz + radius, g.min_z, g.inv_cell, g.G);
   const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-  // cells of one x-row are contiguous in memory: a (y, z) row is one contiguous range of sorted points
-  for (int row = 0; row < ny * nz; ++row) {
+  // cells of one x-row are contiguous in memory: a (y, z) row is one contiguous range of sorted points.  Rows are
+  // short (a few points), so every thread takes whole rows.
+  for (int row = threadIdx.x; row < ny * nz; row += kPatchThreads) {
     const int y = y0 + row % ny, z = z0 + row / ny;
     const int c0 = (z * g.G + y) * g.G + x0, c1 = c0 + nx;
     const int beg = cell_start[c0], end = c1 < n_cells ? cell_start[c1] : N;
-    for (int t = beg + threadIdx.x; t < end; t += kPatchThreads) {
+    for (int t = beg; t < end; ++t) {
       const float4 s = __ldg(sorted + t);
       // distances in fp64 like the KD-tree the reference uses (sklearn promotes to float64)
       const double dx = (double)s.x - (double)cx, dy = (double)s.y - (double)cy, dz = (double)s.z - (double)cz;
