@@ -47,6 +47,8 @@ def parse():
     p.add_argument("--batch", type=int, default=BATCH)
     p.add_argument("--num-points", type=int, default=NUM_POINTS)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                   help="replay the whole training step as one CUDA graph (auto: on)")
     return p.parse_args()
 
 
@@ -292,14 +294,26 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.graph != "off":
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required for capturing NCCL collectives
     rank, world, local_rank = distributed.init("nccl")
     lib = _lib.load()
     cfgmod.runtime.pseudo_grid_precision = args.pseudo_grid_precision
 
     model, criterion, cfg = build_model(args.operator, args.num_points)
     model = model.to(dev)
-    net = distributed.wrap(model, local_rank)  # DDP + NCCL gradient all-reduce when world > 1 (train_dist.py:375)
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay)
+    # gradient averaging when world > 1 (train_dist.py:375 uses DDP): `--graph off` wraps the model in DDP exactly like
+    # the reference; the graph mode uses one flat gradient bucket + a single NCCL all-reduce that is captured with
+    # the rest of the step (DDP's reducer hooks do not replay)
+    bucket = None
+    if world > 1 and args.graph != "off":
+        net = model
+        bucket = distributed.FlatGradAllReduce(model.parameters())
+    else:
+        net = distributed.wrap(model, local_rank)
+    use_graph = args.graph != "off"
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay,
+                           capturable=use_graph)
     B, N = args.batch, args.num_points
 
     def host_batch(step):  # per-rank shard of the synthetic patch stream
@@ -307,9 +321,14 @@ def main():
         return [torch.from_numpy(a).pin_memory() for a in arrs]
 
     def train_step(pts, mask, feats, offs):
-        opt.zero_grad(set_to_none=True)
+        if bucket is not None:
+            bucket.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss = criterion(net(pts, mask, feats).transpose(1, 2), offs, mask)
         loss.backward()
+        if bucket is not None:
+            bucket.reduce()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 10)
         opt.step()
         return loss
@@ -320,29 +339,57 @@ def main():
     n_host = 4
     host = [host_batch(s) for s in range(n_host)]
     resident = [[t.to(dev) for t in hb] for hb in host]
+    static = [t.clone() for t in resident[0]]  # the step always reads these buffers (CUDA-graph friendly)
+
+    # ---- warm-up (eager, on a side stream as graph capture requires), launch count of one step, capture ----
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for w in range(max(args.warmup, 3, 11 if (use_graph and world > 1) else 0)):
+            for d, src in zip(static, resident[w % n_host]):
+                d.copy_(src)
+            if w == 2:
+                launches0 = lib.d3d_kernel_launches()
+            train_step(*static)
+            if w == 2:
+                launches_per_step = lib.d3d_kernel_launches() - launches0
+    torch.cuda.current_stream().wait_stream(side)
+    barrier()
+    graph, static_loss = None, None
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = train_step(*static)
+        barrier()
+
+    def run_step(batch, non_blocking=False):
+        for d, src in zip(static, batch):
+            d.copy_(src, non_blocking=non_blocking)
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return train_step(*static)
 
     # ---- device-resident timing -------------------------------------------------------------------------
-    for w in range(max(args.warmup, 3)):
-        train_step(*resident[w % n_host])
+    for w in range(3):
+        run_step(resident[w % n_host])
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    launches0 = lib.d3d_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for s in range(args.steps):
-        train_step(*resident[s % n_host])
+        run_step(resident[s % n_host])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = lib.d3d_kernel_launches() - launches0
+    launches = launches_per_step * args.steps
     clock_info = clocks.stop()
 
     # ---- end to end: host batches in, loss out ----------------------------------------------------------
     def e2e_step(hb):
-        dbatch = [t.to(dev, non_blocking=True) for t in hb]
-        return train_step(*dbatch).item()  # D2H read of the loss
+        return run_step(hb, non_blocking=True).item()  # pinned H2D copies of the inputs, D2H read of the loss
 
     for w in range(3):
         e2e_step(host[w % n_host])
@@ -361,6 +408,9 @@ def main():
     # (every rank runs these steps — they contain the gradient all-reduce — only rank 0 reports them)
     kernels, roofline = None, None
     n_inst = 3
+    for s in range(2):  # eager again after graph replay: let the caching allocator settle before timing single ops
+        train_step(*resident[s % n_host])
+    barrier()
     with OpTimer(ops) as timer:
         for s in range(n_inst):
             train_step(*resident[s % n_host])
@@ -418,7 +468,9 @@ def main():
                 "config": {"workload": workload_name(args.operator, B, N), "global_batch": world * B,
                            "num_points": N, "operator": args.operator,
                            "pseudo_grid_precision": args.pseudo_grid_precision if args.operator == "pseudo_grid" else None,
-                           "parallelism": f"dp{world}", "optimizer": "adam", "l2": "per-step working set (activations, "
+                           "parallelism": f"dp{world}", "optimizer": "adam",
+                           "grad_allreduce": None if world == 1 else ("flat bucket, 1 NCCL all-reduce" if bucket is not None else "DDP"),
+                           "cuda_graph": graph is not None, "l2": "per-step working set (activations, "
                            "several GB) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -427,7 +479,10 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # process-group teardown after captured NCCL collectives can block; every rank is done: leave directly
+        barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -52,3 +52,30 @@ def barrier(device=None):
         dist.barrier()
     if device is not None and torch.device(device).type == "cuda":
         torch.cuda.synchronize(device)
+
+
+class FlatGradAllReduce:
+    """Gradient averaging without DDP's reducer: every parameter's .grad is a view into ONE flat fp32 buffer, so the
+    backward kernels write straight into the bucket and the step issues a single all-reduce (73.7 MB for the U-Net)
+    — a plain NCCL call that a CUDA graph can capture together with forward, backward and the optimiser.
+    Same result as DistributedDataParallel's averaged gradients (train_dist.py:375), no overlap with backward
+    (the transfer is ~0.2 ms over NVLink 5)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def zero(self):
+        self.flat.zero_()  # grads stay views of the bucket (use instead of optimizer.zero_grad(set_to_none=True))
+
+    def reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(self.world)

@@ -40,9 +40,19 @@ def _worker(rank, world, port, out_dir):
     block2 = torch.nn.Sequential(head2.up_conv3, head2.head)
     MaskedL1Loss()(block2(x).transpose(1, 2), torch.from_numpy(offs), torch.from_numpy(mask)).backward()
     local = torch.cat([p.grad.flatten() for p in block2.parameters()])
+    # the DDP-free path: grads as views of one flat bucket + a single all-reduce
+    torch.manual_seed(0)
+    head3 = MultiDimHeadResNet(3, 8, 0.025, [4, 4, 4, 4, 4])
+    block3 = torch.nn.Sequential(head3.up_conv3, head3.head)
+    bucket = distributed.FlatGradAllReduce(block3.parameters())
+    bucket.zero()
+    MaskedL1Loss()(block3(x).transpose(1, 2), torch.from_numpy(offs), torch.from_numpy(mask)).backward()
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in block3.parameters())  # still views of the bucket
+    bucket.reduce()
+    flat_grads = torch.cat([p.grad.flatten() for p in block3.parameters()])
     times = distributed.max_over_ranks([10.0 + rank, 5.0 - rank], "cpu")
     distributed.barrier()
-    torch.save({"ddp": grads, "local": local, "times": times, "seed": distributed.shard_seed(rank, 0),
+    torch.save({"ddp": grads, "local": local, "flat": flat_grads, "times": times, "seed": distributed.shard_seed(rank, 0),
                 "points": torch.from_numpy(pts)}, os.path.join(out_dir, f"rank{rank}.pt"))
     torch.distributed.destroy_process_group()
 
@@ -53,6 +63,8 @@ def test_two_rank_gradient_allreduce_and_sharding(tmp_path):
     r0, r1 = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
     assert torch.equal(r0["ddp"], r1["ddp"])  # every rank holds the same averaged gradient after the all-reduce
     torch.testing.assert_close(r0["ddp"], (r0["local"] + r1["local"]) / 2, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(r0["flat"], r0["ddp"], rtol=1e-6, atol=1e-8)  # flat-bucket all-reduce == DDP
+    assert torch.equal(r0["flat"], r1["flat"])
     assert not torch.equal(r0["local"], r1["local"])  # the ranks really worked on different shards
     assert r0["seed"] != r1["seed"] and not torch.equal(r0["points"], r1["points"])
     assert r0["times"] == r1["times"] == [11.0, 5.0]  # max over ranks, element-wise
