@@ -18,7 +18,7 @@ SIGNATURES = {
     "d3d_abi_version": (_i, []),
     "d3d_error_string": (ctypes.c_char_p, [_i]),
     "d3d_kernel_launches": (ctypes.c_longlong, []),
-    "d3d_ball_query_workspace_bytes": (_sz, [_i, _i]),
+    "d3d_ball_query_workspace_bytes": (_sz, [_i, _i, _i]),
     "d3d_ball_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_nearest_query_workspace_bytes": (_sz, [_i]),
     "d3d_nearest_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

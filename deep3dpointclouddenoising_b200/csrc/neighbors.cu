@@ -43,20 +43,191 @@ __device__ __forceinline__ unsigned long long make_key(float d2, int k) {
   return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)k;
 }
 
+// ---- pass 1 of the ball query: the reference's running (min_dist, min_idx) over ALL in-radius supports (:59-62) ----
+// = the nearest in-radius support, lowest index among equal distances.  Found exactly with a small uniform grid per
+// cloud (built by one block per cloud in shared memory, cells sized ~2 supports) and expanding cube shells of
+// cells: ~100 pair tests per query instead of N.  Distances use the reference's float expression (d3d_dist2).
+constexpr int kNgMaxG = 16;  // up to 16^3 cells per cloud
+
+struct CloudGrid {
+  float min_x, min_y, min_z, cell, inv_cell;
+  int G;
+};
+
+__device__ __forceinline__ int ng_coord(float v, float mn, float inv_cell, int G) {
+  return min(max((int)floorf((v - mn) * inv_cell), 0), G - 1);
+}
+
+__global__ void __launch_bounds__(1024)
+ball_grid_build_kernel(const float* __restrict__ support_xyz, const int* __restrict__ vlen, int N,
+                       CloudGrid* __restrict__ grids, int* __restrict__ cell_start /* (B, 16^3 + 1) */,
+                       float4* __restrict__ sorted /* (B, N) */) {
+  __shared__ int counts[kNgMaxG * kNgMaxG * kNgMaxG];
+  __shared__ float red[6][32];
+  __shared__ int warp_tot[32];
+  __shared__ CloudGrid g;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v = vlen[b];
+  const float* S = support_xyz + (size_t)b * N * 3;
+  int* cs = cell_start + (size_t)b * (kNgMaxG * kNgMaxG * kNgMaxG + 1);
+  float4* out = sorted + (size_t)b * N;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = tid; i < v; i += 1024)
+    for (int d = 0; d < 3; ++d) {
+      const float x = S[3 * (size_t)i + d];
+      lo[d] = fminf(lo[d], x);
+      hi[d] = fmaxf(hi[d], x);
+    }
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(D3D_FULL_MASK, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(D3D_FULL_MASK, hi[d], o));
+    }
+    if (lane == 0) { red[d][warp] = lo[d]; red[3 + d][warp] = hi[d]; }
+  }
+  for (int c = tid; c < kNgMaxG * kNgMaxG * kNgMaxG; c += 1024) counts[c] = 0;
+  __syncthreads();
+  if (warp == 0) {
+    float ext = 0.f, mn[3];
+    for (int d = 0; d < 3; ++d) {
+      float a = red[d][lane], z = red[3 + d][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(D3D_FULL_MASK, a, o));
+        z = fmaxf(z, __shfl_xor_sync(D3D_FULL_MASK, z, o));
+      }
+      mn[d] = a;
+      ext = fmaxf(ext, z - a);
+    }
+    if (lane == 0) {
+      int G = (int)cbrtf((float)max(v, 1) * 0.5f);
+      G = min(max(G, 1), kNgMaxG);
+      if (!(ext > 0.f) || !(ext < INFINITY)) { ext = 1.f; G = 1; }
+      if (v == 0) { mn[0] = mn[1] = mn[2] = 0.f; }
+      g.min_x = mn[0]; g.min_y = mn[1]; g.min_z = mn[2];
+      g.cell = ext * (1.0f + 1e-5f) / (float)G;
+      g.inv_cell = 1.0f / g.cell;
+      g.G = G;
+      grids[b] = g;
+    }
+  }
+  __syncthreads();
+  const int G = g.G, n_cells = G * G * G;
+  for (int i = tid; i < v; i += 1024) {
+    const int c = (ng_coord(S[3 * (size_t)i + 2], g.min_z, g.inv_cell, G) * G + ng_coord(S[3 * (size_t)i + 1], g.min_y, g.inv_cell, G)) * G +
+                  ng_coord(S[3 * (size_t)i], g.min_x, g.inv_cell, G);
+    atomicAdd(&counts[c], 1);
+  }
+  __syncthreads();
+  // exclusive scan of counts[0 .. 4096): 4 cells per thread
+  int loc[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { loc[k] = counts[tid * 4 + k]; sum += loc[k]; }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = warp_tot[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(D3D_FULL_MASK, wi, o);
+      if (lane >= o) wi += up;
+    }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  int run = warp_tot[warp] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = tid * 4 + k;
+    cs[c] = run;
+    counts[c] = run;  // becomes the fill cursor
+    run += loc[k];
+  }
+  if (tid == 1023) cs[kNgMaxG * kNgMaxG * kNgMaxG] = run;
+  __syncthreads();
+  (void)n_cells;
+  for (int i = tid; i < v; i += 1024) {
+    const float x = S[3 * (size_t)i], y = S[3 * (size_t)i + 1], z = S[3 * (size_t)i + 2];
+    const int c = (ng_coord(z, g.min_z, g.inv_cell, G) * G + ng_coord(y, g.min_y, g.inv_cell, G)) * G + ng_coord(x, g.min_x, g.inv_cell, G);
+    out[atomicAdd(&counts[c], 1)] = make_float4(x, y, z, __int_as_float(i));
+  }
+}
+
+__global__ void __launch_bounds__(128)
+ball_nearest_kernel(const float* __restrict__ query_xyz, const CloudGrid* __restrict__ grids,
+                    const int* __restrict__ cell_start, const float4* __restrict__ sorted, int M, int N, float radius,
+                    float* __restrict__ best_d2, int* __restrict__ best_k) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= M) return;
+  const CloudGrid g = grids[b];
+  const int G = g.G;
+  const int* cs = cell_start + (size_t)b * (kNgMaxG * kNgMaxG * kNgMaxG + 1);
+  const float4* pts = sorted + (size_t)b * N;
+  const float* q = query_xyz + ((size_t)b * M + j) * 3;
+  const float qx = q[0], qy = q[1], qz = q[2];
+  const float r2 = __fmul_rn(radius, radius);
+  float best = r2;  // :45-47 min_dist = radius2, min_idx = 0
+  int bk = 0;
+  const int cx = ng_coord(qx, g.min_x, g.inv_cell, G), cy = ng_coord(qy, g.min_y, g.inv_cell, G), cz = ng_coord(qz, g.min_z, g.inv_cell, G);
+  auto visit = [&](int x, int y, int z) {
+    const int c = (z * G + y) * G + x;
+    const int beg = cs[c], end = cs[c + 1];
+    for (int t = beg; t < end; ++t) {
+      const float4 s = __ldg(pts + t);
+      const float d2 = d3d_dist2(qx, qy, qz, s.x, s.y, s.z);
+      const int k = __float_as_int(s.w);
+      // running minimum over ascending index == (smaller distance) or (equal distance and lower index)
+      if (d2 < best || (d2 == best && best < r2 && k < bk)) { best = d2; bk = k; }
+    }
+  };
+  for (int r = 0; r < G; ++r) {
+    // The query's projection onto the grid box lies in the centre cell and is never farther from a support than the
+    // query: every support of shell r is farther than (r - 1) * cell.  Compare in fp64 so that rounding cannot cut
+    // the search short; best starts at radius^2, so shells beyond the radius are never visited.
+    if (r >= 1) {
+      const double reach = (double)(r - 1) * (double)g.cell * (1.0 - 1e-6);
+      if ((double)best <= reach * reach) break;
+    }
+    if (cx - r < 0 && cx + r >= G && cy - r < 0 && cy + r >= G && cz - r < 0 && cz + r >= G) break;
+    for (int z = max(cz - r, 0); z <= min(cz + r, G - 1); ++z) {
+      const bool z_face = (z == cz - r) || (z == cz + r);
+      for (int y = max(cy - r, 0); y <= min(cy + r, G - 1); ++y) {
+        if (z_face || y == cy - r || y == cy + r) {
+          for (int x = max(cx - r, 0); x <= min(cx + r, G - 1); ++x) visit(x, y, z);
+        } else {
+          if (cx - r >= 0) visit(cx - r, y, z);
+          if (cx + r < G) visit(cx + r, y, z);
+        }
+      }
+    }
+  }
+  best_d2[(size_t)b * M + j] = best;
+  best_k[(size_t)b * M + j] = bk;
+}
+
 // far-away filler for the unused tail of a tile: its squared distance overflows to +inf, which fails
 // every "d2 < something" test, so the scan loops need no bounds predicate
 constexpr float kFar = 1.0e30f;
 
-// Per query the scan is split in two passes over the shared-memory tile:
-//   fill pass : 32 supports per step, ballot + prefix popcount append the in-radius ones to the candidate list in
-//               ascending index order; stops as soon as the list holds 3*nsample entries (on the BASELINE patches
-//               after ~1/4 of the supports on average);
-//   min pass  : the reference's running (min_dist, min_idx) over ALL in-radius supports (:59-62), 4 queries at a
-//               time so that each support is read once per 4 queries: 6 FP ops + compare + 2 selects per pair.
+// ---- pass 2: candidate fill + ordered selection ----
+//   fill : 32 supports per step, ballot + prefix popcount append the in-radius ones to the candidate list in
+//          ascending index order; stops as soon as the list holds 3*nsample entries (on the BASELINE patches after
+//          ~1/4 of the supports on average); a block leaves the tile loop once all of its lists are full;
+//   then : nearest-swap with pass 1's result, histogram pre-selection, rank sort, coalesced row emission.
 template <int QW, int kBqWarps>
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__ support_xyz,
-                  const int* __restrict__ query_mask, const int* __restrict__ vlen, int M, int N, int tile,
+                  const int* __restrict__ query_mask, const int* __restrict__ vlen,
+                  const float* __restrict__ best_d2, const int* __restrict__ best_k, int M, int N, int tile,
                   float radius, int nsample, int* __restrict__ idx, int* __restrict__ idx_mask,
                   int* __restrict__ nvalid) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -81,17 +252,20 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
   int* my_sorted = sorted_all + (size_t)warp * QW * nsample;
   int* my_hist = hist_all + warp * 32;
 
-  float qx[QW], qy[QW], qz[QW], best[QW];
-  int bestk[QW], cnt[QW];
+  float qx[QW], qy[QW], qz[QW];
+  int cnt[QW];
 #pragma unroll
   for (int u = 0; u < QW; ++u) {
     const int j = min(q0 + u, M - 1);
     qx[u] = Q[3 * j + 0]; qy[u] = Q[3 * j + 1]; qz[u] = Q[3 * j + 2];
-    best[u] = r2; bestk[u] = 0; cnt[u] = 0;  // :45-47
+    cnt[u] = 0;
   }
 
   for (int base = 0; base < v; base += tile) {
-    __syncthreads();  // everyone is done with the previous tile
+    bool filling = false;
+#pragma unroll
+    for (int u = 0; u < QW; ++u) filling = filling || (cnt[u] < cap && q0 + u < M);
+    if (!__syncthreads_or(filling ? 1 : 0)) break;  // every list of the block is full (also: previous tile consumed)
     const int tile_n = min(tile, v - base);
     for (int i = threadIdx.x; i < tile; i += blockDim.x) {
       float x = kFar, y = kFar, z = kFar;
@@ -118,18 +292,6 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
         }
       }
     }
-    // ---- min pass over the whole tile for all QW queries (strict <: earliest index per lane)
-#pragma unroll 2
-    for (int st = 0; st < steps; ++st) {
-      const int i = (st << 5) + lane;
-      const int k = base + i;
-      const float x = sx[i], y = sy[i], z = sz[i];
-#pragma unroll
-      for (int u = 0; u < QW; ++u) {
-        const float d2 = d3d_dist2(qx[u], qy[u], qz[u], x, y, z);
-        if (d2 < best[u]) { best[u] = d2; bestk[u] = k; }  // best starts at r2: implies in-radius
-      }
-    }
   }
 
 #pragma unroll
@@ -141,17 +303,11 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
     const int c = min(cnt[u], cap);
     __syncwarp();
     if (cnt[u] >= cap) {
-      // global nearest in-radius support: min d2, lowest index among equal d2
-      float bd = best[u];
-      int bk = bestk[u];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float od = __shfl_xor_sync(D3D_FULL_MASK, bd, off);
-        const int ok = __shfl_xor_sync(D3D_FULL_MASK, bk, off);
-        if (od < bd || (od == bd && ok < bk)) { bd = od; bk = ok; }
+      // :72-75  the global nearest in-radius support (pass 1) lies beyond the last slot -> it replaces the last slot
+      if (lane == 0) {
+        const int bk = best_k[(size_t)b * M + j];
+        if (bk > (int)(unsigned)(list[cap - 1] & 0xffffffffull)) list[cap - 1] = make_key(best_d2[(size_t)b * M + j], bk);
       }
-      // :72-75  it lies beyond the last slot -> it replaces the last slot
-      if (lane == 0 && bk > (int)(unsigned)(list[cap - 1] & 0xffffffffull)) list[cap - 1] = make_key(bd, bk);
       __syncwarp();
     }
     // Pre-selection: only the nsample smallest keys are emitted.  d2 -> bin is monotone, so every key in a
@@ -280,30 +436,32 @@ size_t bq_smem_bytes(int warps, int qw, int nsample, int tile) {
 }
 
 template <int QW, int WARPS>
-int launch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, int B, int M, int N,
-                      float radius, int nsample, int* idx, int* idx_mask, int* nvalid, cudaStream_t st) {
+int launch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, const float* best_d2,
+                      const int* best_k, int B, int M, int N, float radius, int nsample, int* idx, int* idx_mask,
+                      int* nvalid, cudaStream_t st) {
   const int tile = bq_tile(N);
   const size_t smem = bq_smem_bytes(WARPS, QW, nsample, tile);
   cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<QW, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(d3d_ceil_div(M, WARPS * QW), B);
-  ball_query_kernel<QW, WARPS><<<grid, WARPS * 32, smem, st>>>(q, s, qm, vlen, M, N, tile, radius, nsample, idx,
-                                                             idx_mask, nvalid);
+  ball_query_kernel<QW, WARPS><<<grid, WARPS * 32, smem, st>>>(q, s, qm, vlen, best_d2, best_k, M, N, tile, radius, nsample,
+                                                             idx, idx_mask, nvalid);
   d3d_note_launches(1);
   return d3d_launch_status();
 }
 
 template <int WARPS>
-int dispatch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, int B, int M, int N,
-                        float radius, int nsample, int* idx, int* idx_mask, int* nvalid, cudaStream_t st) {
+int dispatch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, const float* best_d2,
+                        const int* best_k, int B, int M, int N, float radius, int nsample, int* idx, int* idx_mask,
+                        int* nvalid, cudaStream_t st) {
   const size_t budget = 220 * 1024;  // opt-in shared memory per block on sm_100a is 227 KB
   const int tile = bq_tile(N);
   if (bq_smem_bytes(WARPS, 4, nsample, tile) <= budget / 2)
-    return launch_ball_query<4, WARPS>(q, s, qm, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<4, WARPS>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   if (bq_smem_bytes(WARPS, 2, nsample, tile) <= budget / 2)
-    return launch_ball_query<2, WARPS>(q, s, qm, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<2, WARPS>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   if (bq_smem_bytes(WARPS, 1, nsample, tile) <= budget)
-    return launch_ball_query<1, WARPS>(q, s, qm, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<1, WARPS>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   return D3D_ERR_UNSUPPORTED;
 }
 
@@ -316,9 +474,14 @@ void d3d_launch_prefix_len(const int* mask, int B, int N, int* vlen, cudaStream_
 
 extern "C" {
 
-size_t d3d_ball_query_workspace_bytes(int B, int M) {
-  (void)M;  // a split min / fill variant needed 8 bytes per query here; measured slower (1.09 vs 0.95 ms), not kept
-  return (size_t)(B > 0 ? B : 0) * sizeof(int);
+static size_t bq_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+/* [vlen: B int][grids: B][cell_start: B x (16^3 + 1)][sorted supports: B x N float4][best d2, best k: B x M each] */
+size_t d3d_ball_query_workspace_bytes(int B, int M, int N) {
+  if (B <= 0 || M < 0 || N <= 0) return 0;
+  return bq_align((size_t)B * sizeof(int)) + bq_align((size_t)B * sizeof(CloudGrid)) +
+         bq_align((size_t)B * (kNgMaxG * kNgMaxG * kNgMaxG + 1) * sizeof(int)) + bq_align((size_t)B * N * sizeof(float4)) +
+         2 * bq_align((size_t)B * M * sizeof(float));
 }
 
 int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
@@ -327,14 +490,24 @@ int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* 
   D3D_REQUIRE(query_xyz && support_xyz && query_mask && support_mask && idx && idx_mask);
   D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE);
   if (B == 0 || M == 0) return 0;
-  if (!ws || ws_bytes < d3d_ball_query_workspace_bytes(B, M)) return D3D_ERR_WORKSPACE;
+  if (!ws || ws_bytes < d3d_ball_query_workspace_bytes(B, M, N)) return D3D_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  int* vlen = (int*)ws;
+  unsigned char* p = (unsigned char*)ws;
+  int* vlen = (int*)p; p += bq_align((size_t)B * sizeof(int));
+  CloudGrid* grids = (CloudGrid*)p; p += bq_align((size_t)B * sizeof(CloudGrid));
+  int* cell_start = (int*)p; p += bq_align((size_t)B * (kNgMaxG * kNgMaxG * kNgMaxG + 1) * sizeof(int));
+  float4* sorted = (float4*)p; p += bq_align((size_t)B * N * sizeof(float4));
+  float* best_d2 = (float*)p; p += bq_align((size_t)B * M * sizeof(float));
+  int* best_k = (int*)p;
   d3d_launch_prefix_len(support_mask, B, N, vlen, st);
+  ball_grid_build_kernel<<<B, 1024, 0, st>>>(support_xyz, vlen, N, grids, cell_start, sorted);
+  ball_nearest_kernel<<<dim3(d3d_ceil_div(M, 128), B), 128, 0, st>>>(query_xyz, grids, cell_start, sorted, M, N, radius, best_d2,
+                                                                   best_k);
+  d3d_note_launches(2);
   switch (env_int("D3D_BQ_WARPS", kBqDefaultWarps)) {
-    case 4: return dispatch_ball_query<4>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-    case 16: return dispatch_ball_query<16>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-    default: return dispatch_ball_query<8>(query_xyz, support_xyz, query_mask, vlen, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    case 4: return dispatch_ball_query<4>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    case 16: return dispatch_ball_query<16>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    default: return dispatch_ball_query<8>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   }
 }
 

@@ -64,7 +64,7 @@ def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample
         idx = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
         msk = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
         nv = torch.empty((B, M), dtype=torch.int32, device=q.device) if want_nvalid else None
-        ws = _ws(L.d3d_ball_query_workspace_bytes(B, M), q.device)
+        ws = _ws(L.d3d_ball_query_workspace_bytes(B, M, N), q.device)
         _lib.check(L.d3d_ball_query(_p(q), _p(s), _p(qm), _p(sm), B, M, N, float(radius), int(nsample), _p(idx),
                                     _p(msk), _p(nv), _p(ws), ws.numel(), _stream()), "d3d_ball_query")
     _count()

@@ -50,9 +50,9 @@ long long d3d_kernel_launches(void);
  * Out: idx, idx_mask (B, M, nsample) int32.  nvalid (B, M) int32 may be NULL; when given it receives
  * min(#in-radius supports, nsample) per query BEFORE the query mask is applied (the fused aggregation
  * kernels use it instead of the dense idx_mask).
- * Workspace: d3d_ball_query_workspace_bytes(B, M).  Unlike the reference no (B, M, 3*nsample) scratch
+ * Workspace: d3d_ball_query_workspace_bytes(B, M, N).  Unlike the reference no (B, M, 3*nsample) scratch
  * tensors are needed (masked_ordered_ball_query.cpp:38-44). */
-size_t d3d_ball_query_workspace_bytes(int B, int M);
+size_t d3d_ball_query_workspace_bytes(int B, int M, int N);
 int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
                    const int* support_mask, int B, int M, int N, float radius, int nsample,
                    int* idx, int* idx_mask, int* nvalid, void* ws, size_t ws_bytes, void* stream);

@@ -40,7 +40,7 @@ def test_abi_version_and_error_strings(lib):
 
 
 def test_workspace_queries_are_pure_host_functions(lib):
-    assert lib.d3d_ball_query_workspace_bytes(16, 8192) >= 16 * 4
+    assert lib.d3d_ball_query_workspace_bytes(16, 8192, 8192) >= 16 * 4 + 16 * 8192 * (16 + 8)
     assert lib.d3d_grid_subsample_workspace_bytes(16, 8192) == 0  # sorted in shared memory
     assert lib.d3d_grid_subsample_workspace_bytes(2, 20000) == 2 * 32768 * 8
     assert lib.d3d_inverse_map_workspace_bytes(16, 8192, 8192, 52) >= 16 * 8192 * 52 * 4
