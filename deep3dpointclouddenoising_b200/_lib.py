@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libd3d_b200.so")
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes); mirrors include/d3d_b200.h one to one (tests/test_abi.py checks the
 # header against this table and against the symbols the .so exports).
@@ -52,6 +53,8 @@ SIGNATURES = {
     "d3d_bn_act_workspace_bytes": (_sz, [_i]),
     "d3d_bn_act_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_bn_act_bwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
+    "d3d_bn_act_cl_fwd": (_i, [_vp] * 6 + [_ll, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "d3d_bn_act_cl_bwd": (_i, [_vp] * 7 + [_ll, _i, _i, _i] + [_vp] * 5 + [_sz, _vp]),
 }
 
 _lib = None

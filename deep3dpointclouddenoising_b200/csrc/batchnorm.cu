@@ -364,6 +364,225 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, con
   invstd[c] = rsqrtf(running_var[c] + eps);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Channel-last variants: the activation is (R, C) row-major with R = B*N rows — the layout the local aggregation
+// kernels gather from and write.  With the 1x1 convolutions run as (R, Cin) x (Cin, Cout) GEMMs the whole network
+// stays in this layout and no transposition kernel is needed between the convolutions and the aggregations.
+// A thread owns one float4 of channels; a block covers kClGroups float4 columns x (256 / groups) rows per iteration,
+// which is one contiguous span of memory when the block spans all channels.
+constexpr int kClThreads = 256;
+constexpr int kClGroups = 64;  // float4 channel groups per block at most (256 channels)
+
+struct ClGeom {
+  int c4, groups, rows_per_iter, gx;
+};
+__host__ __device__ inline ClGeom cl_geom(int C) {
+  ClGeom g;
+  g.c4 = C / 4;
+  g.groups = g.c4 < kClGroups ? g.c4 : kClGroups;
+  g.rows_per_iter = kClThreads / g.groups;
+  g.gx = (g.c4 + g.groups - 1) / g.groups;
+  return g;
+}
+
+// Sums the per-thread float4 pairs over the rows of the block (fp64), stores the block's partials and returns true in
+// the row-0 threads of the LAST block of this channel slab, with tot1/tot2 = the S partials added in fixed order.
+__device__ __forceinline__ bool cl_combine(const float4 s1, const float4 s2, int cx, int ry, int group, bool active,
+                                           const ClGeom g, int C, int S, double* __restrict__ partials,
+                                           unsigned* __restrict__ counters, double tot1[4], double tot2[4]) {
+  __shared__ float4 sh1[kClThreads], sh2[kClThreads];
+  sh1[threadIdx.x] = s1;
+  sh2[threadIdx.x] = s2;
+  __syncthreads();
+  const bool owner = active && ry == 0;
+  if (owner) {
+    double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+    for (int r = 0; r < g.rows_per_iter; ++r) {
+      const float4 u = sh1[r * g.groups + cx], v = sh2[r * g.groups + cx];
+      a1[0] += u.x; a1[1] += u.y; a1[2] += u.z; a1[3] += u.w;
+      a2[0] += v.x; a2[1] += v.y; a2[2] += v.z; a2[3] += v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t slot = ((size_t)(group * 4 + j) * S + blockIdx.y) * 2;
+      partials[slot] = a1[j];
+      partials[slot + 1] = a2[j];
+    }
+  }
+  if (!last_block_of_channel(counters, blockIdx.x, S)) return false;
+  if (!owner) return false;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int k = 0; k < S; ++k) {
+      const size_t slot = ((size_t)(group * 4 + j) * S + k) * 2;
+      a1 += partials[slot];
+      a2 += partials[slot + 1];
+    }
+    tot1[j] = a1;
+    tot2[j] = a2;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kClThreads)
+bn_stats_cl_kernel(const float* __restrict__ x, long long R, int C, int S, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
+                   float* __restrict__ save_invstd, double* __restrict__ partials, unsigned* __restrict__ counters) {
+  const ClGeom g = cl_geom(C);
+  const int cx = threadIdx.x % g.groups, ry = threadIdx.x / g.groups;
+  const int group = blockIdx.x * g.groups + cx;
+  const bool active = ry < g.rows_per_iter && group < g.c4;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1, shift = s1;
+  if (active) {
+    shift = __ldg(reinterpret_cast<const float4*>(x) + group);  // row 0
+    const float4* col = reinterpret_cast<const float4*>(x) + group;
+    const long long step = (long long)S * g.rows_per_iter;
+    for (long long r = (long long)blockIdx.y * g.rows_per_iter + ry; r < R; r += step) {
+      const float4 v = __ldg(col + r * g.c4);
+      const float a0 = v.x - shift.x, a1 = v.y - shift.y, a2 = v.z - shift.z, a3 = v.w - shift.w;
+      s1.x += a0; s1.y += a1; s1.z += a2; s1.w += a3;
+      s2.x += a0 * a0; s2.y += a1 * a1; s2.z += a2 * a2; s2.w += a3 * a3;
+    }
+  }
+  double t1[4], t2[4];
+  if (!cl_combine(s1, s2, cx, ry, group, active, g, C, S, partials, counters, t1, t2)) return;
+  const float sh[4] = {shift.x, shift.y, shift.z, shift.w};
+  const double n = (double)R;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = group * 4 + j;
+    const double m = t1[j] / n;
+    double var = t2[j] / n - m * m;
+    if (var < 0) var = 0;
+    const float mean = (float)(m + (double)sh[j]);
+    save_mean[c] = mean;
+    save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = n > 1 ? var * n / (n - 1) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+  }
+}
+
+__device__ __forceinline__ void cl_scale_offset(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                int group, float4& m, float4& is, float4& scale, float4& offset) {
+  m = __ldg(reinterpret_cast<const float4*>(mean) + group);
+  is = __ldg(reinterpret_cast<const float4*>(invstd) + group);
+  const float4 gm = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + group) : make_float4(1, 1, 1, 1);
+  const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta) + group) : make_float4(0, 0, 0, 0);
+  scale = make_float4(is.x * gm.x, is.y * gm.y, is.z * gm.z, is.w * gm.w);
+  offset = make_float4(bt.x - m.x * scale.x, bt.y - m.y * scale.y, bt.z - m.z * scale.z, bt.w - m.w * scale.w);
+}
+
+__global__ void __launch_bounds__(256)
+bn_apply_cl_kernel(const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                   int c4, long long total4, int relu, float* __restrict__ y) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= total4) return;
+  const int group = (int)(e % c4);
+  float4 m, is, scale, offset;
+  cl_scale_offset(gamma, beta, mean, invstd, group, m, is, scale, offset);
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + e);
+  v.x = v.x * scale.x + offset.x; v.y = v.y * scale.y + offset.y;
+  v.z = v.z * scale.z + offset.z; v.w = v.w * scale.w + offset.w;
+  if (residual) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + e);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+  }
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  reinterpret_cast<float4*>(y)[e] = v;
+}
+
+// dy masked by the ReLU, same expressions as the forward pass so the mask is bit-identical
+__device__ __forceinline__ float4 cl_masked_dy(float4 d, const float4 xv, const float* __restrict__ y, long long e, int relu,
+                                               const float4 scale, const float4 offset) {
+  if (relu == 2) {
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + e);
+    d.x = yv.x > 0.f ? d.x : 0.f; d.y = yv.y > 0.f ? d.y : 0.f; d.z = yv.z > 0.f ? d.z : 0.f; d.w = yv.w > 0.f ? d.w : 0.f;
+  } else if (relu == 1) {
+    d.x = xv.x * scale.x + offset.x > 0.f ? d.x : 0.f; d.y = xv.y * scale.y + offset.y > 0.f ? d.y : 0.f;
+    d.z = xv.z * scale.z + offset.z > 0.f ? d.z : 0.f; d.w = xv.w * scale.w + offset.w > 0.f ? d.w : 0.f;
+  }
+  return d;
+}
+
+__global__ void __launch_bounds__(kClThreads)
+bn_bwd_reduce_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, long long R, int C, int S, int relu, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, float* __restrict__ sums, double* __restrict__ partials,
+                        unsigned* __restrict__ counters) {
+  const ClGeom g = cl_geom(C);
+  const int cx = threadIdx.x % g.groups, ry = threadIdx.x / g.groups;
+  const int group = blockIdx.x * g.groups + cx;
+  const bool active = ry < g.rows_per_iter && group < g.c4;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1, m = s1, is = s1, scale = s1, offset = s1;
+  if (active) {
+    cl_scale_offset(gamma, beta, mean, invstd, group, m, is, scale, offset);
+    const long long step = (long long)S * g.rows_per_iter;
+    for (long long r = (long long)blockIdx.y * g.rows_per_iter + ry; r < R; r += step) {
+      const long long e = r * g.c4 + group;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e);
+      const float4 d = cl_masked_dy(__ldg(reinterpret_cast<const float4*>(dy) + e), xv, y, e, relu, scale, offset);
+      s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+      s2.x += d.x * (xv.x - m.x); s2.y += d.y * (xv.y - m.y); s2.z += d.z * (xv.z - m.z); s2.w += d.w * (xv.w - m.w);
+    }
+  }
+  double t1[4], t2[4];
+  if (!cl_combine(s1, s2, cx, ry, group, active, g, C, S, partials, counters, t1, t2)) return;
+  const float isv[4] = {is.x, is.y, is.z, is.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = group * 4 + j;
+    const double a2 = t2[j] * (double)isv[j];
+    if (dbeta) dbeta[c] = (float)t1[j];
+    if (dgamma) dgamma[c] = (float)a2;
+    sums[2 * c] = (float)t1[j];
+    sums[2 * c + 1] = (float)a2;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ sums, int c4, long long total4,
+                       float inv_count, int relu, int use_batch_stats, float* __restrict__ dx, float* __restrict__ dres) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= total4) return;
+  const int group = (int)(e % c4);
+  float4 m, is, g, offset;
+  cl_scale_offset(gamma, beta, mean, invstd, group, m, is, g, offset);
+  float4 k1 = make_float4(0, 0, 0, 0), k2 = k1;
+  if (use_batch_stats) {
+    const float4 sa = __ldg(reinterpret_cast<const float4*>(sums) + 2 * group);      // (s1, s2) of channels 0, 1
+    const float4 sb = __ldg(reinterpret_cast<const float4*>(sums) + 2 * group + 1);  // channels 2, 3
+    k1 = make_float4(sa.x * inv_count, sa.z * inv_count, sb.x * inv_count, sb.z * inv_count);
+    k2 = make_float4(sa.y * inv_count * is.x, sa.w * inv_count * is.y, sb.y * inv_count * is.z, sb.w * inv_count * is.w);
+  }
+  const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e);
+  const float4 d = cl_masked_dy(__ldg(reinterpret_cast<const float4*>(dy) + e), xv, y, e, relu, g, offset);
+  if (dres) reinterpret_cast<float4*>(dres)[e] = d;
+  float4 o;
+  o.x = g.x * (d.x - k1.x - (xv.x - m.x) * k2.x); o.y = g.y * (d.y - k1.y - (xv.y - m.y) * k2.y);
+  o.z = g.z * (d.z - k1.z - (xv.z - m.z) * k2.z); o.w = g.w * (d.w - k1.w - (xv.w - m.w) * k2.w);
+  reinterpret_cast<float4*>(dx)[e] = o;
+}
+
+int cl_splits(const ClGeom g, long long R) {
+  long long S = (148 * 3 + g.gx - 1) / g.gx;
+  const long long max_s = (R + g.rows_per_iter - 1) / g.rows_per_iter;
+  if (S > max_s) S = max_s;
+  if (S > 64) S = 64;
+  if (S < 1) S = 1;
+  return (int)S;
+}
+
+bool aligned16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
+
 bool vec_ok(int N, const void* a, const void* b, const void* c, const void* d) {
   auto al = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
   return N % 4 == 0 && al(a) && al(b) && al(c) && al(d);
@@ -461,6 +680,59 @@ int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float*
     bn_bwd_apply_kernel<false><<<d3d_ceil_div(rows * N, 256), 256, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, sums,
                                                                            C, N, rows, inv_count, relu, training, dx, dres);
   }
+  d3d_note_launches(2);
+  return d3d_launch_status();
+}
+
+/* Channel-last variants: x, residual, y, dy, dx, dres are (R, C) row-major with R = B * N rows.  C % 4 == 0 and
+ * 16-byte aligned pointers are required (D3D_ERR_ARG otherwise: the caller falls back to the channel-major entry). */
+int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long long R, int C, float eps, float momentum, int training, int relu, float* y,
+                      float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, void* stream) {
+  D3D_REQUIRE(x && y && save_mean && save_invstd);
+  D3D_REQUIRE(R > 0 && C > 0 && C % 4 == 0);
+  D3D_REQUIRE(aligned16(x) && aligned16(residual) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
+              aligned16(save_mean) && aligned16(save_invstd));
+  D3D_REQUIRE(training || (running_mean && running_var));
+  cudaStream_t st = (cudaStream_t)stream;
+  const ClGeom g = cl_geom(C);
+  if (training) {
+    if (!ws || ws_bytes < d3d_bn_act_workspace_bytes(C)) return D3D_ERR_WORKSPACE;
+    float* sums; double* partials; unsigned* counters;
+    carve(ws, C, &sums, &partials, &counters);
+    const int S = cl_splits(g, R);
+    bn_stats_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(x, R, C, S, eps, momentum, running_mean, running_var, save_mean,
+                                                             save_invstd, partials, counters);
+  } else {
+    bn_eval_stats_kernel<<<d3d_ceil_div(C, 256), 256, 0, st>>>(running_mean, running_var, C, eps, save_mean, save_invstd);
+  }
+  const long long total4 = R * g.c4;
+  bn_apply_cl_kernel<<<(unsigned)d3d_ceil_div(total4, 256), 256, 0, st>>>(x, residual, gamma, beta, save_mean, save_invstd, g.c4,
+                                                                         total4, relu, y);
+  d3d_note_launches(2);
+  return d3d_launch_status();
+}
+
+int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* beta,
+                      const float* save_mean, const float* save_invstd, long long R, int C, int training, int relu, float* dx,
+                      float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+  D3D_REQUIRE(dy && x && save_mean && save_invstd && dx);
+  D3D_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && relu >= 0 && relu <= 2);
+  D3D_REQUIRE(relu != 2 || y);
+  D3D_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(y) && aligned16(dx) && aligned16(dres) && aligned16(gamma) &&
+              aligned16(beta) && aligned16(save_mean) && aligned16(save_invstd));
+  if (!ws || ws_bytes < d3d_bn_act_workspace_bytes(C)) return D3D_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sums; double* partials; unsigned* counters;
+  carve(ws, C, &sums, &partials, &counters);
+  const ClGeom g = cl_geom(C);
+  const int S = cl_splits(g, R);
+  bn_bwd_reduce_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, R, C, S, relu,
+                                                                dgamma, dbeta, sums, partials, counters);
+  const long long total4 = R * g.c4;
+  bn_bwd_apply_cl_kernel<<<(unsigned)d3d_ceil_div(total4, 256), 256, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, sums,
+                                                                             g.c4, total4, 1.0f / (float)R, relu, training, dx,
+                                                                             dres);
   d3d_note_launches(2);
   return d3d_launch_status();
 }

@@ -1,6 +1,12 @@
-"""Autograd Functions over the fused kernels.  Inputs and outputs use the reference's channel-major
-(B, C, N) layout; the layout change to channel-last happens inside (d3d_cm_to_cl / d3d_cl_to_cm), so the
-callers — the modules mirroring pt_utils.py and local_aggregation_operators.py — keep the reference API.
+"""Autograd Functions over the fused kernels.  Inputs and outputs have the reference's LOGICAL shape
+(B, C, N), so the callers — the modules mirroring pt_utils.py and local_aggregation_operators.py — keep the
+reference API.  The kernels work on channel-last rows (B, N, C):
+
+* a channel-major contiguous input is transposed inside (d3d_cm_to_cl / d3d_cl_to_cm);
+* a "channel-last view" — the (B, C, N) permutation of a contiguous (B, N, C) buffer — is used in place, and
+  with `runtime.channel_last` (default) outputs are returned as such views.  The U-Net then never leaves the
+  row layout: aggregations, fused BatchNorm (d3d_bn_act_cl_*) and the 1x1 convolutions (row-major GEMMs,
+  models/blocks.py) hand rows to each other and the step has no transposition kernel at all.
 
 Differentiable w.r.t. features (and PseudoGrid's kernel_weights) only, like the reference
 (pt_utils.py:43-62: GroupingOperation returns a gradient for features, None for idx; coordinates never
@@ -10,6 +16,34 @@ import torch
 from torch.autograd import Function
 
 from . import ops
+from .utils.config import runtime
+
+
+def is_channel_last(t):
+    """True for the (B, C, N) view of a contiguous (B, N, C) buffer."""
+    return t.dim() == 3 and not t.is_contiguous() and t.permute(0, 2, 1).is_contiguous()
+
+
+def _rows(t):
+    """Contiguous (B, N, C) rows of a logical (B, C, N) tensor (no copy for channel-last views)."""
+    return t.permute(0, 2, 1) if is_channel_last(t) else ops.cm_to_cl(t.contiguous())
+
+
+def _logical(rows, channel_last):
+    """Logical (B, C, N) tensor over (B, N, C) rows: a view, or a channel-major copy."""
+    return rows.permute(0, 2, 1) if channel_last else ops.cl_to_cm(rows)
+
+
+def rows_of(t):
+    """Differentiable (B, N, C) rows of a logical (B, C, N) tensor, for torch ops (1x1 convolutions as GEMMs)."""
+    return t.permute(0, 2, 1) if is_channel_last(t) else t.transpose(1, 2).contiguous()
+
+
+def cat_channels(tensors):
+    """torch.cat(tensors, 1) that keeps channel-last views channel-last (a plain cat would re-layout)."""
+    if all(is_channel_last(t) for t in tensors):
+        return torch.cat([t.permute(0, 2, 1) for t in tensors], 2).permute(0, 2, 1)
+    return torch.cat(tensors, 1)
 
 
 class PosPoolFunction(Function):
@@ -17,21 +51,21 @@ class PosPoolFunction(Function):
 
     @staticmethod
     def forward(ctx, features, query_xyz, support_xyz, query_mask, nbr, radius, reduction):
-        feat_cl = ops.cm_to_cl(features.contiguous())
+        feat_cl, ctx.in_cl = _rows(features), is_channel_last(features)
         out_cl = ops.pospool_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, radius, reduction)
         ctx.nbr, ctx.radius, ctx.reduction = nbr, radius, reduction
         ctx.save_for_backward(query_xyz, support_xyz, query_mask)
-        return ops.cl_to_cm(out_cl)
+        return _logical(out_cl, runtime.channel_last)
 
     @staticmethod
     def backward(ctx, grad_out):
         query_xyz, support_xyz, query_mask = ctx.saved_tensors
         nbr = ctx.nbr
         rowptr, entries = nbr.csr()
-        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        g_cl = _rows(grad_out)
         gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,
                                 nbr.nsample, ctx.radius, ctx.reduction)
-        return ops.cl_to_cm(gf_cl), None, None, None, None, None, None
+        return _logical(gf_cl, ctx.in_cl), None, None, None, None, None, None
 
 
 class PseudoGridFunction(Function):
@@ -40,24 +74,24 @@ class PseudoGridFunction(Function):
     @staticmethod
     def forward(ctx, features, kernel_weights, query_xyz, support_xyz, query_mask, nbr, k_points, extent, influence,
                 precision):
-        feat_cl = ops.cm_to_cl(features.contiguous())
+        feat_cl, ctx.in_cl = _rows(features), is_channel_last(features)
         w = kernel_weights.contiguous()
         out_cl = ops.pseudogrid_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, k_points, w,
                                     extent, influence, precision)
         ctx.nbr, ctx.extent, ctx.influence, ctx.precision = nbr, extent, influence, precision
         ctx.save_for_backward(feat_cl, w, query_xyz, support_xyz, query_mask, k_points)
-        return ops.cl_to_cm(out_cl)
+        return _logical(out_cl, runtime.channel_last)
 
     @staticmethod
     def backward(ctx, grad_out):
         feat_cl, w, query_xyz, support_xyz, query_mask, k_points = ctx.saved_tensors
         nbr = ctx.nbr
         rowptr, entries = nbr.csr()
-        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        g_cl = _rows(grad_out)
         gf_cl, gw = ops.pseudogrid_bwd(g_cl, feat_cl, query_xyz, support_xyz, nbr.idx, rowptr, entries, nbr.nvalid,
                                        query_mask, k_points, w, ctx.extent, ctx.influence, ctx.precision,
                                        need_feat=ctx.needs_input_grad[0], need_weights=ctx.needs_input_grad[1])
-        gf = ops.cl_to_cm(gf_cl) if gf_cl is not None else None
+        gf = _logical(gf_cl, ctx.in_cl) if gf_cl is not None else None
         return gf, gw, None, None, None, None, None, None, None, None
 
 
@@ -66,19 +100,19 @@ class GatherMaxFunction(Function):
 
     @staticmethod
     def forward(ctx, features, nbr):
-        feat_cl = ops.cm_to_cl(features.contiguous())
+        feat_cl, ctx.in_cl = _rows(features), is_channel_last(features)
         out_cl, arg = ops.gather_max_fwd(feat_cl, nbr.idx)
         ctx.nbr = nbr
         ctx.save_for_backward(arg)
-        return ops.cl_to_cm(out_cl)
+        return _logical(out_cl, runtime.channel_last)
 
     @staticmethod
     def backward(ctx, grad_out):
         (arg,) = ctx.saved_tensors
         rowptr, entries = ctx.nbr.csr()
-        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        g_cl = _rows(grad_out)
         gf_cl = ops.gather_max_bwd(g_cl, arg, rowptr, entries, ctx.nbr.n_support)
-        return ops.cl_to_cm(gf_cl), None
+        return _logical(gf_cl, ctx.in_cl), None
 
 
 class NearestGatherFunction(Function):
@@ -86,17 +120,17 @@ class NearestGatherFunction(Function):
 
     @staticmethod
     def forward(ctx, features, nbr):
-        feat_cl = ops.cm_to_cl(features.contiguous())
+        feat_cl, ctx.in_cl = _rows(features), is_channel_last(features)
         out_cl = ops.nearest_gather_fwd(feat_cl, nbr.idx.view(nbr.idx.shape[0], nbr.idx.shape[1]))
         ctx.nbr = nbr
-        return ops.cl_to_cm(out_cl)
+        return _logical(out_cl, runtime.channel_last)
 
     @staticmethod
     def backward(ctx, grad_out):
         rowptr, entries = ctx.nbr.csr()
-        g_cl = ops.cm_to_cl(grad_out.contiguous())
+        g_cl = _rows(grad_out)
         gf_cl = ops.nearest_gather_bwd(g_cl, rowptr, entries, ctx.nbr.n_support)
-        return ops.cl_to_cm(gf_cl), None
+        return _logical(gf_cl, ctx.in_cl), None
 
 
 class BatchNormActFunction(Function):
@@ -104,10 +138,19 @@ class BatchNormActFunction(Function):
 
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu):
+        ctx.training, ctx.has_res = training, residual is not None
+        ctx.rows = is_channel_last(x) and x.shape[1] % 4 == 0
+        ctx.relu_mode = 0 if not relu else (2 if residual is not None else 1)
+        if ctx.rows:  # channel-last view in, channel-last view out: no layout change anywhere
+            xr = x.permute(0, 2, 1)
+            rr = _rows(residual) if residual is not None else None
+            y, mean, invstd = ops.bn_act_cl_fwd(xr, rr, weight, bias, running_mean, running_var, eps, momentum, training,
+                                                relu)
+            ctx.save_for_backward(xr, y if ctx.relu_mode == 2 else None, weight, bias, mean, invstd)
+            return y.permute(0, 2, 1)
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
         y, mean, invstd = ops.bn_act_fwd(x, res, weight, bias, running_mean, running_var, eps, momentum, training, relu)
-        ctx.training, ctx.has_res = training, residual is not None
         # the ReLU mask is recomputed from x in backward unless a residual was added (then y itself is needed)
         ctx.relu_mode = 0 if not relu else (2 if residual is not None else 1)
         ctx.save_for_backward(x, y if ctx.relu_mode == 2 else None, weight, bias, mean, invstd)
@@ -116,8 +159,15 @@ class BatchNormActFunction(Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, y, weight, bias, mean, invstd = ctx.saved_tensors
-        dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, bias, mean, invstd, ctx.training,
-                                                 ctx.relu_mode, ctx.has_res and ctx.needs_input_grad[1])
+        need_res = ctx.has_res and ctx.needs_input_grad[1]
+        if ctx.rows:
+            dx, dres, dgamma, dbeta = ops.bn_act_cl_bwd(_rows(grad_out), x, y, weight, bias, mean, invstd, ctx.training,
+                                                        ctx.relu_mode, need_res)
+            dx = dx.permute(0, 2, 1)
+            dres = dres.permute(0, 2, 1) if dres is not None else None
+        else:
+            dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, bias, mean, invstd,
+                                                     ctx.training, ctx.relu_mode, need_res)
         return (dx, dres, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
                 None, None, None)
 

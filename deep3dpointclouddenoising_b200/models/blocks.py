@@ -1,17 +1,26 @@
 """Conv1d / BatchNorm1d / ReLU stacks with the reference's module layout (nn.Sequential children '0', '1', '2', so
 state-dict keys are identical: ref u_net_arch/models/backbones/resnet.py:32-45, local_aggregation_operators.py:117-123,
 heads/multi_dimensional_head.py:40-59) whose forward runs every BatchNorm1d (+ following ReLU, + optional residual
-add) through the fused kernel (csrc/batchnorm.cu).  The 1x1 convolutions stay cuDNN/cuBLAS."""
+add) through the fused kernel (csrc/batchnorm.cu).  With `runtime.channel_last` (default) the 1x1 convolutions run
+as row-major GEMMs over (B*N, Cin) rows (cuBLAS through F.linear: same arithmetic as Conv1d with kernel_size 1), so
+activations stay in the channel-last layout of the aggregation kernels and no transposition is launched."""
 import torch.nn as nn
+import torch.nn.functional as F
 
-from ..fused import batch_norm_act
+from ..fused import batch_norm_act, rows_of
 from ..utils.config import runtime
+
+
+def _is_pointwise(m):
+    return (isinstance(m, nn.Conv1d) and m.kernel_size == (1,) and m.stride == (1,) and m.padding == (0,)
+            and m.dilation == (1,) and m.groups == 1 and m.padding_mode == 'zeros')
 
 
 class FusedSequential(nn.Sequential):
     def forward(self, x, residual=None, final_relu=False):
         mods = list(self._modules.values())
         use_fused = x.is_cuda and runtime.fused_batchnorm
+        use_rows = x.is_cuda and runtime.channel_last and x.dim() == 3
         i = 0
         while i < len(mods):
             m = mods[i]
@@ -24,7 +33,10 @@ class FusedSequential(nn.Sequential):
                     residual, final_relu = None, False
                 i += 2 if next_is_relu else 1
                 continue
-            x = m(x)
+            if use_rows and _is_pointwise(m):
+                x = F.linear(rows_of(x), m.weight.squeeze(-1), m.bias).permute(0, 2, 1)
+            else:
+                x = m(x)
             i += 1
         if residual is not None:
             x = x + residual

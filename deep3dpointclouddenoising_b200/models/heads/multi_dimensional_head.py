@@ -1,9 +1,9 @@
 """U-Net decoder head (mirror of u_net_arch/models/heads/multi_dimensional_head.py:16-85): four nearest
 upsamplings, skip concatenation, 1x1 conv blocks, and a final Conv1d to `num_classes` output dims
 (3 for offset regression).  Module names up0..up3, up_conv0..up_conv3, head are the reference's."""
-import torch
 import torch.nn as nn
 
+from ...fused import cat_channels
 from ...pt_custom_ops.pt_utils import MaskedUpsample
 from ..blocks import FusedSequential, conv_bn
 
@@ -33,6 +33,6 @@ class MultiDimHeadResNet(nn.Module):
             fine, coarse = f"res{4 - level}", f"res{5 - level}"
             features = getattr(self, f"up{level}")(end_points[fine + '_xyz'], end_points[coarse + '_xyz'],
                                                    end_points[fine + '_mask'], end_points[coarse + '_mask'], features)
-            features = torch.cat([features, end_points[fine + '_features']], 1)
+            features = cat_channels([features, end_points[fine + '_features']])
             features = getattr(self, f"up_conv{level}")(features)
         return self.head(features)

@@ -344,6 +344,43 @@ def bn_act_bwd(dy, x, y, gamma, beta, mean, invstd, training, relu_mode, need_re
     return dx, dres, dgamma, dbeta
 
 
+def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var, eps, momentum, training, relu):
+    """Channel-last variant: x_rows is a contiguous (..., C) tensor (rows = all leading dims)."""
+    L = _lib.load()
+    x_rows = _f32(x_rows, "input")
+    C = x_rows.shape[-1]
+    R = x_rows.numel() // C
+    with torch.cuda.device(x_rows.device):
+        y = torch.empty_like(x_rows)
+        mean = torch.empty((C,), dtype=torch.float32, device=x_rows.device)
+        invstd = torch.empty((C,), dtype=torch.float32, device=x_rows.device)
+        ws = _bn_ws(x_rows.device, C)
+        _lib.check(L.d3d_bn_act_cl_fwd(_p(x_rows), _p(residual_rows), _p(gamma), _p(beta), _p(running_mean),
+                                       _p(running_var), R, C, float(eps), float(momentum), int(bool(training)),
+                                       int(bool(relu)), _p(y), _p(mean), _p(invstd), _p(ws), ws.numel(), _stream()),
+                   "d3d_bn_act_cl_fwd")
+    _count()
+    return y, mean, invstd
+
+
+def bn_act_cl_bwd(dy_rows, x_rows, y_rows, gamma, beta, mean, invstd, training, relu_mode, need_res):
+    L = _lib.load()
+    dy_rows = _f32(dy_rows, "grad_out")
+    C = dy_rows.shape[-1]
+    R = dy_rows.numel() // C
+    with torch.cuda.device(dy_rows.device):
+        dx = torch.empty_like(dy_rows)
+        dres = torch.empty_like(dy_rows) if need_res else None
+        dgamma = torch.empty((C,), dtype=torch.float32, device=dy_rows.device)
+        dbeta = torch.empty((C,), dtype=torch.float32, device=dy_rows.device)
+        ws = _bn_ws(dy_rows.device, C)
+        _lib.check(L.d3d_bn_act_cl_bwd(_p(dy_rows), _p(x_rows), _p(y_rows), _p(gamma), _p(beta), _p(mean), _p(invstd), R, C,
+                                       int(bool(training)), int(relu_mode), _p(dx), _p(dres), _p(dgamma), _p(dbeta),
+                                       _p(ws), ws.numel(), _stream()), "d3d_bn_act_cl_bwd")
+    _count()
+    return dx, dres, dgamma, dbeta
+
+
 # ------------------------------------------------------------------------------------------------
 # exact nearest neighbours / Chamfer distance on large clouds
 # ------------------------------------------------------------------------------------------------

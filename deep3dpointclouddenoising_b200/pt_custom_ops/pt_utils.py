@@ -95,7 +95,7 @@ def _group(idx, query_xyz, support_xyz, features, radius, normalize_xyz, use_xyz
     if features is None:
         assert use_xyz, "Cannot have not features and not use xyz as a feature!"
         return rel, rel
-    grouped = grouping_operation(features, idx)
+    grouped = grouping_operation(features.contiguous(), idx)  # channel-last views are re-laid out for the composed path
     return (torch.cat([rel, grouped], dim=1) if use_xyz else grouped), rel
 
 

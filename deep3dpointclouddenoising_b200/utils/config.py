@@ -76,7 +76,9 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   'fp32' CUDA cores (parity tolerance 1e-5) | 'bf16' tcgen05 tensor cores (separate tolerance)
 # Kept outside the yaml-checked key set so that reference yaml files stay valid and unknown keys still raise.
 #   fused_batchnorm: BatchNorm1d (+ReLU, +residual) through csrc/batchnorm.cu instead of cuDNN/ATen (row f4)
-runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True})
+#   channel_last: fused ops return channel-last views and the 1x1 convolutions run as row-major GEMMs, so the
+#     network never transposes between the convolutions and the aggregations (fused.py, models/blocks.py)
+runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True})
 
 
 def reset_config():

@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("B,C,N", [(4, 72, 2048), (2, 144, 513), (3, 1152, 64), (16, 72, 8192)])
 @pytest.mark.parametrize("relu,residual", [(True, False), (False, False), (True, True)])
-def test_fused_bn_matches_torch(cuda_device, B, C, N, relu, residual):
+@pytest.mark.parametrize("channel_last", [False, True])
+def test_fused_bn_matches_torch(cuda_device, B, C, N, relu, residual, channel_last):
     from deep3dpointclouddenoising_b200.fused import batch_norm_act
     torch.manual_seed(C + N)
     bn_ref = nn.BatchNorm1d(C, momentum=0.1).to(cuda_device)
@@ -18,9 +19,16 @@ def test_fused_bn_matches_torch(cuda_device, B, C, N, relu, residual):
         bn_ref.bias.uniform_(-0.5, 0.5)
     bn = nn.BatchNorm1d(C, momentum=0.1).to(cuda_device)
     bn.load_state_dict(bn_ref.state_dict())
-    x = (torch.randn(B, C, N, device=cuda_device) * 2 + 3).requires_grad_(True)  # mean >> 0: exercises the shifted sums
-    res = torch.randn(B, C, N, device=cuda_device, requires_grad=True) if residual else None
-    g = torch.randn(B, C, N, device=cuda_device)
+    def make(scale, shift, grad):
+        if channel_last:  # (B, C, N) view of (B, N, C) rows: the d3d_bn_act_cl_* kernels, no layout change
+            t = (torch.randn(B, N, C, device=cuda_device) * scale + shift).requires_grad_(grad).permute(0, 2, 1)
+            assert not t.is_contiguous()
+            return t
+        return (torch.randn(B, C, N, device=cuda_device) * scale + shift).requires_grad_(grad)
+
+    x = make(2, 3, True)  # mean >> 0: exercises the shifted sums
+    res = make(1, 0, True) if residual else None
+    g = make(1, 0, False)
     for training in (True, False):
         bn.train(training)
         bn_ref.train(training)
@@ -30,6 +38,7 @@ def test_fused_bn_matches_torch(cuda_device, B, C, N, relu, residual):
         if relu:
             y_ref = torch.relu(y_ref)
         y = batch_norm_act(bn, x, relu=relu, residual=res)
+        assert y.is_contiguous() != channel_last
         torch.testing.assert_close(y, y_ref, rtol=1e-5, atol=2e-5)
         inputs = [x, bn.weight, bn.bias] + ([res] if res is not None else [])
         inputs_ref = [x, bn_ref.weight, bn_ref.bias] + ([res] if res is not None else [])
@@ -82,3 +91,38 @@ def test_model_with_and_without_fused_bn_agree(cuda_device):
     g0 = torch.cat([g.flatten() for g in outs[0][2].values()])
     g1 = torch.cat([g.flatten() for g in outs[1][2].values()])
     assert ((g0 - g1).norm() / g1.norm()).item() < 1e-2
+
+
+def test_model_channel_last_matches_channel_major(cuda_device):
+    """Whole U-Net with activations kept channel-last (row-major GEMM convolutions, d3d_bn_act_cl_*, aggregation
+    kernels without transposition) against the channel-major path (Conv1d, d3d_bn_act_*, transposes around every
+    aggregation).  fp32 everywhere (TF32 off); same amplification caveat as above."""
+    from deep3dpointclouddenoising_b200 import synthetic
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    import bench
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        outs = []
+        for operator in ("pospool", "pseudo_grid"):
+            model, criterion, cfg = bench.build_model(operator, 4096)
+            model = model.to(cuda_device)
+            batch = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(5, 4, 4096, ragged=True)]
+            state = {k: v.clone() for k, v in model.state_dict().items()}
+            for flag in (True, False):
+                runtime.channel_last = flag
+                model.load_state_dict(state)
+                model.zero_grad(set_to_none=True)
+                pred = model(batch[0], batch[1], batch[2])
+                assert pred.shape == (4, 3, 4096)
+                loss = criterion(pred.transpose(1, 2), batch[3], batch[1])
+                loss.backward()
+                outs.append((pred.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+            rel = ((outs[-2][0] - outs[-1][0]).norm() / outs[-1][0].norm()).item()
+            assert rel < 1e-3, (operator, rel)
+            num = sum(((outs[-2][1][n] - outs[-1][1][n]) ** 2).sum() for n in outs[-1][1]).sqrt().item()
+            den = sum((outs[-1][1][n] ** 2).sum() for n in outs[-1][1]).sqrt().item()
+            assert num / den < 2e-2, (operator, num / den)
+    finally:
+        runtime.channel_last = True
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
