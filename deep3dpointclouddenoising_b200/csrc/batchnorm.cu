@@ -40,14 +40,17 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // fixed order — deterministic — and finalises.  The counters are zeroed by the finaliser for the next launch.
 __device__ __forceinline__ bool last_block_of_channel(unsigned* counters, int c, int S) {
   __shared__ bool is_last;
-  __threadfence();  // this block's partials are visible before the ticket is taken
+  __syncthreads();  // every partial of this block is written ...
   if (threadIdx.x == 0) {
+    __threadfence();  // ... and (fences are cumulative) visible device-wide before the ticket is taken
     const unsigned ticket = atomicAdd(&counters[c], 1u);
     is_last = (ticket == (unsigned)S - 1u);
-    if (is_last) counters[c] = 0u;
+    if (is_last) {
+      counters[c] = 0u;
+      __threadfence();
+    }
   }
   __syncthreads();
-  if (is_last) __threadfence();
   return is_last;
 }
 
@@ -94,7 +97,7 @@ bn_stats_kernel(const float* __restrict__ x, int B, int C, int N, int S, float e
   if (!last_block_of_channel(counters, c, S)) return;
   if (threadIdx.x == 0) {
     double a1 = 0.0, a2 = 0.0;
-    for (int k = 0; k < S; ++k) { a1 += partials[((size_t)c * S + k) * 2]; a2 += partials[((size_t)c * S + k) * 2 + 1]; }
+    for (int k = 0; k < S; ++k) { a1 += __ldcg(&partials[((size_t)c * S + k) * 2]); a2 += __ldcg(&partials[((size_t)c * S + k) * 2 + 1]); }
     const double n = (double)B * N;
     const double m = a1 / n;                       // mean of the shifted data
     double var = a2 / n - m * m;                   // biased variance
@@ -303,7 +306,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   if (!last_block_of_channel(counters, c, S)) return;
   if (threadIdx.x == 0) {
     double a1 = 0.0, a2 = 0.0;
-    for (int k = 0; k < S; ++k) { a1 += partials[((size_t)c * S + k) * 2]; a2 += partials[((size_t)c * S + k) * 2 + 1]; }
+    for (int k = 0; k < S; ++k) { a1 += __ldcg(&partials[((size_t)c * S + k) * 2]); a2 += __ldcg(&partials[((size_t)c * S + k) * 2 + 1]); }
     a2 *= (double)is;  // sum(dyr * xhat)
     if (dbeta) dbeta[c] = (float)a1;
     if (dgamma) dgamma[c] = (float)a2;
@@ -368,10 +371,11 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ running_mean, con
 // Channel-last variants: the activation is (R, C) row-major with R = B*N rows — the layout the local aggregation
 // kernels gather from and write.  With the 1x1 convolutions run as (R, Cin) x (Cin, Cout) GEMMs the whole network
 // stays in this layout and no transposition kernel is needed between the convolutions and the aggregations.
-// A thread owns one float4 of channels; a block covers kClGroups float4 columns x (256 / groups) rows per iteration,
-// which is one contiguous span of memory when the block spans all channels.
+// A thread owns one float4 of channels; a block covers up to kClGroups float4 columns x (256 / groups) rows per
+// iteration.
 constexpr int kClThreads = 256;
-constexpr int kClGroups = 64;  // float4 channel groups per block at most (256 channels)
+constexpr int kClGroups = 8;  // float4 channel groups per block at most: 128-byte row segments.  Narrow slabs keep
+                              // the number of blocks per channel — hence the partials the finaliser reads — small
 
 struct ClGeom {
   int c4, groups, rows_per_iter, gx;
@@ -380,48 +384,69 @@ __host__ __device__ inline ClGeom cl_geom(int C) {
   ClGeom g;
   g.c4 = C / 4;
   g.groups = g.c4 < kClGroups ? g.c4 : kClGroups;
+  for (int d = kClGroups; d >= 4; --d)  // prefer a width that divides the channel count: no idle threads
+    if (g.c4 % d == 0) { g.groups = d; break; }
   g.rows_per_iter = kClThreads / g.groups;
   g.gx = (g.c4 + g.groups - 1) / g.groups;
   return g;
 }
 
-// Sums the per-thread float4 pairs over the rows of the block (fp64), stores the block's partials and returns true in
-// the row-0 threads of the LAST block of this channel slab, with tot1/tot2 = the S partials added in fixed order.
+// Tree reduction over the rows of the block: sh[0..7][row * groups + cx] -> row 0 (value-major: conflict-free).
+// Fixed shape, so deterministic.
+__device__ __forceinline__ void cl_tree(double (*sh)[kClThreads], int cx, int ry, bool active, const ClGeom g) {
+  for (int n = g.rows_per_iter; n > 1;) {
+    const int h = (n + 1) >> 1;
+    if (active && ry + h < n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + h * g.groups];
+    }
+    __syncthreads();
+    n = h;
+  }
+}
+
+// Sums the per-thread float4 pairs over the rows of the block, stores the block's fp64 partials; in the LAST block of
+// this channel slab all threads then add the S partials (thread (cx, ry) takes k = ry, ry + rows, ...; fixed order, so
+// the result is deterministic) and the row-0 threads return true with the totals in tot1 / tot2.
 __device__ __forceinline__ bool cl_combine(const float4 s1, const float4 s2, int cx, int ry, int group, bool active,
                                            const ClGeom g, int C, int S, double* __restrict__ partials,
                                            unsigned* __restrict__ counters, double tot1[4], double tot2[4]) {
-  __shared__ float4 sh1[kClThreads], sh2[kClThreads];
-  sh1[threadIdx.x] = s1;
-  sh2[threadIdx.x] = s2;
-  __syncthreads();
-  const bool owner = active && ry == 0;
-  if (owner) {
-    double a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
-    for (int r = 0; r < g.rows_per_iter; ++r) {
-      const float4 u = sh1[r * g.groups + cx], v = sh2[r * g.groups + cx];
-      a1[0] += u.x; a1[1] += u.y; a1[2] += u.z; a1[3] += u.w;
-      a2[0] += v.x; a2[1] += v.y; a2[2] += v.z; a2[3] += v.w;
-    }
+  __shared__ double sh[8][kClThreads];
+  const float f[8] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const size_t slot = ((size_t)(group * 4 + j) * S + blockIdx.y) * 2;
-      partials[slot] = a1[j];
-      partials[slot + 1] = a2[j];
+  for (int j = 0; j < 8; ++j) sh[j][threadIdx.x] = (double)f[j];
+  __syncthreads();
+  cl_tree(sh, cx, ry, active, g);
+  const bool owner = active && ry == 0;
+  if (S == 1) {  // one block per slab: nothing to combine across blocks
+    if (owner) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { tot1[j] = sh[j][threadIdx.x]; tot2[j] = sh[4 + j][threadIdx.x]; }
     }
+    return owner;
+  }
+  if (owner) {
+    // partials: [slab][S][column in slab][8]  -> the finaliser reads them coalesced
+    double* dst = partials + (((size_t)blockIdx.x * S + blockIdx.y) * g.groups + cx) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j] = sh[j][threadIdx.x];
   }
   if (!last_block_of_channel(counters, blockIdx.x, S)) return false;
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    for (int k = ry; k < S; k += g.rows_per_iter) {  // a handful of iterations: S <= ~150 per slab
+      const double* src = partials + (((size_t)blockIdx.x * S + k) * g.groups + cx) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += __ldcg(src + j);  // L2: written by other SMs in this launch
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[j][threadIdx.x] = a[j];
+  __syncthreads();
+  cl_tree(sh, cx, ry, active, g);
   if (!owner) return false;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    double a1 = 0.0, a2 = 0.0;
-    for (int k = 0; k < S; ++k) {
-      const size_t slot = ((size_t)(group * 4 + j) * S + k) * 2;
-      a1 += partials[slot];
-      a2 += partials[slot + 1];
-    }
-    tot1[j] = a1;
-    tot2[j] = a2;
-  }
+  for (int j = 0; j < 4; ++j) { tot1[j] = sh[j][threadIdx.x]; tot2[j] = sh[4 + j][threadIdx.x]; }
   return true;
 }
 
@@ -436,13 +461,26 @@ bn_stats_cl_kernel(const float* __restrict__ x, long long R, int C, int S, float
   float4 s1 = make_float4(0, 0, 0, 0), s2 = s1, shift = s1;
   if (active) {
     shift = __ldg(reinterpret_cast<const float4*>(x) + group);  // row 0
-    const float4* col = reinterpret_cast<const float4*>(x) + group;
+    // loads are issued in batches of 8 before any is consumed (a plain unrolled loop keeps its exit test between
+    // consecutive loads, which leaves one load in flight per thread)
+    const long long r0 = (long long)blockIdx.y * g.rows_per_iter + ry;
     const long long step = (long long)S * g.rows_per_iter;
-    for (long long r = (long long)blockIdx.y * g.rows_per_iter + ry; r < R; r += step) {
-      const float4 v = __ldg(col + r * g.c4);
+    const int iters = r0 < R ? (int)((R - r0 + step - 1) / step) : 0;
+    const float4* p = reinterpret_cast<const float4*>(x) + r0 * g.c4 + group;
+    const long long pstep = step * g.c4;
+    auto acc = [&](const float4 v) {
       const float a0 = v.x - shift.x, a1 = v.y - shift.y, a2 = v.z - shift.z, a3 = v.w - shift.w;
       s1.x += a0; s1.y += a1; s1.z += a2; s1.w += a3;
       s2.x += a0 * a0; s2.y += a1 * a1; s2.z += a2 * a2; s2.w += a3 * a3;
+    };
+    for (int it = 0; it < iters; it += 8, p += 8 * pstep) {  // the tail batch is predicated, not serialised
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (it + j < iters) v[j] = __ldg(p + j * pstep);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (it + j < iters) acc(v[j]);
     }
   }
   double t1[4], t2[4];
@@ -523,13 +561,29 @@ bn_bwd_reduce_cl_kernel(const float* __restrict__ dy, const float* __restrict__ 
   float4 s1 = make_float4(0, 0, 0, 0), s2 = s1, m = s1, is = s1, scale = s1, offset = s1;
   if (active) {
     cl_scale_offset(gamma, beta, mean, invstd, group, m, is, scale, offset);
+    const long long r0 = (long long)blockIdx.y * g.rows_per_iter + ry;
     const long long step = (long long)S * g.rows_per_iter;
-    for (long long r = (long long)blockIdx.y * g.rows_per_iter + ry; r < R; r += step) {
-      const long long e = r * g.c4 + group;
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e);
-      const float4 d = cl_masked_dy(__ldg(reinterpret_cast<const float4*>(dy) + e), xv, y, e, relu, scale, offset);
+    const int iters = r0 < R ? (int)((R - r0 + step - 1) / step) : 0;
+    long long e = r0 * g.c4 + group;
+    const long long estep = step * g.c4;
+    const float4* dy4 = reinterpret_cast<const float4*>(dy);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    auto acc = [&](const float4 dv, const float4 xv, long long at) {
+      const float4 d = cl_masked_dy(dv, xv, y, at, relu, scale, offset);
       s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
       s2.x += d.x * (xv.x - m.x); s2.y += d.y * (xv.y - m.y); s2.z += d.z * (xv.z - m.z); s2.w += d.w * (xv.w - m.w);
+    };
+    for (int it = 0; it < iters; it += 4, e += 4 * estep) {  // 8 independent loads in flight; predicated tail
+      float4 dv[4], xv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (it + j < iters) {
+          dv[j] = __ldg(dy4 + e + j * estep);
+          xv[j] = __ldg(x4 + e + j * estep);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (it + j < iters) acc(dv[j], xv[j], e + j * estep);
     }
   }
   double t1[4], t2[4];
@@ -572,11 +626,14 @@ bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x
   reinterpret_cast<float4*>(dx)[e] = o;
 }
 
+constexpr int kClBlocks = 148 * 4;  // four 8-warp blocks per SM, 8 independent 16-byte loads in flight per thread;
+                                    // more splits only lengthen the finaliser's chain of L2 round trips
+
 int cl_splits(const ClGeom g, long long R) {
-  long long S = (148 * 3 + g.gx - 1) / g.gx;
-  const long long max_s = (R + g.rows_per_iter - 1) / g.rows_per_iter;
+  long long S = (kClBlocks + g.gx - 1) / g.gx;
+  const long long max_s = (R + 4LL * g.rows_per_iter - 1) / (4LL * g.rows_per_iter);  // >= 4 rows per thread
   if (S > max_s) S = max_s;
-  if (S > 64) S = 64;
+  if (R * g.groups * 16 <= 300 * 1024) S = 1;  // a slab a single block streams in ~2 us: skip partials and ticket
   if (S < 1) S = 1;
   return (int)S;
 }
@@ -605,15 +662,22 @@ extern "C" {
 
 /* workspace layout (both directions): [sums: 2*C float][partials: C*S*2 double][counters: C unsigned, must be ZERO
  * before the first use; the kernels leave them zero] */
+static size_t partial_doubles(int C) {
+  // channel-major kernels: C * 64 splits * 2; channel-last kernels: slabs * S * groups * 8 with slabs * S <= 148 * 4 + slabs
+  const size_t cm = (size_t)C * 64 * 2;
+  const size_t cl = (size_t)(148 * 4 + (C + 15) / 16) * kClGroups * 8;
+  return cm > cl ? cm : cl;
+}
+
 size_t d3d_bn_act_workspace_bytes(int C) {
   if (C <= 0) return 0;
-  return align256((size_t)C * 2 * sizeof(float)) + align256((size_t)C * 64 * 2 * sizeof(double)) + align256((size_t)C * sizeof(unsigned));
+  return align256((size_t)C * 2 * sizeof(float)) + align256(partial_doubles(C) * sizeof(double)) + align256((size_t)C * sizeof(unsigned));
 }
 
 static void carve(void* ws, int C, float** sums, double** partials, unsigned** counters) {
   unsigned char* p = (unsigned char*)ws;
   *sums = (float*)p; p += align256((size_t)C * 2 * sizeof(float));
-  *partials = (double*)p; p += align256((size_t)C * 64 * 2 * sizeof(double));
+  *partials = (double*)p; p += align256(partial_doubles(C) * sizeof(double));
   *counters = (unsigned*)p;
 }
 

@@ -4,11 +4,54 @@ heads/multi_dimensional_head.py:40-59) whose forward runs every BatchNorm1d (+ f
 add) through the fused kernel (csrc/batchnorm.cu).  With `runtime.channel_last` (default) the 1x1 convolutions run
 as row-major GEMMs over (B*N, Cin) rows (cuBLAS through F.linear: same arithmetic as Conv1d with kernel_size 1), so
 activations stay in the channel-last layout of the aggregation kernels and no transposition is launched."""
+import contextlib
+
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
+from torch.autograd import Function
 
 from ..fused import batch_norm_act, rows_of
 from ..utils.config import runtime
+
+
+@contextlib.contextmanager
+def _conv_math():
+    """The reference's Conv1d runs under torch.backends.cudnn.allow_tf32 (default True: TF32 tensor cores); the GEMM
+    form follows the same switch instead of cuBLAS's own (default False: fp32 SIMT, 10x slower on these shapes)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32
+    try:
+        yield
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class PointwiseConvRows(Function):
+    """Conv1d(kernel_size=1) on channel-last rows: (B, N, Cin) x (Cout, Cin, 1) -> (B, N, Cout), three cuBLAS GEMMs
+    (forward, data gradient, weight gradient)."""
+
+    @staticmethod
+    def forward(ctx, rows, weight, bias):
+        w = weight.squeeze(-1)
+        ctx.save_for_backward(rows, w)
+        ctx.has_bias = bias is not None
+        with _conv_math():
+            return F.linear(rows, w, bias)
+
+    @staticmethod
+    def backward(ctx, grad):
+        rows, w = ctx.saved_tensors
+        g2 = grad.contiguous().view(-1, grad.shape[-1])
+        d_rows = d_w = d_b = None
+        with _conv_math():
+            if ctx.needs_input_grad[0]:
+                d_rows = (g2 @ w).view_as(rows)
+            if ctx.needs_input_grad[1]:
+                d_w = (g2.t() @ rows.reshape(-1, rows.shape[-1])).unsqueeze(-1)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            d_b = g2.sum(0)
+        return d_rows, d_w, d_b
 
 
 def _is_pointwise(m):
@@ -34,7 +77,7 @@ class FusedSequential(nn.Sequential):
                 i += 2 if next_is_relu else 1
                 continue
             if use_rows and _is_pointwise(m):
-                x = F.linear(rows_of(x), m.weight.squeeze(-1), m.bias).permute(0, 2, 1)
+                x = PointwiseConvRows.apply(rows_of(x), m.weight, m.bias).permute(0, 2, 1)
             else:
                 x = m(x)
             i += 1
