@@ -25,8 +25,11 @@ def is_channel_last(t):
 
 
 def _rows(t):
-    """Contiguous (B, N, C) rows of a logical (B, C, N) tensor (no copy for channel-last views)."""
-    return t.permute(0, 2, 1) if is_channel_last(t) else ops.cm_to_cl(t.contiguous())
+    """Contiguous (B, N, C) rows of a logical (B, C, N) tensor: no copy for channel-last views, a row-wise copy for
+    channel slices of one (the gradient of a skip concatenation), a transposition for channel-major tensors."""
+    if t.dim() == 3 and t.stride(1) == 1 and t.shape[1] > 1:
+        return t.permute(0, 2, 1).contiguous()
+    return ops.cm_to_cl(t.contiguous())
 
 
 def _logical(rows, channel_last):

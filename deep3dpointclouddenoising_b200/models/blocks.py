@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.autograd import Function
 
-from ..fused import batch_norm_act, rows_of
+from ..fused import batch_norm_act, cat_channels, is_channel_last, rows_of
 from ..utils.config import runtime
 
 
@@ -65,6 +65,44 @@ class PointwiseConvRows(Function):
         return d_rows, d_w, d_b
 
 
+class PointwiseConvCatRows(Function):
+    """Conv1d(kernel_size=1) applied to the channel concatenation of several row tensors WITHOUT materialising it:
+    y = sum_i rows_i @ W[:, slice_i]^T.  The decoder's skip concatenations (multi_dimensional_head.py:36) then cost no
+    copy forward and hand each branch a contiguous gradient backward (a torch.cat would give strided slices that the
+    next kernel has to re-pack)."""
+
+    @staticmethod
+    def forward(ctx, weight, bias, *rows_list):
+        w = weight.squeeze(-1)
+        ctx.save_for_backward(w, *rows_list)
+        ctx.has_bias = bias is not None
+        with _conv_math():
+            c0 = rows_list[0].shape[-1]
+            y = F.linear(rows_list[0], w[:, :c0], bias)
+            y2 = y.view(-1, y.shape[-1])
+            for rows in rows_list[1:]:
+                c1 = c0 + rows.shape[-1]
+                y2.addmm_(rows.reshape(-1, rows.shape[-1]), w[:, c0:c1].t())
+                c0 = c1
+        return y
+
+    @staticmethod
+    def backward(ctx, grad):
+        w, *rows_list = ctx.saved_tensors
+        g2 = grad.contiguous().view(-1, grad.shape[-1])
+        d_rows, d_w, c0 = [], [], 0
+        with _conv_math():
+            for i, rows in enumerate(rows_list):
+                c1 = c0 + rows.shape[-1]
+                d_rows.append((g2 @ w[:, c0:c1]).view_as(rows) if ctx.needs_input_grad[2 + i] else None)
+                if ctx.needs_input_grad[0]:
+                    d_w.append(_weight_grad(g2, rows.reshape(-1, rows.shape[-1])))
+                c0 = c1
+        d_weight = torch.cat(d_w, 1).unsqueeze(-1) if ctx.needs_input_grad[0] else None
+        d_b = g2.sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
+        return (d_weight, d_b, *d_rows)
+
+
 def _is_pointwise(m):
     return (isinstance(m, nn.Conv1d) and m.kernel_size == (1,) and m.stride == (1,) and m.padding == (0,)
             and m.dilation == (1,) and m.groups == 1 and m.padding_mode == 'zeros')
@@ -72,7 +110,17 @@ def _is_pointwise(m):
 
 class FusedSequential(nn.Sequential):
     def forward(self, x, residual=None, final_relu=False):
+        """x: a (B, C, N) tensor, or a list of them standing for their channel concatenation."""
         mods = list(self._modules.values())
+        if isinstance(x, (list, tuple)):
+            parts = list(x)
+            if (parts[0].is_cuda and runtime.channel_last and _is_pointwise(mods[0])
+                    and all(is_channel_last(t) for t in parts)):
+                x = PointwiseConvCatRows.apply(mods[0].weight, mods[0].bias, *[t.permute(0, 2, 1) for t in parts])
+                x = x.permute(0, 2, 1)
+                mods = mods[1:]
+            else:
+                x = cat_channels(parts)
         use_fused = x.is_cuda and runtime.fused_batchnorm
         use_rows = x.is_cuda and runtime.channel_last and x.dim() == 3
         i = 0

@@ -3,7 +3,6 @@ upsamplings, skip concatenation, 1x1 conv blocks, and a final Conv1d to `num_cla
 (3 for offset regression).  Module names up0..up3, up_conv0..up_conv3, head are the reference's."""
 import torch.nn as nn
 
-from ...fused import cat_channels
 from ...pt_custom_ops.pt_utils import MaskedUpsample
 from ..blocks import FusedSequential, conv_bn
 
@@ -33,6 +32,6 @@ class MultiDimHeadResNet(nn.Module):
             fine, coarse = f"res{4 - level}", f"res{5 - level}"
             features = getattr(self, f"up{level}")(end_points[fine + '_xyz'], end_points[coarse + '_xyz'],
                                                    end_points[fine + '_mask'], end_points[coarse + '_mask'], features)
-            features = cat_channels([features, end_points[fine + '_features']])
-            features = getattr(self, f"up_conv{level}")(features)
+            # torch.cat([features, skip], 1) -> up_conv (ref :36-37); the block consumes the pair without the copy
+            features = getattr(self, f"up_conv{level}")([features, end_points[fine + '_features']])
         return self.head(features)
