@@ -116,6 +116,7 @@ struct Args {
   float extent;
   int n_items_max;  // items staged per piece (multiple of 16, <= 256)
   int tmem_cols;
+  int rows_per_cta;
 };
 
 // kBackward: rows are support points and items are inverse-map entries; else rows are queries, items are slots.
@@ -124,7 +125,7 @@ struct Args {
 // resident CTAs (8 per SM: <= 64 registers, 64 TMEM columns) and the next row's index/coordinate loads are issued
 // before the current row's gathers are consumed.
 template <bool kBackward, bool kTensorCore>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, kTensorCore ? 8 : 6)
 pseudogrid_rows_kernel(const Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -177,8 +178,8 @@ pseudogrid_rows_kernel(const Args a) {
   const float* src_b = a.src + (size_t)b * (kBackward ? a.M : a.N) * C;
   const float coef = influence_coef(a.extent, a.influence);
 
-  for (int ri = 0; ri < kRowsPerCta; ++ri) {
-    const int row = blockIdx.x * kRowsPerCta + ri;
+  for (int ri = 0; ri < a.rows_per_cta; ++ri) {
+    const int row = blockIdx.x * a.rows_per_cta + ri;
     if (row >= n_rows) break;  // block-uniform
     const size_t grow = (size_t)b * n_rows + row;
     int item_beg = 0, n_items = 0;
@@ -402,13 +403,16 @@ pseudogrid_weight_grad_kernel(const float* __restrict__ grad_out, const float* _
 // (16 per K-step, up to 64 per row), accumulated in ONE TMEM tile over every row the CTA visits.  A thread owns a
 // channel: it gathers its 16 features per K-step, multiplies by g, rounds to bf16 and writes them as two 16-byte
 // stores into the K-major A tile (its own row of the tile); the B tile holds the influence weights transposed.
-// Two staging buffers: while the tensor core consumes one, the threads fill the other.
+// kDwBufs staging buffers (see below).
 constexpr int kDwItems = 64;                         // items staged per buffer (4 K-steps)
 constexpr int kDwABytes = (kDwItems / 16) * 4096;    // 4 x [128 x 16] bf16
 constexpr int kDwBBytes = (kDwItems / 16) * 512;     // 4 x [16 x 16] bf16
 constexpr int kDwBufBytes = kDwABytes + kDwBBytes;
+// Staging buffers per CTA.  One: 23 KB of shared memory per CTA, 8 resident CTAs per SM hide each other's MMA waits
+// and row latencies (measured faster than two buffers at 5 CTAs per SM: the kernel is bound by the per-row chain).
+constexpr int kDwBufs = 1;
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)
 pseudogrid_weight_grad_tc_kernel(const float* __restrict__ grad_out, const float* __restrict__ feat,
                                  const float* __restrict__ query_xyz, const float* __restrict__ support_xyz,
                                  const int* __restrict__ idx, const int* __restrict__ nvalid,
@@ -420,7 +424,7 @@ pseudogrid_weight_grad_tc_kernel(const float* __restrict__ grad_out, const float
   __shared__ unsigned tmem_base_slot;
   __shared__ float kp[52];
   unsigned char* bufs = smem;                                           // 2 x (A | B)
-  int* srow = reinterpret_cast<int*>(smem + 2 * kDwBufBytes);           // kDwItems offsets
+  int* srow = reinterpret_cast<int*>(smem + kDwBufs * kDwBufBytes);     // kDwItems offsets
   float* srel = reinterpret_cast<float*>(srow + kDwItems);              // kDwItems x 3
   float* w_f32 = srel + 3 * kDwItems;                                   // kDwItems x 16 (fp32 staging of the weights)
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -535,17 +539,17 @@ pseudogrid_weight_grad_tc_kernel(const float* __restrict__ grad_out, const float
       }
       n_issued += ksteps;
       pending[buf] = 1;
-      buf ^= 1;
+      buf = (buf + 1) % kDwBufs;
     }
   }
   // drain: both buffers' MMA groups complete (in issue order), then read the accumulator
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < kDwBufs; ++k) {
     if (pending[buf]) {
       mbar_wait(smem_u32(&mbar[buf]), phase[buf]);
       phase[buf] ^= 1u;
       pending[buf] = 0;
     }
-    buf ^= 1;
+    buf = (buf + 1) % kDwBufs;
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   unsigned r[16];
@@ -604,7 +608,9 @@ int launch_rows(Args a, int B, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int n_rows = kBackward ? a.N : a.M;
-  dim3 grid(d3d_ceil_div(n_rows, kRowsPerCta), B);
+  const char* env_rows = getenv("D3D_PG_ROWS");
+  a.rows_per_cta = env_rows ? atoi(env_rows) : kRowsPerCta;
+  dim3 grid(d3d_ceil_div(n_rows, a.rows_per_cta), B);
   kernel<<<grid, kThreads, smem, st>>>(a);
   d3d_note_launches(1);
   return d3d_launch_status();
@@ -660,13 +666,21 @@ int d3d_pseudogrid_bwd(const float* grad_out_cl, const float* feat_cl, const flo
   if (grad_weights) {
     if (M == 0) return (int)cudaMemsetAsync(grad_weights, 0, (size_t)K * C * sizeof(float), st);
     if (!ws || ws_bytes < d3d_pseudogrid_bwd_workspace_bytes(B, M, C, K)) return D3D_ERR_WORKSPACE;
-    const int nblk = weight_blocks(B, M, C);
+    int nblk = weight_blocks(B, M, C);
     const size_t smem = (size_t)((nsample + 7) & ~7) * (kK * sizeof(float) + sizeof(int) + 3 * sizeof(float)) + 16;
     cudaError_t e = cudaFuncSetAttribute(pseudogrid_weight_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((C + 127) / 128, nblk);
     if (precision == 1) {
-      const size_t smem_tc = 2 * kDwBufBytes + (size_t)kDwItems * (sizeof(int) + 3 * sizeof(float) + kK * sizeof(float)) + 16;
+      const size_t smem_tc = kDwBufs * kDwBufBytes + (size_t)kDwItems * (sizeof(int) + 3 * sizeof(float) + kK * sizeof(float)) + 16;
+      // exactly one wave: every CTA walks its share of the rows start to finish, so a partial second wave would run
+      // at a fraction of the machine (1776 CTAs at 5 resident per SM took 2.4 waves' worth of 3)
+      const char* env_occ = getenv("D3D_PG_DW_CTAS_PER_SM");
+      int per_sm = env_occ ? atoi(env_occ) : (int)((227 * 1024) / (smem_tc + 1024));
+      if (per_sm > 8) per_sm = 8;  // __launch_bounds__(kThreads, 8)
+      const int one_wave = (148 * (per_sm < 1 ? 1 : per_sm)) / (int)grid.x;
+      if (one_wave >= 1 && one_wave < nblk) nblk = one_wave;
+      grid.y = nblk;
       e = cudaFuncSetAttribute(pseudogrid_weight_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
       if (e != cudaSuccess) return (int)e;
       pseudogrid_weight_grad_tc_kernel<<<grid, kThreads, smem_tc, st>>>(grad_out_cl, feat_cl, query_xyz, support_xyz, idx,
