@@ -305,14 +305,18 @@ def main():
     # gradient averaging when world > 1 (train_dist.py:375 uses DDP): `--graph off` wraps the model in DDP exactly like
     # the reference; the graph mode uses one flat gradient bucket + a single NCCL all-reduce that is captured with
     # the rest of the step (DDP's reducer hooks do not replay)
+    # In graph mode parameters and gradients are additionally views of two flat buffers (distributed.FlatParameters):
+    # Adam and the gradient clipping then run on one tensor — same arithmetic, a handful of launches.
     bucket = None
-    if world > 1 and args.graph != "off":
+    use_graph = args.graph != "off"
+    if use_graph:
         net = model
-        bucket = distributed.FlatGradAllReduce(model.parameters())
+        bucket = distributed.FlatParameters(model)
+        opt_params = [bucket.param]
     else:
         net = distributed.wrap(model, local_rank)
-    use_graph = args.graph != "off"
-    opt = torch.optim.Adam(model.parameters(), lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay,
+        opt_params = list(model.parameters())
+    opt = torch.optim.Adam(opt_params, lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay,
                            capturable=use_graph)
     B, N = args.batch, args.num_points
 
@@ -329,7 +333,7 @@ def main():
         loss.backward()
         if bucket is not None:
             bucket.reduce()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 10)
+        torch.nn.utils.clip_grad_norm_(opt_params, 10)
         opt.step()
         return loss
 

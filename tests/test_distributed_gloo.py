@@ -68,3 +68,34 @@ def test_two_rank_gradient_allreduce_and_sharding(tmp_path):
     assert not torch.equal(r0["local"], r1["local"])  # the ranks really worked on different shards
     assert r0["seed"] != r1["seed"] and not torch.equal(r0["points"], r1["points"])
     assert r0["times"] == r1["times"] == [11.0, 5.0]  # max over ranks, element-wise
+
+
+def test_flat_parameters_match_per_tensor_adam_and_clipping():
+    """distributed.FlatParameters: Adam + clip_grad_norm_ on the one flat parameter == on the individual tensors."""
+    from deep3dpointclouddenoising_b200 import distributed
+
+    def make():
+        torch.manual_seed(3)
+        return torch.nn.Sequential(torch.nn.Conv1d(3, 10, 1), torch.nn.BatchNorm1d(10), torch.nn.ReLU(),
+                                   torch.nn.Conv1d(10, 3, 1))  # sizes 30, 10, 10, 10, 30, 3: exercises the padding
+
+    x = torch.randn(4, 3, 50)
+    ref, flat_model = make(), make()
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-2, weight_decay=1e-3)
+    flat = distributed.FlatParameters(flat_model)
+    assert all(p.data_ptr() % 16 == 0 for p in flat_model.parameters())
+    opt_flat = torch.optim.Adam([flat.param], lr=1e-2, weight_decay=1e-3)
+    for _ in range(5):
+        opt_ref.zero_grad(set_to_none=True)
+        ref(x).abs().sum().backward()
+        n_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        opt_ref.step()
+        flat.zero()
+        flat_model(x).abs().sum().backward()
+        flat.reduce()  # world size 1: no-op
+        n_flat = torch.nn.utils.clip_grad_norm_([flat.param], 0.5)
+        opt_flat.step()
+        torch.testing.assert_close(n_flat, n_ref, rtol=1e-5, atol=1e-7)
+    for a, b in zip(flat_model.parameters(), ref.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+    assert set(flat_model.state_dict()) == set(ref.state_dict())
