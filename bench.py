@@ -316,8 +316,9 @@ def main():
     else:
         net = distributed.wrap(model, local_rank)
         opt_params = list(model.parameters())
+    # fused=True: torch's single-kernel Adam (same update rule) — with the flat parameter it is ONE launch per step
     opt = torch.optim.Adam(opt_params, lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay,
-                           capturable=use_graph)
+                           capturable=use_graph, fused=True if use_graph else None)
     B, N = args.batch, args.num_points
 
     def host_batch(step):  # per-rank shard of the synthetic patch stream
