@@ -475,7 +475,9 @@ def main():
                            "pseudo_grid_precision": args.pseudo_grid_precision if args.operator == "pseudo_grid" else None,
                            "parallelism": f"dp{world}", "optimizer": "adam",
                            "grad_allreduce": None if world == 1 else ("flat bucket, 1 NCCL all-reduce" if bucket is not None else "DDP"),
-                           "cuda_graph": graph is not None, "l2": "per-step working set (activations, "
+                           "cuda_graph": graph is not None,
+                           "layout": "channel-last activations end to end" if cfgmod.runtime.channel_last else "channel-major",
+                           "conv_math": "tf32" if torch.backends.cudnn.allow_tf32 else "fp32", "l2": "per-step working set (activations, "
                            "several GB) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
