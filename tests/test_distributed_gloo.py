@@ -102,6 +102,8 @@ def test_flat_parameters_match_per_tensor_adam_and_clipping():
         n_flat = torch.nn.utils.clip_grad_norm_([flat.param], 0.5)
         opt_flat.step()
         torch.testing.assert_close(n_flat, n_ref, rtol=1e-5, atol=1e-7)
+    # Adam divides by sqrt(v): for a parameter whose gradient is ~0 the last-bit differences of two reduction orders
+    # are amplified to ~1e-6 after 5 steps of size 1e-2 — hence atol 1e-5 (a wrong update rule is off by ~1e-2)
     for a, b in zip(flat_model.parameters(), ref.parameters()):
-        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
     assert set(flat_model.state_dict()) == set(ref.state_dict())
