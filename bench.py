@@ -453,6 +453,43 @@ def main():
                             "the aggregation kernels are bound by the L2->SM gather of B*M*ns*C*4 bytes (reported under "
                             "'gather'), the ball query by instruction issue (brute-force pair scan)"}
 
+    # ---- neighbour build alone (BASELINE.json metric, second figure): the full 5-level pyramid of one batch ----
+    neighbor_build = None
+    if rank == 0:
+        from deep3dpointclouddenoising_b200 import ops as d3d_ops
+
+        def pyramid(pts, mask):  # resnet.py:94-188 + multi_dimensional_head.py:62-85: 4 subsamplings, 9 distinct ball
+            xyz, m, r, dl = pts, mask, float(cfg.radius), float(cfg.sampleDl)  # queries, 4 nearest-upsample queries
+            d3d_ops.ball_query(xyz, xyz, m, m, r, cfg.nsamples[0], want_nvalid=True)
+            levels = [(xyz, m)]
+            for stage in range(4):
+                dl *= 2
+                sx, sm = d3d_ops.grid_subsample(xyz, m, cfg.npoints[stage], dl)
+                d3d_ops.ball_query(sx, xyz, sm, m, r, cfg.nsamples[stage], want_nvalid=True)
+                r *= 2
+                d3d_ops.ball_query(sx, sx, sm, sm, r, cfg.nsamples[stage + 1], want_nvalid=True)
+                levels.append((sx, sm))
+                xyz, m = sx, sm
+            for stage in range(4, 0, -1):
+                d3d_ops.nearest_query(levels[stage - 1][0], levels[stage][0], levels[stage - 1][1], levels[stage][1])
+            return sum(lv[0].shape[1] for lv in levels)
+
+        for _ in range(3):
+            pyramid(resident[0][0], resident[0][1])
+        n_rep = 20
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s in range(n_rep):
+            pyramid(resident[s % n_host][0], resident[s % n_host][1])
+        t1.record()
+        torch.cuda.synchronize()
+        nb_ms = t0.elapsed_time(t1) / n_rep
+        neighbor_build = {"value": round(B * N / nb_ms / 1e3, 2), "unit": "Mpts/s (patch points per second, one GPU)",
+                          "ms_per_batch": round(nb_ms, 4),
+                          # ball queries: N + 2 per coarser level; nearest queries: every level but the coarsest
+                          "query_points_per_batch": B * (N + 2 * sum(cfg.npoints) + N + sum(cfg.npoints[:3])),
+                          "ops": "4 grid subsamplings + 9 ordered ball queries + 4 nearest queries, eager launches"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -482,6 +519,8 @@ def main():
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels}
+        if neighbor_build is not None:
+            line["neighbor_build"] = neighbor_build
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
