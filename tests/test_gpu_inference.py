@@ -51,6 +51,47 @@ def test_voxel_barycentres_match_reference_cpu(cuda_device):
     assert np.array_equal(key(got), key(ref))
 
 
+def test_config0_pyramid_on_100k_cloud(cuda_device):
+    """BASELINE configs[0]: 5-level grid subsampling + radius neighbours of one 100k-point noisy shape.  Every level's
+    barycentres equal the reference's grid_subsampling.cpp bit for bit (as sets: the reference emits hash-map order),
+    and the radius neighbour lists equal sklearn's KDTree.query_radius (the reference's neighbour search on the host)."""
+    from deep3dpointclouddenoising_b200 import inference, ops
+    from oracle import cpu_index_ops
+    pts = _cloud(100_000, 0)
+    try:
+        ref = cpu_index_ops.ref_gridsub_cpu()
+    except (FileNotFoundError, OSError):
+        ref = None
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    cur_gpu, cur_ref = torch.from_numpy(pts).to(cuda_device), pts
+    sizes = []
+    for level in range(5):
+        dl = 0.01 * 2 ** level
+        sub, counts = inference.voxel_barycentres(cur_gpu, dl)
+        got = sub.cpu().numpy()
+        assert int(counts.sum()) == cur_gpu.shape[0]
+        if ref is not None:
+            cur_ref = ref.compute(cur_ref, dl)
+            assert np.array_equal(key(got), key(cur_ref)), level
+        radius = 2.5 * dl
+        idx, cnt = ops.radius_patches(sub, sub.contiguous(), radius, 64)
+        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+        tree = KDTree(got)
+        probe = np.arange(0, len(got), max(len(got) // 300, 1))
+        ref_idx, ref_d = tree.query_radius(got[probe], r=radius, return_distance=True, sort_results=True)
+        for k, p_ in enumerate(probe):
+            assert cnt[p_] == len(ref_idx[k]), (level, p_)
+            take = min(cnt[p_], 64)
+            if not np.array_equal(idx[p_, :take], ref_idx[k][:take]):  # equal-distance groups may be ordered differently
+                d_got = np.linalg.norm(got[idx[p_, :take]].astype(np.float64) - got[p_], axis=1)
+                np.testing.assert_allclose(d_got, ref_d[k][:take], rtol=1e-12, atol=1e-12)
+        sizes.append(len(got))
+        # the next level sums points in input order (fp32): both sides continue from the SAME array, the reference's
+        # own output order when it is available
+        cur_gpu = torch.from_numpy(cur_ref).to(cuda_device) if ref is not None else sub.contiguous()
+    assert sizes == sorted(sizes, reverse=True) and sizes[-1] >= 1
+
+
 def test_radius_patches_match_kdtree(cuda_device):
     from deep3dpointclouddenoising_b200 import inference, ops
     pts = _cloud(30000, 2)
