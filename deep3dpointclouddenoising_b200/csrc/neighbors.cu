@@ -24,6 +24,7 @@ namespace {
 // tuning knobs (overridable through the environment for experiments: D3D_BQ_WARPS in {4,8,16}, D3D_BQ_TILE)
 constexpr int kBqDefaultWarps = 16;  // measured on B200 (tools/bq_sweep.py): 16 warps x 2048-support tiles is the fastest of the sweep
 constexpr int kBqDefaultTile = 2048;  // supports staged per shared-memory tile
+constexpr int kScanMinN = 1024;       // at most this many supports: the fill kernel scans them all and finds the nearest itself
 
 __global__ void prefix_len_kernel(const int* __restrict__ mask, int N, int* __restrict__ vlen) {
   __shared__ int first_zero;
@@ -223,7 +224,9 @@ constexpr float kFar = 1.0e30f;
 //          ascending index order; stops as soon as the list holds 3*nsample entries (on the BASELINE patches after
 //          ~1/4 of the supports on average); a block leaves the tile loop once all of its lists are full;
 //   then : nearest-swap with pass 1's result, histogram pre-selection, rank sort, coalesced row emission.
-template <int QW, int kBqWarps>
+// kScanMin (small support sets, N <= kScanMinN): the kernel scans every support itself and keeps the running nearest
+// in-radius support — one launch instead of grid build + grid search + this kernel, which are pure latency there.
+template <int QW, int kBqWarps, bool kScanMin>
 __global__ void __launch_bounds__(kBqWarps * 32)
 ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__ support_xyz,
                   const int* __restrict__ query_mask, const int* __restrict__ vlen,
@@ -254,17 +257,21 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
 
   float qx[QW], qy[QW], qz[QW];
   int cnt[QW];
+  float near_d2[QW];  // kScanMin: this lane's running nearest in-radius support (:45-47, :59-62)
+  int near_k[QW];
 #pragma unroll
   for (int u = 0; u < QW; ++u) {
     const int j = min(q0 + u, M - 1);
     qx[u] = Q[3 * j + 0]; qy[u] = Q[3 * j + 1]; qz[u] = Q[3 * j + 2];
     cnt[u] = 0;
+    near_d2[u] = r2;
+    near_k[u] = 0;
   }
 
   for (int base = 0; base < v; base += tile) {
     bool filling = false;
 #pragma unroll
-    for (int u = 0; u < QW; ++u) filling = filling || (cnt[u] < cap && q0 + u < M);
+    for (int u = 0; u < QW; ++u) filling = filling || ((kScanMin || cnt[u] < cap) && q0 + u < M);
     if (!__syncthreads_or(filling ? 1 : 0)) break;  // every list of the block is full (also: previous tile consumed)
     const int tile_n = min(tile, v - base);
     for (int i = threadIdx.x; i < tile; i += blockDim.x) {
@@ -280,10 +287,11 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
     // ---- fill pass, one query at a time, until its list is full
 #pragma unroll
     for (int u = 0; u < QW; ++u) {
-      for (int st = 0; st < steps && cnt[u] < cap; ++st) {
+      for (int st = 0; st < steps && (kScanMin || cnt[u] < cap); ++st) {
         const int i = (st << 5) + lane;
         const float d2 = d3d_dist2(qx[u], qy[u], qz[u], sx[i], sy[i], sz[i]);
         const bool inr = d2 < r2;
+        if (kScanMin && d2 < near_d2[u]) { near_d2[u] = d2; near_k[u] = base + i; }  // a lane's indices ascend
         const unsigned ball = __ballot_sync(D3D_FULL_MASK, inr);
         if (ball) {
           const int pos = cnt[u] + __popc(ball & lt_mask);
@@ -304,10 +312,22 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
     __syncwarp();
     if (cnt[u] >= cap) {
       // :72-75  the global nearest in-radius support (pass 1) lies beyond the last slot -> it replaces the last slot
-      if (lane == 0) {
-        const int bk = best_k[(size_t)b * M + j];
-        if (bk > (int)(unsigned)(list[cap - 1] & 0xffffffffull)) list[cap - 1] = make_key(best_d2[(size_t)b * M + j], bk);
+      float bd;
+      int bk;
+      if (kScanMin) {  // warp minimum of (d2, index): smaller distance, then lower index — the scan order's winner
+        unsigned long long key = make_key(near_d2[u], near_k[u]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(D3D_FULL_MASK, key, o);
+          key = other < key ? other : key;
+        }
+        bd = __uint_as_float((unsigned)(key >> 32));
+        bk = (int)(unsigned)(key & 0xffffffffull);
+      } else {
+        bd = best_d2[(size_t)b * M + j];
+        bk = best_k[(size_t)b * M + j];
       }
+      if (lane == 0 && bk > (int)(unsigned)(list[cap - 1] & 0xffffffffull)) list[cap - 1] = make_key(bd, bk);
       __syncwarp();
     }
     // Pre-selection: only the nsample smallest keys are emitted.  d2 -> bin is monotone, so every key in a
@@ -435,33 +455,33 @@ size_t bq_smem_bytes(int warps, int qw, int nsample, int tile) {
          (size_t)warps * qw * nsample * sizeof(int) + (size_t)warps * 32 * sizeof(int);
 }
 
-template <int QW, int WARPS>
+template <int QW, int WARPS, bool SCAN>
 int launch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, const float* best_d2,
                       const int* best_k, int B, int M, int N, float radius, int nsample, int* idx, int* idx_mask,
                       int* nvalid, cudaStream_t st) {
   const int tile = bq_tile(N);
   const size_t smem = bq_smem_bytes(WARPS, QW, nsample, tile);
-  cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<QW, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<QW, WARPS, SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(d3d_ceil_div(M, WARPS * QW), B);
-  ball_query_kernel<QW, WARPS><<<grid, WARPS * 32, smem, st>>>(q, s, qm, vlen, best_d2, best_k, M, N, tile, radius, nsample,
+  ball_query_kernel<QW, WARPS, SCAN><<<grid, WARPS * 32, smem, st>>>(q, s, qm, vlen, best_d2, best_k, M, N, tile, radius, nsample,
                                                              idx, idx_mask, nvalid);
   d3d_note_launches(1);
   return d3d_launch_status();
 }
 
-template <int WARPS>
+template <int WARPS, bool SCAN>
 int dispatch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, const float* best_d2,
                         const int* best_k, int B, int M, int N, float radius, int nsample, int* idx, int* idx_mask,
                         int* nvalid, cudaStream_t st) {
   const size_t budget = 220 * 1024;  // opt-in shared memory per block on sm_100a is 227 KB
   const int tile = bq_tile(N);
   if (bq_smem_bytes(WARPS, 4, nsample, tile) <= budget / 2)
-    return launch_ball_query<4, WARPS>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<4, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   if (bq_smem_bytes(WARPS, 2, nsample, tile) <= budget / 2)
-    return launch_ball_query<2, WARPS>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<2, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   if (bq_smem_bytes(WARPS, 1, nsample, tile) <= budget)
-    return launch_ball_query<1, WARPS>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<1, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   return D3D_ERR_UNSUPPORTED;
 }
 
@@ -500,14 +520,22 @@ int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* 
   float* best_d2 = (float*)p; p += bq_align((size_t)B * M * sizeof(float));
   int* best_k = (int*)p;
   d3d_launch_prefix_len(support_mask, B, N, vlen, st);
+  const int warps = env_int("D3D_BQ_WARPS", kBqDefaultWarps);
+  if (N <= env_int("D3D_BQ_SCANMIN_N", kScanMinN)) {  // small support set: one launch, the kernel finds the nearest itself
+    switch (warps) {
+      case 4: return dispatch_ball_query<4, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+      case 16: return dispatch_ball_query<16, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+      default: return dispatch_ball_query<8, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    }
+  }
   ball_grid_build_kernel<<<B, 1024, 0, st>>>(support_xyz, vlen, N, grids, cell_start, sorted);
   ball_nearest_kernel<<<dim3(d3d_ceil_div(M, 128), B), 128, 0, st>>>(query_xyz, grids, cell_start, sorted, M, N, radius, best_d2,
                                                                    best_k);
   d3d_note_launches(2);
-  switch (env_int("D3D_BQ_WARPS", kBqDefaultWarps)) {
-    case 4: return dispatch_ball_query<4>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-    case 16: return dispatch_ball_query<16>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-    default: return dispatch_ball_query<8>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+  switch (warps) {
+    case 4: return dispatch_ball_query<4, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    case 16: return dispatch_ball_query<16, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    default: return dispatch_ball_query<8, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
   }
 }
 
