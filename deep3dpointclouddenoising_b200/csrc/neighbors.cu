@@ -24,7 +24,7 @@ namespace {
 // tuning knobs (overridable through the environment for experiments: D3D_BQ_WARPS in {4,8,16}, D3D_BQ_TILE)
 constexpr int kBqDefaultWarps = 16;  // measured on B200 (tools/bq_sweep.py): 16 warps x 2048-support tiles is the fastest of the sweep
 constexpr int kBqDefaultTile = 2048;  // supports staged per shared-memory tile
-constexpr int kScanMinN = 1024;       // at most this many supports: the fill kernel scans them all and finds the nearest itself
+constexpr int kScanMinN = 2048;       // at most this many supports: the fill kernel scans them all and finds the nearest itself
 
 __global__ void prefix_len_kernel(const int* __restrict__ mask, int N, int* __restrict__ vlen) {
   __shared__ int first_zero;
