@@ -164,11 +164,20 @@ pseudogrid_rows_kernel(const Args a) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int e = tid; e < n_ctile * 128 * 16; e += kThreads) {
-      const int ct = e >> 11, k = (e >> 7) & 15, cl = e & 127;  // consecutive threads -> consecutive channels
-      const int c = ct * 128 + cl;
-      const float w = (c < C && k < K) ? a.weights[(size_t)k * C + c] : 0.0f;
-      *reinterpret_cast<__nv_bfloat16*>(a_tiles + (size_t)ct * kTileBytes + operand_offset(cl, k)) = __float2bfloat16_rn(w);
+    // A tiles (W^T, K-major): a thread owns one channel = one 32-byte operand row per tile: 16 coalesced loads, two
+    // 16-byte stores (k 0..7 and, one K chunk = LBO further, k 8..15)
+    for (int ct = 0; ct < n_ctile; ++ct) {
+      const int c = ct * 128 + tid;
+      __nv_bfloat162 h[8];
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        const float w0 = (c < C && 2 * k2 < K) ? __ldg(a.weights + (size_t)(2 * k2) * C + c) : 0.0f;
+        const float w1 = (c < C && 2 * k2 + 1 < K) ? __ldg(a.weights + (size_t)(2 * k2 + 1) * C + c) : 0.0f;
+        h[k2] = __floats2bfloat162_rn(w0, w1);
+      }
+      unsigned char* dst = a_tiles + (size_t)ct * kTileBytes + (tid >> 3) * kSbo + (tid & 7) * 16;
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&h[0]);
+      *reinterpret_cast<uint4*>(dst + kLbo) = *reinterpret_cast<const uint4*>(&h[4]);
     }
   }
   if (tid < 52) kp[tid] = tid < K * 3 ? a.kpoints[tid] : 0.0f;
