@@ -7,9 +7,11 @@ The 1x1 convolutions and BatchNorm stay in PyTorch (outside the hot path, SURVEY
 between them — subsampling, neighbour lists, max-pool, local aggregation — runs on the fused kernels.
 One forward builds each distinct neighbour list once (neighbors.cache) instead of 14 ball queries.
 """
+import torch
 import torch.nn as nn
 
 from ... import neighbors as _neighbors
+from ...utils.config import runtime
 from ...pt_custom_ops.pt_utils import MaskedMaxPool
 from ..blocks import conv_bn
 from ..local_aggregation_operators import LocalAggregation
@@ -63,9 +65,12 @@ class ResNet(nn.Module):
         self.conv1 = _conv_bn(input_features_dim, half, config.bn_momentum, relu=True)
         self.la1 = LocalAggregation(half, half, radius, nsamples[0], config)
         self.btnk1 = Bottleneck(half, width, bottleneck_ratio, radius, nsamples[0], config)
+        # what one forward will ask neighbors.py for, with the very values handed to the modules below (cache keys)
+        self._radius0, self._nsample0, self._stages = radius, nsamples[0], []
         # four strided stages: each halves the resolution (grid cell x2) and doubles radius and width
         for stage in range(4):
             sampleDl *= 2
+            self._stages.append((sampleDl, npoints[stage], radius, nsamples[stage], radius * 2, nsamples[stage + 1]))
             layer = MultiInputSequential()
             layer.add_module("strided_bottleneck",
                              Bottleneck(width, 2 * width, bottleneck_ratio, radius, nsamples[stage], config,
@@ -79,6 +84,10 @@ class ResNet(nn.Module):
 
     def forward(self, xyz, mask, features, end_points=None):
         _neighbors.cache.clear()  # neighbour lists are valid for one forward only
+        if runtime.prefetch_neighbors and xyz.is_cuda:
+            # the whole pyramid (+ inverse maps when gradients are on) goes to a side stream and overlaps with the
+            # convolutions / BatchNorm / aggregations below; consumers wait on per-item events (neighbors.py)
+            _neighbors.prebuild(xyz, mask, self._radius0, self._nsample0, self._stages, torch.is_grad_enabled())
         if not end_points:
             end_points = {}
         features = self.conv1(features)

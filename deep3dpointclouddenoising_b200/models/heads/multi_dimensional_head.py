@@ -3,6 +3,7 @@ upsamplings, skip concatenation, 1x1 conv blocks, and a final Conv1d to `num_cla
 (3 for offset regression).  Module names up0..up3, up_conv0..up_conv3, head are the reference's."""
 import torch.nn as nn
 
+from ... import neighbors as _neighbors
 from ...pt_custom_ops.pt_utils import MaskedUpsample
 from ..blocks import FusedSequential, conv_bn
 
@@ -34,4 +35,5 @@ class MultiDimHeadResNet(nn.Module):
                                                    end_points[fine + '_mask'], end_points[coarse + '_mask'], features)
             # torch.cat([features, skip], 1) -> up_conv (ref :36-37); the block consumes the pair without the copy
             features = getattr(self, f"up_conv{level}")([features, end_points[fine + '_features']])
+        _neighbors.join()  # side-stream neighbourhood work of this forward (neighbors.prebuild) is complete from here on
         return self.head(features)

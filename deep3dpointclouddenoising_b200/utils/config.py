@@ -78,7 +78,9 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   fused_batchnorm: BatchNorm1d (+ReLU, +residual) through csrc/batchnorm.cu instead of cuDNN/ATen (row f4)
 #   channel_last: fused ops return channel-last views and the 1x1 convolutions run as row-major GEMMs, so the
 #     network never transposes between the convolutions and the aggregations (fused.py, models/blocks.py)
-runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True})
+#   prefetch_neighbors: the backbone enqueues all neighbourhood structures of a forward on a side stream (neighbors.py)
+runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
+                    "prefetch_neighbors": True})
 
 
 def reset_config():
