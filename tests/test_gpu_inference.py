@@ -156,3 +156,16 @@ def test_extract_and_vote(cuda_device):
         c[inds_h[b][mask_h[b]]] += 1
     np.testing.assert_allclose(mean.cpu().numpy(), s / c, rtol=1e-5, atol=1e-5)
     assert np.array_equal(votes.cpu().numpy(), np.round(c[:, 0]))
+
+
+def test_denoise_cloud_graph_replay_equals_eager(cuda_device):
+    """Full-shape inference (row f2): the CUDA-graph replay of the per-batch forward gives the eager result."""
+    import bench
+    from deep3dpointclouddenoising_b200 import inference
+    pts = torch.from_numpy(_cloud(60000, 5)).to(cuda_device)
+    model, _, _ = bench.build_model("pospool", 1024)
+    model = model.to(cuda_device).eval()
+    out_g = inference.denoise_cloud(model, pts, 0.05, 0.05, 1024, batch_size=4, use_graph=True)
+    out_e = inference.denoise_cloud(model, pts, 0.05, 0.05, 1024, batch_size=4, use_graph=False)
+    assert torch.equal(out_g[2], out_e[2]) and bool((out_g[2] > 0).all())  # votes: every point covered
+    torch.testing.assert_close(out_g[1], out_e[1], rtol=1e-5, atol=1e-6)
