@@ -9,7 +9,10 @@
 //     __ballot_sync + prefix popcount gives every in-radius support its slot in ASCENDING INDEX
 //     order — exactly the reference's append order — without any atomics;
 //   * supports are staged tile by tile in shared memory in SoA form (conflict-free, shared by the
-//     8 warps = 32 queries of the block);
+//     16 warps = 32 queries of the block), the next tile travelling through registers meanwhile;
+//   * the reference's "nearest in-radius support over ALL supports" (it replaces the last candidate
+//     when the list overflowed) comes from an exact uniform-grid search per cloud (ball_grid_build +
+//     ball_nearest) — or, for support sets of at most kScanMinN points, from the fill scan itself;
 //   * candidates live in shared memory as 64-bit keys (d2 bits << 32 | index): d2 >= 0 so the IEEE
 //     bit pattern is monotonic and one integer compare is the reference's stable sort-by-distance
 //     order (ties -> lower index first);

@@ -128,9 +128,10 @@ struct Args {
 
 // kBackward: rows are support points and items are inverse-map entries; else rows are queries, items are slots.
 // kTensorCore: E from tcgen05.mma into TMEM; else 16 fp32 FMAs per (item, channel) against W in registers.
-// Per-row latency chain (stage -> MMA -> TMEM load -> gathers) is what bounds this kernel, so it is tuned for many
-// resident CTAs (8 per SM: <= 64 registers, 64 TMEM columns) and the next row's index/coordinate loads are issued
-// before the current row's gathers are consumed.
+// ncu: the tensor-core variant is instruction-issue bound (73 % of the issue slots; 40 % of the instructions are the
+// gather epilogue, 26 % the influence weights), with barrier waits between the per-row phases as the main stall — so
+// it runs 8 resident CTAs per SM (<= 64 registers, 64 TMEM columns each) and keeps the per-gather address arithmetic
+// at one 64-bit add.  Prefetching the next row's indices was measured and changed nothing (not latency-bound).
 template <bool kBackward, bool kTensorCore>
 __global__ void __launch_bounds__(kThreads, kTensorCore ? 8 : 6)
 pseudogrid_rows_kernel(const Args a) {
