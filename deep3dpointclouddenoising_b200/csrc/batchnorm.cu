@@ -452,8 +452,9 @@ __device__ __forceinline__ bool cl_combine(const float4 s1, const float4 s2, int
 
 __global__ void __launch_bounds__(kClThreads)
 bn_stats_cl_kernel(const float* __restrict__ x, long long R, int C, int S, float eps, float momentum,
-                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
-                   float* __restrict__ save_invstd, double* __restrict__ partials, unsigned* __restrict__ counters) {
+                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ num_batches,
+                   float* __restrict__ save_mean, float* __restrict__ save_invstd, double* __restrict__ partials,
+                   unsigned* __restrict__ counters) {
   const ClGeom g = cl_geom(C);
   const int cx = threadIdx.x % g.groups, ry = threadIdx.x / g.groups;
   const int group = blockIdx.x * g.groups + cx;
@@ -485,6 +486,7 @@ bn_stats_cl_kernel(const float* __restrict__ x, long long R, int C, int S, float
   }
   double t1[4], t2[4];
   if (!cl_combine(s1, s2, cx, ry, group, active, g, C, S, partials, counters, t1, t2)) return;
+  if (group == 0 && num_batches) *num_batches += 1;  // BatchNorm1d.num_batches_tracked: one thread per launch gets here
   const float sh[4] = {shift.x, shift.y, shift.z, shift.w};
   const double n = (double)R;
 #pragma unroll
@@ -751,8 +753,9 @@ int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float*
 /* Channel-last variants: x, residual, y, dy, dx, dres are (R, C) row-major with R = B * N rows.  C % 4 == 0 and
  * 16-byte aligned pointers are required (D3D_ERR_ARG otherwise: the caller falls back to the channel-major entry). */
 int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
-                      float* running_var, long long R, int C, float eps, float momentum, int training, int relu, float* y,
-                      float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, void* stream) {
+                      float* running_var, long long* num_batches_tracked, long long R, int C, float eps, float momentum,
+                      int training, int relu, float* y, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes,
+                      void* stream) {
   D3D_REQUIRE(x && y && save_mean && save_invstd);
   D3D_REQUIRE(R > 0 && C > 0 && C % 4 == 0);
   D3D_REQUIRE(aligned16(x) && aligned16(residual) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
@@ -765,8 +768,8 @@ int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma,
     float* sums; double* partials; unsigned* counters;
     carve(ws, C, &sums, &partials, &counters);
     const int S = cl_splits(g, R);
-    bn_stats_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(x, R, C, S, eps, momentum, running_mean, running_var, save_mean,
-                                                             save_invstd, partials, counters);
+    bn_stats_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(x, R, C, S, eps, momentum, running_mean, running_var,
+                                                             num_batches_tracked, save_mean, save_invstd, partials, counters);
   } else {
     bn_eval_stats_kernel<<<d3d_ceil_div(C, 256), 256, 0, st>>>(running_mean, running_var, C, eps, save_mean, save_invstd);
   }

@@ -140,7 +140,7 @@ class BatchNormActFunction(Function):
     """y = act(BatchNorm1d(x) [+ residual]) in one statistics pass and one apply pass (csrc/batchnorm.cu)."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu, counter=None):
         ctx.training, ctx.has_res = training, residual is not None
         ctx.rows = is_channel_last(x) and x.shape[1] % 4 == 0
         ctx.relu_mode = 0 if not relu else (2 if residual is not None else 1)
@@ -148,9 +148,11 @@ class BatchNormActFunction(Function):
             xr = x.permute(0, 2, 1)
             rr = _rows(residual) if residual is not None else None
             y, mean, invstd = ops.bn_act_cl_fwd(xr, rr, weight, bias, running_mean, running_var, eps, momentum, training,
-                                                relu)
+                                                relu, counter)  # num_batches_tracked += 1 rides on the statistics kernel
             ctx.save_for_backward(xr, y if ctx.relu_mode == 2 else None, weight, bias, mean, invstd)
             return y.permute(0, 2, 1)
+        if counter is not None:
+            counter.add_(1)
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
         y, mean, invstd = ops.bn_act_fwd(x, res, weight, bias, running_mean, running_var, eps, momentum, training, relu)
@@ -172,14 +174,19 @@ class BatchNormActFunction(Function):
             dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, bias, mean, invstd,
                                                      ctx.training, ctx.relu_mode, need_res)
         return (dx, dres, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
-                None, None, None)
+                None, None, None, None)
 
 
 def batch_norm_act(bn, x, relu, residual=None):
     """Applies nn.BatchNorm1d module `bn` (its parameters, buffers, momentum, eps, training flag) with the fused kernel."""
     training = bn.training or bn.running_mean is None
-    if bn.training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-    momentum = bn.momentum if bn.momentum is not None else 1.0 / float(max(int(bn.num_batches_tracked), 1))
+    counter = bn.num_batches_tracked if (bn.training and bn.num_batches_tracked is not None) else None
+    if bn.momentum is None:  # cumulative moving average: the factor needs the updated count on the host
+        if counter is not None:
+            counter.add_(1)
+            counter = None
+        momentum = 1.0 / float(max(int(bn.num_batches_tracked), 1))
+    else:
+        momentum = bn.momentum
     return BatchNormActFunction.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, momentum,
-                                      training, relu)
+                                      training, relu, counter)

@@ -344,8 +344,12 @@ def bn_act_bwd(dy, x, y, gamma, beta, mean, invstd, training, relu_mode, need_re
     return dx, dres, dgamma, dbeta
 
 
-def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var, eps, momentum, training, relu):
-    """Channel-last variant: x_rows is a contiguous (..., C) tensor (rows = all leading dims)."""
+def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var, eps, momentum, training, relu,
+                  num_batches_tracked=None):
+    """Channel-last variant: x_rows is a contiguous (..., C) tensor (rows = all leading dims).  num_batches_tracked:
+    the module's int64 counter, incremented inside the statistics kernel in training mode."""
+    if num_batches_tracked is not None and not (training and num_batches_tracked.dtype == torch.int64):
+        num_batches_tracked = None
     L = _lib.load()
     x_rows = _f32(x_rows, "input")
     C = x_rows.shape[-1]
@@ -356,7 +360,8 @@ def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var,
         invstd = torch.empty((C,), dtype=torch.float32, device=x_rows.device)
         ws = _bn_ws(x_rows.device, C)
         _lib.check(L.d3d_bn_act_cl_fwd(_p(x_rows), _p(residual_rows), _p(gamma), _p(beta), _p(running_mean),
-                                       _p(running_var), R, C, float(eps), float(momentum), int(bool(training)),
+                                       _p(running_var), _p(num_batches_tracked), R, C, float(eps), float(momentum),
+                                       int(bool(training)),
                                        int(bool(relu)), _p(y), _p(mean), _p(invstd), _p(ws), ws.numel(), _stream()),
                    "d3d_bn_act_cl_fwd")
     _count()

@@ -185,9 +185,12 @@ int d3d_bn_act_bwd(const float* dy, const float* x, const float* y, const float*
 /* Channel-last variants: every activation is (R, C) row-major with R = B * N rows — the layout the aggregation
  * kernels read and write, so a network whose 1x1 convolutions run as row-major GEMMs needs no transposition at all.
  * Requires C % 4 == 0 and 16-byte aligned pointers (D3D_ERR_ARG otherwise).  Same workspace, same semantics. */
+/* num_batches_tracked (device int64 scalar, may be NULL) is incremented by one in training mode — the counter
+ * torch.nn.BatchNorm1d keeps — so that the host does not launch a kernel of its own for it. */
 int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* running_mean,
-                      float* running_var, long long R, int C, float eps, float momentum, int training, int relu,
-                      float* y, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes, void* stream);
+                      float* running_var, long long* num_batches_tracked, long long R, int C, float eps, float momentum,
+                      int training, int relu, float* y, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes,
+                      void* stream);
 int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* beta,
                       const float* save_mean, const float* save_invstd, long long R, int C, int training, int relu,
                       float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
