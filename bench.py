@@ -313,6 +313,9 @@ def main():
         net = model
         bucket = distributed.FlatParameters(model)
         opt_params = [bucket.param]
+        # every gradient buffer exists for the whole run and nothing hooks the gradients: the backward kernels add
+        # into the buffers directly instead of returning tensors that autograd accumulates with ~120 tiny add kernels
+        cfgmod.runtime.grads_in_place = True
     else:
         net = distributed.wrap(model, local_rank)
         opt_params = list(model.parameters())

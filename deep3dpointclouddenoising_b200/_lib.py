@@ -54,7 +54,7 @@ SIGNATURES = {
     "d3d_bn_act_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_bn_act_bwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "d3d_bn_act_cl_fwd": (_i, [_vp] * 7 + [_ll, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "d3d_bn_act_cl_bwd": (_i, [_vp] * 7 + [_ll, _i, _i, _i] + [_vp] * 5 + [_sz, _vp]),
+    "d3d_bn_act_cl_bwd": (_i, [_vp] * 7 + [_ll, _i, _i, _i] + [_vp] * 4 + [_i, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -553,9 +553,9 @@ __device__ __forceinline__ float4 cl_masked_dy(float4 d, const float4 xv, const 
 __global__ void __launch_bounds__(kClThreads)
 bn_bwd_reduce_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                        const float* __restrict__ invstd, long long R, int C, int S, int relu, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, float* __restrict__ sums, double* __restrict__ partials,
-                        unsigned* __restrict__ counters) {
+                        const float* __restrict__ invstd, long long R, int C, int S, int relu, int accumulate,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ sums,
+                        double* __restrict__ partials, unsigned* __restrict__ counters) {
   const ClGeom g = cl_geom(C);
   const int cx = threadIdx.x % g.groups, ry = threadIdx.x / g.groups;
   const int group = blockIdx.x * g.groups + cx;
@@ -595,8 +595,9 @@ bn_bwd_reduce_cl_kernel(const float* __restrict__ dy, const float* __restrict__ 
   for (int j = 0; j < 4; ++j) {
     const int c = group * 4 + j;
     const double a2 = t2[j] * (double)isv[j];
-    if (dbeta) dbeta[c] = (float)t1[j];
-    if (dgamma) dgamma[c] = (float)a2;
+    // accumulate != 0: dgamma / dbeta ARE the parameters' gradient buffers (+=, one thread per channel: no race)
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)t1[j];
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)a2;
     sums[2 * c] = (float)t1[j];
     sums[2 * c + 1] = (float)a2;
   }
@@ -782,7 +783,8 @@ int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma,
 
 int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* beta,
                       const float* save_mean, const float* save_invstd, long long R, int C, int training, int relu, float* dx,
-                      float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream) {
+                      float* dres, float* dgamma, float* dbeta, int accumulate_param_grads, void* ws, size_t ws_bytes,
+                      void* stream) {
   D3D_REQUIRE(dy && x && save_mean && save_invstd && dx);
   D3D_REQUIRE(R > 0 && C > 0 && C % 4 == 0 && relu >= 0 && relu <= 2);
   D3D_REQUIRE(relu != 2 || y);
@@ -795,7 +797,7 @@ int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const flo
   const ClGeom g = cl_geom(C);
   const int S = cl_splits(g, R);
   bn_bwd_reduce_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, R, C, S, relu,
-                                                                dgamma, dbeta, sums, partials, counters);
+                                                                accumulate_param_grads, dgamma, dbeta, sums, partials, counters);
   const long long total4 = R * g.c4;
   bn_bwd_apply_cl_kernel<<<(unsigned)d3d_ceil_div(total4, 256), 256, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, sums,
                                                                              g.c4, total4, 1.0f / (float)R, relu, training, dx,

@@ -19,6 +19,12 @@ from . import ops
 from .utils.config import runtime
 
 
+def _is_grad_buffer(p):
+    """A parameter whose gradient buffer exists and can be written by a kernel (runtime.grads_in_place)."""
+    g = getattr(p, "grad", None)
+    return g is not None and g.is_contiguous() and g.dtype == torch.float32 and g.shape == p.shape
+
+
 def is_channel_last(t):
     """True for the (B, C, N) view of a contiguous (B, N, C) buffer."""
     return t.dim() == 3 and not t.is_contiguous() and t.permute(0, 2, 1).is_contiguous()
@@ -142,6 +148,7 @@ class BatchNormActFunction(Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu, counter=None):
         ctx.training, ctx.has_res = training, residual is not None
+        ctx.wparam, ctx.bparam = weight, bias  # the Parameter objects (their .grad buffers, see runtime.grads_in_place)
         ctx.rows = is_channel_last(x) and x.shape[1] % 4 == 0
         ctx.relu_mode = 0 if not relu else (2 if residual is not None else 1)
         if ctx.rows:  # channel-last view in, channel-last view out: no layout change anywhere
@@ -166,15 +173,19 @@ class BatchNormActFunction(Function):
         x, y, weight, bias, mean, invstd = ctx.saved_tensors
         need_res = ctx.has_res and ctx.needs_input_grad[1]
         if ctx.rows:
+            into = (None, None)
+            if runtime.grads_in_place and weight is not None and bias is not None and _is_grad_buffer(ctx.wparam) \
+                    and _is_grad_buffer(ctx.bparam):
+                into = (ctx.wparam.grad, ctx.bparam.grad)  # the kernel adds into the gradient buffers: no add kernels
             dx, dres, dgamma, dbeta = ops.bn_act_cl_bwd(_rows(grad_out), x, y, weight, bias, mean, invstd, ctx.training,
-                                                        ctx.relu_mode, need_res)
+                                                        ctx.relu_mode, need_res, *into)
             dx = dx.permute(0, 2, 1)
             dres = dres.permute(0, 2, 1) if dres is not None else None
         else:
             dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, bias, mean, invstd,
                                                      ctx.training, ctx.relu_mode, need_res)
         return (dx, dres, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
-                None, None, None, None)
+                None, None, None, None)  # dgamma / dbeta are None when they were added in place
 
 
 def batch_norm_act(bn, x, relu, residual=None):

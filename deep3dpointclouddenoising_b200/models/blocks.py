@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.autograd import Function
 
-from ..fused import batch_norm_act, cat_channels, is_channel_last, rows_of
+from ..fused import _is_grad_buffer, batch_norm_act, cat_channels, is_channel_last, rows_of
 from ..utils.config import runtime
 
 
@@ -27,15 +27,29 @@ def _conv_math():
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def _weight_grad(g2, x2):
+_ones = {}
+
+
+def _weight_grad(g2, x2, into=None):
     """dW = g^T x for (R, Cout), (R, Cin) with R >> Cout, Cin.  One cuBLAS GEMM with a 131072-long reduction and a
     72 x 72 result runs on a handful of CTAs (114 us measured on B200, tools/wgrad_probe.py); split into R / 1024
-    independent row chunks (bmm) plus a sum it takes 32 us."""
+    independent row chunks (bmm) plus a reduction it takes 32 us.
+    into: a (Cout, Cin) gradient buffer to ADD the result to (runtime.grads_in_place); returns None then."""
     R = g2.shape[0]
     S = min(R // 1024, 128)
     if R < 16384 or R % S:
-        return g2.t() @ x2
-    return torch.bmm(g2.view(S, R // S, -1).transpose(1, 2), x2.view(S, R // S, -1)).sum(0)
+        if into is None:
+            return g2.t() @ x2
+        into.addmm_(g2.t(), x2)
+        return None
+    partial = torch.bmm(g2.view(S, R // S, -1).transpose(1, 2), x2.view(S, R // S, -1))
+    if into is None:
+        return partial.sum(0)
+    key = (S, g2.device)
+    if key not in _ones:
+        _ones[key] = torch.ones((1, S), dtype=g2.dtype, device=g2.device)
+    into.view(1, -1).addmm_(_ones[key], partial.view(S, -1))  # the sum over the chunks, accumulated into the buffer
+    return None
 
 
 class PointwiseConvRows(Function):
@@ -47,6 +61,7 @@ class PointwiseConvRows(Function):
         w = weight.squeeze(-1)
         ctx.save_for_backward(rows, w)
         ctx.has_bias = bias is not None
+        ctx.wparam = weight  # the Parameter: its .grad buffer is written in place under runtime.grads_in_place
         with _conv_math():
             return F.linear(rows, w, bias)
 
@@ -59,7 +74,9 @@ class PointwiseConvRows(Function):
             if ctx.needs_input_grad[0]:
                 d_rows = (g2 @ w).view_as(rows)
             if ctx.needs_input_grad[1]:
-                d_w = _weight_grad(g2, rows.reshape(-1, rows.shape[-1])).unsqueeze(-1)
+                into = ctx.wparam.grad.view(w.shape) if runtime.grads_in_place and _is_grad_buffer(ctx.wparam) else None
+                d_w = _weight_grad(g2, rows.reshape(-1, rows.shape[-1]), into)
+                d_w = d_w.unsqueeze(-1) if d_w is not None else None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = g2.sum(0)
         return d_rows, d_w, d_b

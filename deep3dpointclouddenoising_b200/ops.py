@@ -368,7 +368,10 @@ def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var,
     return y, mean, invstd
 
 
-def bn_act_cl_bwd(dy_rows, x_rows, y_rows, gamma, beta, mean, invstd, training, relu_mode, need_res):
+def bn_act_cl_bwd(dy_rows, x_rows, y_rows, gamma, beta, mean, invstd, training, relu_mode, need_res,
+                  grad_gamma_into=None, grad_beta_into=None):
+    """grad_gamma_into / grad_beta_into: the parameters' gradient buffers; when given, the kernel ADDS into them and the
+    returned dgamma / dbeta are None."""
     L = _lib.load()
     dy_rows = _f32(dy_rows, "grad_out")
     C = dy_rows.shape[-1]
@@ -376,14 +379,15 @@ def bn_act_cl_bwd(dy_rows, x_rows, y_rows, gamma, beta, mean, invstd, training, 
     with torch.cuda.device(dy_rows.device):
         dx = torch.empty_like(dy_rows)
         dres = torch.empty_like(dy_rows) if need_res else None
-        dgamma = torch.empty((C,), dtype=torch.float32, device=dy_rows.device)
-        dbeta = torch.empty((C,), dtype=torch.float32, device=dy_rows.device)
+        in_place = grad_gamma_into is not None and grad_beta_into is not None
+        dgamma = grad_gamma_into if in_place else torch.empty((C,), dtype=torch.float32, device=dy_rows.device)
+        dbeta = grad_beta_into if in_place else torch.empty((C,), dtype=torch.float32, device=dy_rows.device)
         ws = _bn_ws(dy_rows.device, C)
         _lib.check(L.d3d_bn_act_cl_bwd(_p(dy_rows), _p(x_rows), _p(y_rows), _p(gamma), _p(beta), _p(mean), _p(invstd), R, C,
                                        int(bool(training)), int(relu_mode), _p(dx), _p(dres), _p(dgamma), _p(dbeta),
-                                       _p(ws), ws.numel(), _stream()), "d3d_bn_act_cl_bwd")
+                                       int(in_place), _p(ws), ws.numel(), _stream()), "d3d_bn_act_cl_bwd")
     _count()
-    return dx, dres, dgamma, dbeta
+    return (dx, dres, None, None) if in_place else (dx, dres, dgamma, dbeta)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -79,8 +79,11 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   channel_last: fused ops return channel-last views and the 1x1 convolutions run as row-major GEMMs, so the
 #     network never transposes between the convolutions and the aggregations (fused.py, models/blocks.py)
 #   prefetch_neighbors: the backbone enqueues all neighbourhood structures of a forward on a side stream (neighbors.py)
+#   grads_in_place: backward kernels ADD parameter gradients straight into existing .grad buffers and return None to
+#     autograd (no per-parameter accumulation kernels).  Only valid when nothing hooks the gradients (no DDP reducer):
+#     distributed.FlatParameters-style training loops switch it on, the default is off.
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
-                    "prefetch_neighbors": True})
+                    "prefetch_neighbors": True, "grads_in_place": False})
 
 
 def reset_config():

@@ -191,9 +191,11 @@ int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma,
                       float* running_var, long long* num_batches_tracked, long long R, int C, float eps, float momentum,
                       int training, int relu, float* y, float* save_mean, float* save_invstd, void* ws, size_t ws_bytes,
                       void* stream);
+/* accumulate_param_grads != 0: dgamma / dbeta are added to (they are the parameters' gradient buffers), else stored. */
 int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* beta,
                       const float* save_mean, const float* save_invstd, long long R, int C, int training, int relu,
-                      float* dx, float* dres, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, void* stream);
+                      float* dx, float* dres, float* dgamma, float* dbeta, int accumulate_param_grads, void* ws,
+                      size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 5. Exact nearest neighbours on large clouds and the Chamfer distance

@@ -126,3 +126,29 @@ def test_model_channel_last_matches_channel_major(cuda_device):
     finally:
         runtime.channel_last = True
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_in_place_parameter_gradients_match_autograd_accumulation(cuda_device):
+    """runtime.grads_in_place: BN and 1x1-conv backward add the parameter gradients straight into the (flat) gradient
+    buffers and return None to autograd — the buffers must equal what autograd's own accumulation produces."""
+    from deep3dpointclouddenoising_b200 import distributed, synthetic
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    import bench
+    model, criterion, cfg = bench.build_model("pospool", 2048)
+    model = model.to(cuda_device)
+    flat = distributed.FlatParameters(model)
+    batch = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(9, 4, 2048, ragged=True)]
+    grads = []
+    try:
+        for flag in (False, True, True):  # twice in place: the second pass checks that the buffers really accumulate
+            runtime.grads_in_place = flag
+            if len(grads) < 2:
+                flat.zero()
+            loss = criterion(model(batch[0], batch[1], batch[2]).transpose(1, 2), batch[3], batch[1])
+            loss.backward()
+            grads.append(flat.flat.clone())
+    finally:
+        runtime.grads_in_place = False
+    assert grads[0].abs().max() > 0
+    torch.testing.assert_close(grads[1], grads[0], rtol=1e-4, atol=1e-5 * grads[0].abs().max().item())
+    torch.testing.assert_close(grads[2], 2 * grads[0], rtol=1e-3, atol=1e-4 * grads[0].abs().max().item())

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--tf32", type=int, default=0)
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--flat", type=int, default=0, help="flat parameter/gradient buffers + in-place parameter gradients")
     ap.add_argument("--list", default=None, help="substring: print every launch of matching kernels in order")
     args = ap.parse_args()
     runtime.channel_last = bool(args.channel_last)
@@ -26,11 +27,19 @@ def main():
     dev = torch.device("cuda:0")
     model, criterion, cfg = bench.build_model(args.operator, 8192)
     model = model.to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    flat = None
+    if args.flat:
+        from deep3dpointclouddenoising_b200 import distributed
+        flat = distributed.FlatParameters(model)
+        runtime.grads_in_place = True
+    opt = torch.optim.Adam([flat.param] if flat else model.parameters(), lr=1e-3)
     batch = [torch.from_numpy(a).to(dev) for a in synthetic.make_batch(0, 16, 8192, ragged=True)]
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        if flat:
+            flat.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss = criterion(model(batch[0], batch[1], batch[2]).transpose(1, 2), batch[3], batch[1])
         loss.backward()
         opt.step()
