@@ -285,7 +285,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch.distributed as dist
     from deep3dpointclouddenoising_b200 import _lib, distributed, ops, synthetic
     from deep3dpointclouddenoising_b200.utils import config as cfgmod
 

@@ -1,7 +1,6 @@
 """Writes a markdown summary of one `ncu --set full` report (first captured launch) into profiles/.
 usage: python tools/summarize_ncu.py gpurun_out/x.ncu-rep profiles/x.md "<command that was profiled>" "<reading>" """
 import csv
-import json
 import subprocess
 import sys
 
