@@ -626,7 +626,9 @@ int launch_rows(Args a, int B, cudaStream_t st) {
   if (e != cudaSuccess) return (int)e;
   const int n_rows = kBackward ? a.N : a.M;
   const char* env_rows = getenv("D3D_PG_ROWS");
-  a.rows_per_cta = env_rows ? atoi(env_rows) : kRowsPerCta;
+  // inverse-map segments vary a lot in length: fewer rows per CTA balance the backward pass better (measured 0.86 ->
+  // 0.83 ms at level 0), the forward pass prefers to amortise the per-CTA weight staging over 8 rows
+  a.rows_per_cta = env_rows ? atoi(env_rows) : (kBackward ? kRowsPerCta / 2 : kRowsPerCta);
   dim3 grid(d3d_ceil_div(n_rows, a.rows_per_cta), B);
   kernel<<<grid, kThreads, smem, st>>>(a);
   d3d_note_launches(1);
