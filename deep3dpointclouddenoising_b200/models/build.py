@@ -3,7 +3,7 @@ import torch.nn as nn
 
 from .backbones import ResNet
 from .heads import MultiDimHeadResNet
-from .losses import MaskedL1Loss
+from .losses import MaskedAdaptiveL1ChamferLoss, MaskedChamferL1Loss, MaskedChamferLoss, MaskedL1Loss
 
 OFFSET_REG_DIM = 3
 
@@ -42,9 +42,18 @@ def build_offset_regression(config):
         criterion = MaskedL1Loss()
     elif config.loss is None:
         raise ValueError("Please specify a loss in the config file")
-    elif config.loss in ('chamfer_L1', 'chamfer', 'chamfer_sparse', 'l1_chamfer_sparse',
-                         'l1_chamfer_adaptive_to_chamfer', 'l1_chamfer_adaptive_to_l1'):
-        raise NotImplementedError(f"The loss {config.loss} needs pytorch3d's knn (outside the hot path, SURVEY.md row f3)")
+    elif config.loss == 'chamfer_L1':  # build.py:51-62: forward(pred, target, mask, points) for all of these
+        criterion = MaskedChamferL1Loss()
+    elif config.loss == 'chamfer':
+        criterion = MaskedChamferLoss()
+    elif config.loss == 'chamfer_sparse':
+        criterion = MaskedChamferLoss(norm_type='L1')
+    elif config.loss == 'l1_chamfer_sparse':
+        criterion = MaskedChamferL1Loss(norm_type='L1')
+    elif config.loss == 'l1_chamfer_adaptive_to_chamfer':
+        criterion = MaskedAdaptiveL1ChamferLoss(converging_to='chamfer')
+    elif config.loss == 'l1_chamfer_adaptive_to_l1':
+        criterion = MaskedAdaptiveL1ChamferLoss(converging_to='L1')
     else:
         raise ValueError(f"The loss {config.loss} is not implemented")
     return model, criterion
