@@ -517,24 +517,40 @@ __device__ __forceinline__ void cl_scale_offset(const float* __restrict__ gamma,
   offset = make_float4(bt.x - m.x * scale.x, bt.y - m.y * scale.y, bt.z - m.z * scale.z, bt.w - m.w * scale.w);
 }
 
+// The elementwise passes give every thread kApplyRows consecutive rows of ONE float4 channel group: the per-channel
+// parameters (4 to 6 float4 loads) are fetched once per thread instead of once per 16 payload bytes — those loads hit L1
+// but still cost LSU write-back passes — and kApplyRows independent payload loads are in flight per thread.
+constexpr int kApplyRows = 4;
+
 __global__ void __launch_bounds__(256)
 bn_apply_cl_kernel(const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
-                   int c4, long long total4, int relu, float* __restrict__ y) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= total4) return;
-  const int group = (int)(e % c4);
+                   int c4, long long R, int relu, float* __restrict__ y) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long rb = t / c4;
+  const int group = (int)(t - rb * c4);
+  const long long row0 = rb * kApplyRows;
+  if (row0 >= R) return;
   float4 m, is, scale, offset;
   cl_scale_offset(gamma, beta, mean, invstd, group, m, is, scale, offset);
-  float4 v = __ldg(reinterpret_cast<const float4*>(x) + e);
-  v.x = v.x * scale.x + offset.x; v.y = v.y * scale.y + offset.y;
-  v.z = v.z * scale.z + offset.z; v.w = v.w * scale.w + offset.w;
-  if (residual) {
-    const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + e);
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-  }
-  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-  reinterpret_cast<float4*>(y)[e] = v;
+  float4 v[kApplyRows], r[kApplyRows];
+#pragma unroll
+  for (int k = 0; k < kApplyRows; ++k)
+    if (row0 + k < R) {
+      const long long e = (row0 + k) * c4 + group;
+      v[k] = __ldg(reinterpret_cast<const float4*>(x) + e);
+      if (residual) r[k] = __ldg(reinterpret_cast<const float4*>(residual) + e);
+    }
+#pragma unroll
+  for (int k = 0; k < kApplyRows; ++k)
+    if (row0 + k < R) {
+      float4 o = v[k];
+      o.x = o.x * scale.x + offset.x; o.y = o.y * scale.y + offset.y;
+      o.z = o.z * scale.z + offset.z; o.w = o.w * scale.w + offset.w;
+      if (residual) { o.x += r[k].x; o.y += r[k].y; o.z += r[k].z; o.w += r[k].w; }
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      reinterpret_cast<float4*>(y)[(row0 + k) * c4 + group] = o;
+    }
 }
 
 // dy masked by the ReLU, same expressions as the forward pass so the mask is bit-identical
@@ -606,11 +622,13 @@ bn_bwd_reduce_cl_kernel(const float* __restrict__ dy, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                       const float* __restrict__ invstd, const float* __restrict__ sums, int c4, long long total4,
+                       const float* __restrict__ invstd, const float* __restrict__ sums, int c4, long long R,
                        float inv_count, int relu, int use_batch_stats, float* __restrict__ dx, float* __restrict__ dres) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= total4) return;
-  const int group = (int)(e % c4);
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long rb = t / c4;
+  const int group = (int)(t - rb * c4);
+  const long long row0 = rb * kApplyRows;
+  if (row0 >= R) return;
   float4 m, is, g, offset;
   cl_scale_offset(gamma, beta, mean, invstd, group, m, is, g, offset);
   float4 k1 = make_float4(0, 0, 0, 0), k2 = k1;
@@ -620,13 +638,25 @@ bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x
     k1 = make_float4(sa.x * inv_count, sa.z * inv_count, sb.x * inv_count, sb.z * inv_count);
     k2 = make_float4(sa.y * inv_count * is.x, sa.w * inv_count * is.y, sb.y * inv_count * is.z, sb.w * inv_count * is.w);
   }
-  const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + e);
-  const float4 d = cl_masked_dy(__ldg(reinterpret_cast<const float4*>(dy) + e), xv, y, e, relu, g, offset);
-  if (dres) reinterpret_cast<float4*>(dres)[e] = d;
-  float4 o;
-  o.x = g.x * (d.x - k1.x - (xv.x - m.x) * k2.x); o.y = g.y * (d.y - k1.y - (xv.y - m.y) * k2.y);
-  o.z = g.z * (d.z - k1.z - (xv.z - m.z) * k2.z); o.w = g.w * (d.w - k1.w - (xv.w - m.w) * k2.w);
-  reinterpret_cast<float4*>(dx)[e] = o;
+  float4 xv[kApplyRows], dv[kApplyRows];
+#pragma unroll
+  for (int k = 0; k < kApplyRows; ++k)
+    if (row0 + k < R) {
+      const long long e = (row0 + k) * c4 + group;
+      xv[k] = __ldg(reinterpret_cast<const float4*>(x) + e);
+      dv[k] = __ldg(reinterpret_cast<const float4*>(dy) + e);
+    }
+#pragma unroll
+  for (int k = 0; k < kApplyRows; ++k)
+    if (row0 + k < R) {
+      const long long e = (row0 + k) * c4 + group;
+      const float4 d = cl_masked_dy(dv[k], xv[k], y, e, relu, g, offset);
+      if (dres) reinterpret_cast<float4*>(dres)[e] = d;
+      float4 o;
+      o.x = g.x * (d.x - k1.x - (xv[k].x - m.x) * k2.x); o.y = g.y * (d.y - k1.y - (xv[k].y - m.y) * k2.y);
+      o.z = g.z * (d.z - k1.z - (xv[k].z - m.z) * k2.z); o.w = g.w * (d.w - k1.w - (xv[k].w - m.w) * k2.w);
+      reinterpret_cast<float4*>(dx)[e] = o;
+    }
 }
 
 constexpr int kClBlocks = 148 * 4;  // four 8-warp blocks per SM, 8 independent 16-byte loads in flight per thread;
@@ -774,9 +804,9 @@ int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma,
   } else {
     bn_eval_stats_kernel<<<d3d_ceil_div(C, 256), 256, 0, st>>>(running_mean, running_var, C, eps, save_mean, save_invstd);
   }
-  const long long total4 = R * g.c4;
-  bn_apply_cl_kernel<<<(unsigned)d3d_ceil_div(total4, 256), 256, 0, st>>>(x, residual, gamma, beta, save_mean, save_invstd, g.c4,
-                                                                         total4, relu, y);
+  const long long apply_threads = ((R + kApplyRows - 1) / kApplyRows) * g.c4;
+  bn_apply_cl_kernel<<<(unsigned)d3d_ceil_div(apply_threads, 256), 256, 0, st>>>(x, residual, gamma, beta, save_mean, save_invstd,
+                                                                                g.c4, R, relu, y);
   d3d_note_launches(2);
   return d3d_launch_status();
 }
@@ -798,10 +828,10 @@ int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const flo
   const int S = cl_splits(g, R);
   bn_bwd_reduce_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, R, C, S, relu,
                                                                 accumulate_param_grads, dgamma, dbeta, sums, partials, counters);
-  const long long total4 = R * g.c4;
-  bn_bwd_apply_cl_kernel<<<(unsigned)d3d_ceil_div(total4, 256), 256, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, sums,
-                                                                             g.c4, total4, 1.0f / (float)R, relu, training, dx,
-                                                                             dres);
+  const long long apply_threads = ((R + kApplyRows - 1) / kApplyRows) * g.c4;
+  bn_bwd_apply_cl_kernel<<<(unsigned)d3d_ceil_div(apply_threads, 256), 256, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd,
+                                                                                    sums, g.c4, R, 1.0f / (float)R, relu, training,
+                                                                                    dx, dres);
   d3d_note_launches(2);
   return d3d_launch_status();
 }
