@@ -452,8 +452,9 @@ def main():
                     "share_of_step": round(top["ms_per_step"] / step_ms, 4),
                     "our_kernels_share_of_step": round(ours_ms / step_ms, 4), "gather": gather,
                     "note": "algorithmic bytes = compulsory HBM traffic (features + idx + xyz in, result out, DESIGN.md §3); "
-                            "the aggregation kernels are bound by the L2->SM gather of B*M*ns*C*4 bytes (reported under "
-                            "'gather'), the ball query by instruction issue (brute-force pair scan)"}
+                            "the aggregation kernels are bound by the register write-back of the L2->SM gather of B*M*ns*C*4 "
+                            "bytes (reported under 'gather'; ncu: profiles/r01_pospool_fwd_ncu.md), the ball query by "
+                            "instruction issue (ordered prefix scan, profiles/r01_ball_query_v3_ncu.md)"}
 
     # ---- neighbour build alone (BASELINE.json metric, second figure): the full 5-level pyramid of one batch ----
     neighbor_build = None
