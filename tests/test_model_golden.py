@@ -1,0 +1,97 @@
+"""Whole-model parity against the REFERENCE'S OWN MODEL.
+
+tests/golden/model_{pospool,pseudo_grid}.npz were written by oracle/make_golden_model.py: the reference's
+u_net_arch/models (build.py:236-262, backbones/resnet.py:71-188, heads/multi_dimensional_head.py) imported from
+/root/reference, one fp32 training step on the CPU at B=2, N=1024, ragged masks.  Here:
+
+* CPU (not gpu): the oracle port of the step (oracle/cpu_model.py, the thing bench.py times as cpu_baseline)
+  reproduces the reference's prediction, loss and every parameter gradient;
+* GPU: the CUDA path (this package's model on the fused sm_100a kernels, TF32 off on both sides like the golden run)
+  does too — fp32 tolerances for PosPool and fp32 PseudoGrid, the stated bf16 tolerance for the tcgen05 PseudoGrid.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_golden_model as G
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _build(kind):
+    from deep3dpointclouddenoising_b200.models import build_offset_regression
+    c = G.make_config(kind)
+    torch.manual_seed(0)
+    model, criterion = build_offset_regression(c)
+    missing = model.load_state_dict(G.seeded_state(model), strict=False)
+    assert not missing.unexpected_keys
+    return model.train(), criterion
+
+
+def _compare(gold, pred, loss, named_grads, rtol_pred, rtol_grad, label):
+    ref_pred = gold["pred"]
+    scale = np.abs(ref_pred).max()
+    err = np.abs(pred - ref_pred).max()
+    assert err <= rtol_pred * scale, f"{label}: prediction differs by {err:.3e} (scale {scale:.3e})"
+    assert abs(loss - float(gold["loss"])) <= rtol_pred * abs(float(gold["loss"])) * 4, (label, loss, float(gold["loss"]))
+    checked = 0
+    for name, g in named_grads:
+        flat = g.reshape(-1)
+        want = gold["g:" + name]
+        got = flat[G.sample_indices(name, flat.size)]
+        norm_ref, sum_ref = gold["n:" + name]
+        norm = float(np.sqrt((flat.astype(np.float64) ** 2).sum()))
+        denom = max(np.abs(want).max(), norm_ref / np.sqrt(max(flat.size, 1)), 1e-12)
+        e = np.abs(got - want).max() / denom
+        assert e <= rtol_grad, f"{label}: d/d{name} sampled entries differ by {e:.3e} of their scale"
+        assert abs(norm - norm_ref) <= rtol_grad * max(norm_ref, 1e-12), f"{label}: |d/d{name}| {norm} vs {norm_ref}"
+        checked += 1
+    assert checked == sum(1 for k in gold.files if k.startswith("g:")), "parameter sets differ"
+
+
+@pytest.mark.parametrize("kind", ["pospool", "pseudo_grid"])
+def test_cpu_port_reproduces_reference_model_step(oracle, kind):
+    from oracle.cpu_model import CpuUNet
+    gold = np.load(os.path.join(GOLD, f"model_{kind}.npz"))
+    model, criterion = _build(kind)
+    pts, mask, feats, offs = [torch.from_numpy(a) for a in G.make_inputs()]
+    pred = CpuUNet(model, oracle)(pts, mask, feats)
+    loss = criterion(pred.transpose(1, 2), offs, mask)
+    loss.backward()
+    grads = [(n, p.grad.numpy()) for n, p in model.named_parameters()]
+    _compare(gold, pred.detach().numpy(), loss.item(), grads, 2e-5, 2e-4, f"cpu port / {kind}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,precision,rtol_pred,rtol_grad", [
+    ("pospool", "fp32", 1e-4, 1e-3),
+    ("pseudo_grid", "fp32", 1e-4, 1e-3),
+    ("pseudo_grid", "bf16", 2e-2, 5e-2),   # tcgen05 contraction, bf16 operands: stated separately
+])
+def test_cuda_model_matches_reference_model_step(cuda_device, kind, precision, rtol_pred, rtol_grad):
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    gold = np.load(os.path.join(GOLD, f"model_{kind}.npz"))
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, runtime.pseudo_grid_precision)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    runtime.pseudo_grid_precision = precision
+    try:
+        model, criterion = _build(kind)
+        model = model.to(cuda_device)
+        pts, mask, feats, offs = [torch.from_numpy(a).to(cuda_device) for a in G.make_inputs()]
+        pred = model(pts, mask, feats)
+        loss = criterion(pred.transpose(1, 2), offs, mask)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = [(n, p.grad.cpu().numpy()) for n, p in model.named_parameters()]
+        _compare(gold, pred.detach().cpu().numpy(), loss.item(), grads, rtol_pred, rtol_grad,
+                 f"cuda / {kind} / {precision}")
+        sd = model.state_dict()
+        for key in gold.files:  # BatchNorm running statistics after the step (momentum update of batch statistics)
+            if key.startswith("s:"):
+                got, want = sd[key[2:]].cpu().numpy(), gold[key]
+                assert np.abs(got - want).max() <= max(rtol_pred, 1e-4) * max(np.abs(want).max(), 1e-6) * 10, key
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, runtime.pseudo_grid_precision = old
