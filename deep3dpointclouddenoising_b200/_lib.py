@@ -34,6 +34,9 @@ SIGNATURES = {
     "d3d_cl_to_cm": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "d3d_pospool_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "d3d_pospool_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
+    "d3d_spatial_order": (_i, [_vp, _i, _i, _vp, _vp]),
+    "d3d_pospool_tiles_fwd": (_i, [_vp] * 7 + [_i] * 5 + [_f, _i, _vp, _vp]),
+    "d3d_pospool_tiles_bwd": (_i, [_vp] * 9 + [_i] * 5 + [_f, _i, _vp, _vp]),
     "d3d_pseudogrid_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _i, _vp, _vp]),
     "d3d_pseudogrid_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "d3d_pseudogrid_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_f, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -1,0 +1,454 @@
+// PosPool ('xyz' embedding, sum / avg) as a staged-tile kernel: bulk-asynchronous row staging + tcgen05 contraction.
+//
+//   ref: u_net_arch/models/local_aggregation_operators.py:140-147,165-183   (PosPool forward; autograd backward)
+//   ref: u_net_arch/pt_custom_ops/_ext_src/src/group_points_gpu.cu:13-33,48-69 (the gather / scatter-add it replaces)
+//
+// The per-query gather kernel (aggregate.cu) reads every (query, slot) row into registers: 1.96 GB through the LSU
+// write-back path at the first level, although 128 spatially adjacent queries only touch ~390 distinct rows.  Here a
+// CTA owns 128 rows that are adjacent in space (spatial_order.cu) and
+//   1. builds the UNION of the source rows their neighbourhoods reference (shared-memory bitmap + popcount ranks),
+//   2. stages the union 64 rows at a time with cp.async.bulk (global -> shared, no register write-back, completion
+//      counted on an mbarrier),
+//   3. turns the neighbourhood lists into a dense 128 x 64 multiplicity matrix A (0/1/2.. — exact in bf16),
+//   4. contracts  Y1 = A . X  and  Y2 = A . (w * X)  on the tensor cores (tcgen05.mma, accumulators in TMEM), where
+//      w[u, c] = (P[u] - centre)[c mod 3] is the source row's own coordinate relative to the tile centre.
+// PosPool's weight (P[u] - P[owner])[c mod 3] is bilinear in the two positions, so
+//      forward :  out[q, c]  =  rho_q  * (Y2[q, c] - (Q[q] - centre)[c mod 3] * Y1[q, c])       X = features
+//      backward:  dF[i, c]   = -1      * (Y2[i, c] - (S[i] - centre)[c mod 3] * Y1[i, c])       X = sigma_q * grad_out
+// with rho_q = sigma_q = 1 / (radius * neighbourhood size) (avg) or 1 / radius (sum).  The backward pass is the same
+// kernel with the roles swapped: a CTA owns 128 SUPPORT points and the union runs over the queries that gathered
+// them (inverse map) — a fixed-order reduction inside the tensor core, no float atomics.
+// fp32 accuracy: A is exact; X and w * X are split into three bf16 terms each (8 + 8 + 8 mantissa bits, an exact
+// decomposition), products are exact, accumulation is fp32 in TMEM.  Centring on the tile keeps the cancellation in
+// (Y2 - rc * Y1) at the scale of (tile extent + radius) / radius.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kTQ = 128;          // owner rows per CTA = MMA M = TMEM lanes
+constexpr int kThreads = 256;
+constexpr int kKC = 64;           // source rows per chunk (4 K-steps of 16)
+constexpr int kCB = 72;           // channels per CTA (multiple of 24: 8-channel groups and the c mod 3 phase line up)
+constexpr int kMaxPoints = 16384; // bitmap / owner table live in shared memory
+constexpr int kMaxNs = 64;
+constexpr unsigned kASbo = (kKC / 8) * 128;      // A: K-major, 8-row groups 1024 B apart, K chunks 128 B apart
+constexpr unsigned kABytes = (kTQ / 8) * kASbo;  // 16 KB
+
+struct TileArgs {
+  const float* src;          // rows that are staged: features (B, N, C) forward, grad_out (B, M, C) backward
+  float* out;                // (B, M, C) forward, (B, N, C) backward
+  const float* query_xyz;    // (B, M, 3)
+  const float* support_xyz;  // (B, N, 3)
+  const int* idx;            // (B, M, ns)
+  const int* nvalid;         // (B, M)
+  const int* query_mask;     // (B, M)
+  const int* rowptr;         // inverse map (backward)
+  const int* entries;
+  const int* order;          // (B, owners) processing order of the owner rows
+  int M, N, C, nsample, reduction;
+  float inv_radius;
+};
+
+struct Layout {
+  unsigned a, planes, plane_bytes, lbo_b, stage, row_bytes, ent, bitmap, prefix, owner_id, owner_neff, owner_rc, owner_rho,
+      src_id, src_w, src_scale, scan, bars, total;
+  int W, np, tmem_cols;
+};
+
+__host__ __device__ inline unsigned align16(unsigned x) { return (x + 15u) & ~15u; }
+
+__host__ __device__ inline Layout make_layout(int cbn, int ns, int n_src, int n_own, bool backward) {
+  Layout L;
+  unsigned o = 0;
+  L.a = o; o += kABytes;
+  L.lbo_b = (unsigned)((cbn + 7) / 8) * 128u;  // MN-major planes: 8-channel chunks 128 B apart, 8-row K groups lbo_b apart
+  L.plane_bytes = (kKC / 8) * L.lbo_b;
+  L.planes = o; o += 6 * L.plane_bytes + 128;  // +128: the MMA reads N rounded up to 16 channels
+  L.row_bytes = (unsigned)cbn * 4u;
+  L.stage = o; o += kKC * L.row_bytes;
+  L.ent = o; o += backward ? align16((unsigned)n_own) : align16((unsigned)(kTQ * ns * 2));
+  L.W = (n_src + 31) / 32;
+  L.bitmap = o; o += align16((unsigned)L.W * 4u);
+  L.prefix = o; o += align16((unsigned)(L.W + 1) * 4u);
+  L.owner_id = o; o += kTQ * 4;
+  L.owner_neff = o; o += kTQ * 4;
+  L.owner_rc = o; o += kTQ * 12;
+  L.owner_rho = o; o += kTQ * 4;
+  L.src_id = o; o += kKC * 4;
+  L.src_w = o; o += kKC * 12;
+  L.src_scale = o; o += kKC * 4;
+  L.scan = o; o += 16 * 4;
+  L.bars = o; o += 32;
+  L.total = o;
+  L.np = (cbn + 15) & ~15;
+  L.tmem_cols = 32;
+  while (L.tmem_cols < 2 * L.np) L.tmem_cols <<= 1;
+  return L;
+}
+
+__device__ __forceinline__ float rot3(float x, float y, float z, int r) { return r == 0 ? x : (r == 1 ? y : z); }
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kThreads, 2)
+pospool_tiles_kernel(const TileArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, b = blockIdx.z;
+  const int c0 = blockIdx.y * kCB, cbn = min(kCB, a.C - c0);
+  const int n_own = kBackward ? a.N : a.M, n_src = kBackward ? a.M : a.N;
+  const int ns = a.nsample;
+  const Layout L = make_layout(cbn, ns, n_src, n_own, kBackward);
+
+  unsigned char* sA = smem + L.a;
+  unsigned char* sPlanes = smem + L.planes;
+  unsigned char* sStage = smem + L.stage;
+  unsigned short* sEnt = reinterpret_cast<unsigned short*>(smem + L.ent);  // forward: union rank of every (row, slot)
+  unsigned char* sTable = smem + L.ent;                                    // backward: support -> row of this tile
+  unsigned* sBitmap = reinterpret_cast<unsigned*>(smem + L.bitmap);
+  unsigned* sPrefix = reinterpret_cast<unsigned*>(smem + L.prefix);
+  int* sOwnerId = reinterpret_cast<int*>(smem + L.owner_id);
+  int* sOwnerNeff = reinterpret_cast<int*>(smem + L.owner_neff);
+  float* sOwnerRc = reinterpret_cast<float*>(smem + L.owner_rc);
+  float* sOwnerRho = reinterpret_cast<float*>(smem + L.owner_rho);
+  int* sSrcId = reinterpret_cast<int*>(smem + L.src_id);
+  float* sSrcW = reinterpret_cast<float*>(smem + L.src_w);
+  float* sSrcScale = reinterpret_cast<float*>(smem + L.src_scale);
+  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);
+  const unsigned bar_stage = smem_u32(smem + L.bars), bar_mma = bar_stage + 8, tmem_slot = bar_stage + 16;
+
+  const float* own_xyz = (kBackward ? a.support_xyz : a.query_xyz) + (size_t)b * n_own * 3;
+  const float* src_xyz = (kBackward ? a.query_xyz : a.support_xyz) + (size_t)b * n_src * 3;
+  const int* order = a.order + (size_t)b * n_own;
+  const int row0 = tile * kTQ;
+  const int n_rows = min(kTQ, n_own - row0);
+  const size_t qbase = (size_t)b * a.M;
+
+  // ---- P0: owners, tile centre, barriers, TMEM ------------------------------------------------------------------
+  const int first = order[row0];
+  const float ctr_x = own_xyz[3 * (size_t)first], ctr_y = own_xyz[3 * (size_t)first + 1], ctr_z = own_xyz[3 * (size_t)first + 2];
+  if (warp == 0) tmem_alloc(tmem_slot, (unsigned)L.tmem_cols);
+  if (tid == 32) {
+    mbar_init(bar_stage, 1);
+    mbar_init(bar_mma, 1);
+    mbar_init_fence();
+  }
+  if (tid < kTQ) {
+    int own = -1, neff = 0;
+    float rx = 0.f, ry = 0.f, rz = 0.f, rho = 0.f;
+    if (tid < n_rows) {
+      own = order[row0 + tid];
+      rx = own_xyz[3 * (size_t)own] - ctr_x; ry = own_xyz[3 * (size_t)own + 1] - ctr_y; rz = own_xyz[3 * (size_t)own + 2] - ctr_z;
+      if (kBackward) {
+        rho = -1.0f;
+      } else {
+        // feature_mask = idx_mask + (1 - query_mask): a padded query uses all nsample slots (:171)
+        neff = a.query_mask[qbase + own] != 0 ? a.nvalid[qbase + own] : ns;
+        rho = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;  // :175-176
+      }
+    }
+    sOwnerId[tid] = own; sOwnerNeff[tid] = neff;
+    sOwnerRc[3 * tid] = rx; sOwnerRc[3 * tid + 1] = ry; sOwnerRc[3 * tid + 2] = rz;
+    sOwnerRho[tid] = rho;
+  }
+  for (int w = tid; w < L.W; w += kThreads) sBitmap[w] = 0u;
+  if (kBackward)
+    for (int i = tid; i < (int)(align16((unsigned)n_own) >> 4); i += kThreads)
+      reinterpret_cast<uint4*>(sTable)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *reinterpret_cast<volatile unsigned*>(smem + L.bars + 16);
+
+  // ---- P1: union of the referenced source rows --------------------------------------------------------------------
+  if (kBackward) {
+    if (tid < n_rows) sTable[sOwnerId[tid]] = (unsigned char)tid;
+    for (int r = warp; r < n_rows; r += kThreads / 32) {
+      const size_t srow = (size_t)b * a.N + sOwnerId[r];
+      const int beg = a.rowptr[srow], end = a.rowptr[srow + 1];
+      for (int e = beg + lane; e < end; e += 32) {
+        const int packed = a.entries[e];
+        const int q = packed >> 8, k = packed & 255;
+        const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
+        if (k < neff) atomicOr(&sBitmap[q >> 5], 1u << (q & 31));
+      }
+    }
+  } else {
+    for (int r = warp; r < n_rows; r += kThreads / 32) {
+      const int own = sOwnerId[r], neff = sOwnerNeff[r];
+      const int* irow = a.idx + (qbase + own) * ns;
+      for (int k = lane; k < ns; k += 32) {
+        unsigned v = 0xffffu;
+        if (k < neff) {
+          v = (unsigned)d3d_clamp_index(irow[k], a.N);
+          atomicOr(&sBitmap[v >> 5], 1u << (v & 31));
+        }
+        sEnt[r * ns + k] = (unsigned short)v;
+      }
+    }
+  }
+  __syncthreads();
+  {  // exclusive prefix of the per-word popcounts: two words per thread (W <= 512)
+    const int w0 = 2 * tid;
+    const unsigned p0 = w0 < L.W ? __popc(sBitmap[w0]) : 0u, p1 = w0 + 1 < L.W ? __popc(sBitmap[w0 + 1]) : 0u;
+    const unsigned sum = p0 + p1;
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) sScan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned v = lane < kThreads / 32 ? sScan[lane] : 0u;
+      unsigned vi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(D3D_FULL_MASK, vi, o);
+        if (lane >= o) vi += up;
+      }
+      if (lane < kThreads / 32) sScan[lane] = vi - v;
+      if (lane == 31) sScan[8] = vi;
+    }
+    __syncthreads();
+    const unsigned base = sScan[warp] + incl - sum;
+    if (w0 < L.W) sPrefix[w0] = base;
+    if (w0 + 1 < L.W) sPrefix[w0 + 1] = base + p0;
+  }
+  const int U = (int)sScan[8];
+  __syncthreads();
+  if (!kBackward) {  // source id -> rank inside the union
+    for (int e = tid; e < n_rows * ns; e += kThreads) {
+      const unsigned v = sEnt[e];
+      if (v != 0xffffu) sEnt[e] = (unsigned short)(sPrefix[v >> 5] + __popc(sBitmap[v >> 5] & ((1u << (v & 31)) - 1u)));
+    }
+  }
+
+  // ---- chunks of 64 union rows ---------------------------------------------------------------------------------
+  const int n_chunks = (U + kKC - 1) / kKC;
+  const unsigned idesc = idesc_bf16(L.np, false, true);  // A K-major, B MN-major, N = channels rounded up to 16
+  const int n_groups = (cbn + 7) >> 3;
+  const float* src_rows = a.src + (size_t)b * n_src * a.C + c0;
+  constexpr int kBuildThreads = kBackward ? kKC : kTQ;   // threads that fill A; the others convert the staged rows
+  for (int j = 0; j < n_chunks; ++j) {
+    const int rows_here = min(kKC, U - j * kKC);
+    const int ksteps = (rows_here + 15) >> 4;
+    // a. which rows; issue their bulk copies (the staging buffer was released by the barrier ending the previous chunk)
+    if (tid < kKC) {
+      const int r = j * kKC + tid;
+      int src = -1;
+      if (r < U) {
+        int lo = 0, hi = L.W - 1;
+        while (lo < hi) {  // last word whose prefix is <= r: it holds the set bit of rank r
+          const int mid = (lo + hi + 1) >> 1;
+          if ((int)sPrefix[mid] <= r) lo = mid; else hi = mid - 1;
+        }
+        src = lo * 32 + (int)__fns(sBitmap[lo], 0, r - (int)sPrefix[lo] + 1);
+        sSrcW[3 * tid] = src_xyz[3 * (size_t)src] - ctr_x;
+        sSrcW[3 * tid + 1] = src_xyz[3 * (size_t)src + 1] - ctr_y;
+        sSrcW[3 * tid + 2] = src_xyz[3 * (size_t)src + 2] - ctr_z;
+        float scale = 1.0f;
+        if (kBackward) {
+          const int neff = a.query_mask[qbase + src] != 0 ? a.nvalid[qbase + src] : ns;
+          scale = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;
+        }
+        sSrcScale[tid] = scale;
+        bulk_g2s(smem_u32(sStage + (size_t)tid * L.row_bytes), src_rows + (size_t)src * a.C, L.row_bytes, bar_stage);
+      }
+      sSrcId[tid] = src;
+    }
+    if (tid == 0) mbar_arrive_expect_tx(bar_stage, (unsigned)rows_here * L.row_bytes);
+    // b. the previous chunk's MMAs are done reading A and the planes
+    if (j > 0) {
+      mbar_wait(bar_mma, (unsigned)((j - 1) & 1));
+      tc_fence_after();
+    }
+    for (int i = tid; i < (int)(kABytes >> 4); i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tid < kBuildThreads) {
+      // c1. multiplicity matrix A[row][union rank - 64 j]; every element has ONE writer thread (its row forward, its
+      //     column backward), so the read-modify-write needs no atomics and the result does not depend on timing
+      if (kBackward) {
+        const int q = sSrcId[tid];
+        if (q >= 0) {
+          const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
+          const int* irow = a.idx + (qbase + q) * ns;
+          for (int k = 0; k < neff; ++k) {
+            const unsigned tl = sTable[d3d_clamp_index(irow[k], a.N)];
+            if (tl != 255u) {
+              unsigned short* p = reinterpret_cast<unsigned short*>(sA + (tl >> 3) * kASbo + (tid >> 3) * 128 + (tl & 7) * 16 + (tid & 7) * 2);
+              *p = (unsigned short)(__float_as_uint(__uint_as_float((unsigned)*p << 16) + 1.0f) >> 16);
+            }
+          }
+        }
+      } else if (tid < n_rows) {
+        const unsigned short* e = sEnt + tid * ns;
+        unsigned char* arow = sA + (tid >> 3) * kASbo + (tid & 7) * 16;
+        for (int k = 0; k < ns; ++k) {
+          const unsigned r = e[k];
+          if ((int)(r >> 6) == j) {  // 0xffff (masked slot) never matches: fewer than 1023 chunks
+            unsigned short* p = reinterpret_cast<unsigned short*>(arow + ((r & 63) >> 3) * 128 + (r & 7) * 2);
+            *p = (unsigned short)(__float_as_uint(__uint_as_float((unsigned)*p << 16) + 1.0f) >> 16);
+          }
+        }
+      }
+    } else {
+      // c2. staged fp32 rows -> 3 bf16 planes of X and 3 of w * X, MN-major operand layout; task = (row, 8 channels)
+      mbar_wait(bar_stage, (unsigned)(j & 1));
+      const int n_tasks = ksteps * 16 * n_groups;
+      for (int task = tid - kBuildThreads; task < n_tasks; task += kThreads - kBuildThreads) {
+        const int u = task % (ksteps * 16), g = task / (ksteps * 16);
+        unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
+        unsigned hx[3][4], hy[3][4];
+        if (sSrcId[u] < 0) {
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hx[p][i] = hy[p][i] = 0u;
+        } else {
+          const float* row = reinterpret_cast<const float*>(sStage + (size_t)u * L.row_bytes) + 8 * g;
+          const float4 xa = *reinterpret_cast<const float4*>(row);
+          const float4 xb = (8 * g + 4 < cbn) ? *reinterpret_cast<const float4*>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+          const float wx = sSrcW[3 * u], wy = sSrcW[3 * u + 1], wz = sSrcW[3 * u + 2];
+          const int base = (c0 + 8 * g) % 3;
+          const float w0 = rot3(wx, wy, wz, base), w1 = rot3(wy, wz, wx, base), w2 = rot3(wz, wx, wy, base);
+          if (kBackward) {
+            const float sc = sSrcScale[u];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] *= sc;
+          }
+          const float y[8] = {x[0] * w0, x[1] * w1, x[2] * w2, x[3] * w0, x[4] * w1, x[5] * w2, x[6] * w0, x[7] * w1};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            split3_bf16x2(x[2 * i], x[2 * i + 1], hx[0][i], hx[1][i], hx[2][i]);
+            split3_bf16x2(y[2 * i], y[2 * i + 1], hy[0][i], hy[1][i], hy[2][i]);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          *reinterpret_cast<uint4*>(dst + (size_t)p * L.plane_bytes) = make_uint4(hx[p][0], hx[p][1], hx[p][2], hx[p][3]);
+          *reinterpret_cast<uint4*>(dst + (size_t)(3 + p) * L.plane_bytes) = make_uint4(hy[p][0], hy[p][1], hy[p][2], hy[p][3]);
+        }
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // d. Y1 += A . X planes, Y2 += A . (w X) planes
+    if (tid == 0) {
+      tc_fence_after();
+      const unsigned a_addr = smem_u32(sA), p_addr = smem_u32(sPlanes);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const unsigned long long a_desc = smem_desc(a_addr + ks * 256, 128, kASbo);
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          const unsigned long long b_desc = smem_desc(p_addr + p * L.plane_bytes + ks * 2 * L.lbo_b, L.lbo_b, 128);
+          const unsigned acc = (j == 0 && ks == 0 && (p == 0 || p == 3)) ? 0u : 1u;
+          mma_bf16(tmem_base + (p < 3 ? 0u : (unsigned)L.np), a_desc, b_desc, idesc, acc);
+        }
+      }
+      mma_commit(bar_mma);
+    }
+  }
+
+  // ---- epilogue: thread = owner row (TMEM lane); the two warp groups split the 16-column pieces --------------------
+  if (n_chunks > 0) {
+    mbar_wait(bar_mma, (unsigned)((n_chunks - 1) & 1));
+    tc_fence_after();
+  }
+  {
+    const int lq = warp & 3, t = lq * 32 + lane;
+    const int own = sOwnerId[t];
+    const float rcx = sOwnerRc[3 * t], rcy = sOwnerRc[3 * t + 1], rcz = sOwnerRc[3 * t + 2], rho = sOwnerRho[t];
+    float* orow = a.out + ((size_t)b * n_own + (own >= 0 ? own : 0)) * a.C + c0;
+    for (int ch = warp >> 2; ch * 16 < cbn; ch += 2) {
+      unsigned y1[16], y2[16];
+      if (n_chunks > 0) {
+        const unsigned taddr = tmem_base + ((unsigned)(lq * 32) << 16) + (unsigned)(ch * 16);
+        tmem_ld16(taddr, y1);
+        tmem_ld16(taddr + (unsigned)L.np, y2);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y1[i] = y2[i] = 0u;
+      }
+      const int base = (c0 + 16 * ch) % 3;
+      const float r0 = rot3(rcx, rcy, rcz, base), r1 = rot3(rcy, rcz, rcx, base), r2 = rot3(rcz, rcx, rcy, base);
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float rc = (i % 3 == 0) ? r0 : ((i % 3 == 1) ? r1 : r2);
+        o[i] = rho * (__uint_as_float(y2[i]) - rc * __uint_as_float(y1[i]));
+      }
+      if (own >= 0) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (16 * ch + 4 * v < cbn)
+            *reinterpret_cast<float4*>(orow + 16 * ch + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (unsigned)L.tmem_cols);
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+template <bool kBackward>
+int launch_tiles(const TileArgs& a, int B, cudaStream_t st) {
+  const int n_own = kBackward ? a.N : a.M, n_src = kBackward ? a.M : a.N;
+  if (n_own > kMaxPoints || n_src > kMaxPoints || a.nsample > kMaxNs || a.C % 4 != 0) return D3D_ERR_UNSUPPORTED;
+  const int cbn_max = a.C < kCB ? a.C : kCB;
+  const Layout L = make_layout(cbn_max, a.nsample, n_src, n_own, kBackward);
+  auto kernel = pospool_tiles_kernel<kBackward>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(d3d_ceil_div(n_own, kTQ), d3d_ceil_div(a.C, kCB), B);
+  kernel<<<grid, kThreads, L.total, st>>>(a);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
+}  // namespace
+
+extern "C" {
+
+int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+                          const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
+                          int nsample, float radius, int reduction, float* out_cl, void* stream) {
+  D3D_REQUIRE(feat_cl && query_xyz && support_xyz && idx && nvalid && query_mask && query_order && out_cl);
+  D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
+  D3D_REQUIRE(reduction == D3D_REDUCE_SUM || reduction == D3D_REDUCE_AVG);
+  if (!aligned16(feat_cl) || !aligned16(out_cl)) return D3D_ERR_UNSUPPORTED;
+  if (B == 0 || M == 0) return 0;
+  TileArgs a{};
+  a.src = feat_cl; a.out = out_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx; a.nvalid = nvalid;
+  a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
+  a.reduction = reduction; a.inv_radius = 1.0f / radius;
+  return launch_tiles<false>(a, B, (cudaStream_t)stream);
+}
+
+int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+                          const int* rowptr, const int* entries, const int* nvalid, const int* query_mask,
+                          const int* support_order, int B, int M, int N, int C, int nsample, float radius, int reduction,
+                          float* grad_feat_cl, void* stream) {
+  D3D_REQUIRE(grad_out_cl && query_xyz && support_xyz && idx && rowptr && entries && nvalid && query_mask);
+  D3D_REQUIRE(support_order && grad_feat_cl);
+  D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
+  D3D_REQUIRE(reduction == D3D_REDUCE_SUM || reduction == D3D_REDUCE_AVG);
+  if (!aligned16(grad_out_cl) || !aligned16(grad_feat_cl)) return D3D_ERR_UNSUPPORTED;
+  if (B == 0) return 0;
+  if (M == 0) return (int)cudaMemsetAsync(grad_feat_cl, 0, (size_t)B * N * C * sizeof(float), (cudaStream_t)stream);
+  TileArgs a{};
+  a.src = grad_out_cl; a.out = grad_feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx;
+  a.rowptr = rowptr; a.entries = entries; a.nvalid = nvalid; a.query_mask = query_mask; a.order = support_order;
+  a.M = M; a.N = N; a.C = C; a.nsample = nsample; a.reduction = reduction; a.inv_radius = 1.0f / radius;
+  return launch_tiles<true>(a, B, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -156,6 +156,28 @@ def grid_subsample(xyz, mask, npoint, sample_dl):
     return out.sub_xyz, out.sub_mask
 
 
+class _Order(_Produced):
+    __slots__ = ("order", "_keepalive", "_stream", "_event")
+
+    def __init__(self, order, keepalive):
+        self.order, self._keepalive = order, keepalive
+        self._mark()
+
+
+def spatial_order(xyz):
+    """Cached Morton processing order (B, N) int32 of a point set for the staged-tile kernels; None when the set is
+    larger than they support (ops.TILE_MAX_POINTS) or `runtime.staged_tiles` is off."""
+    from .utils.config import runtime
+    if not runtime.staged_tiles or xyz.shape[1] > ops.TILE_MAX_POINTS:
+        return None
+
+    def build():
+        with torch.no_grad():
+            return _Order(ops.spatial_order(xyz), (xyz,))
+
+    return cache.get("order", (xyz,), (), build).sync().order
+
+
 def prebuild(xyz, mask, radius, nsample0, stages, with_csr):
     """Enqueues every neighbourhood structure of one U-Net forward on the side stream and fills the cache.
     stages: per strided stage (sample_dl, npoint, radius_in, nsample_in, radius_out, nsample_out) — the very values the
@@ -174,6 +196,8 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr):
                 lists.append(ball_neighbors(sx, px, sm, pm, r_in, ns_in))
                 lists.append(ball_neighbors(sx, sx, sm, sm, r_out, ns_out))
                 levels.append((sx, sm))
+            for lx, _ in levels:
+                spatial_order(lx)
             ups = [nearest_neighbors(levels[k - 1][0], levels[k][0], levels[k - 1][1], levels[k][1])
                    for k in range(len(levels) - 1, 0, -1)]
             if with_csr:  # in the order backward asks for them: decoder first, then coarse to fine

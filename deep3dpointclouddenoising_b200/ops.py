@@ -176,31 +176,65 @@ def cl_to_cm(x):
 # ------------------------------------------------------------------------------------------------
 # fused aggregation (channel-last tensors)
 # ------------------------------------------------------------------------------------------------
-def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius, reduction):
+TILE_MAX_POINTS, TILE_MAX_NSAMPLE = 16384, 64  # limits of the staged-tile kernels (csrc/pospool_tiles.cu)
+
+
+def spatial_order(xyz):
+    """(B, N, 3) -> (B, N) int32 Morton processing order of every cloud, or None beyond the staged kernels' size limit."""
+    L = _lib.load()
+    p = _f32(xyz, "points")
+    B, N = p.shape[0], p.shape[1]
+    if N > TILE_MAX_POINTS:
+        return None
+    with torch.cuda.device(p.device):
+        order = torch.empty((B, N), dtype=torch.int32, device=p.device)
+        _lib.check(L.d3d_spatial_order(_p(p), B, N, _p(order), _stream()), "d3d_spatial_order")
+    _count()
+    return order
+
+
+def _tiles_ok(M, N, ns, C):
+    return 0 < M <= TILE_MAX_POINTS and N <= TILE_MAX_POINTS and ns <= TILE_MAX_NSAMPLE and C % 4 == 0
+
+
+def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius, reduction, query_order=None):
+    """query_order (B, M) from `spatial_order`: the staged-tile tensor-core kernel; None: the per-query gather kernel."""
     L = _lib.load()
     f = _f32(feat_cl, "features")
     B, N, C = f.shape
     M, ns = idx.shape[1], idx.shape[2]
     with torch.cuda.device(f.device):
         out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
-        _lib.check(L.d3d_pospool_fwd(_p(f), _p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")),
-                                     _p(_i32(idx, "idx")), _p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")),
-                                     B, M, N, C, ns, float(radius), REDUCTIONS[reduction], _p(out), _stream()),
-                   "d3d_pospool_fwd")
+        args = (_p(f), _p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")), _p(_i32(idx, "idx")),
+                _p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")))
+        if query_order is not None and _tiles_ok(M, N, ns, C):
+            _lib.check(L.d3d_pospool_tiles_fwd(*args, _p(_i32(query_order, "query_order")), B, M, N, C, ns, float(radius),
+                                               REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_tiles_fwd")
+        else:
+            _lib.check(L.d3d_pospool_fwd(*args, B, M, N, C, ns, float(radius), REDUCTIONS[reduction], _p(out), _stream()),
+                       "d3d_pospool_fwd")
     _count()
     return out
 
 
 def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, query_mask, n_support, nsample, radius,
-                reduction):
+                reduction, idx=None, support_order=None):
+    """idx + support_order (B, N): the staged-tile kernel; otherwise the per-support segmented reduction."""
     L = _lib.load()
     g = _f32(grad_out_cl, "grad_out")
     B, M, C = g.shape
     with torch.cuda.device(g.device):
         out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
-        _lib.check(L.d3d_pospool_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
-                                     _p(query_mask), B, M, int(n_support), C, int(nsample), float(radius),
-                                     REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_bwd")
+        if support_order is not None and idx is not None and _tiles_ok(M, int(n_support), int(nsample), C):
+            _lib.check(L.d3d_pospool_tiles_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(_i32(idx, "idx")), _p(rowptr),
+                                               _p(entries), _p(nvalid), _p(query_mask),
+                                               _p(_i32(support_order, "support_order")), B, M, int(n_support), C,
+                                               int(nsample), float(radius), REDUCTIONS[reduction], _p(out), _stream()),
+                       "d3d_pospool_tiles_bwd")
+        else:
+            _lib.check(L.d3d_pospool_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
+                                         _p(query_mask), B, M, int(n_support), C, int(nsample), float(radius),
+                                         REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_bwd")
     _count()
     return out
 

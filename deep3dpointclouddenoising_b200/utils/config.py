@@ -82,8 +82,10 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   grads_in_place: backward kernels ADD parameter gradients straight into existing .grad buffers and return None to
 #     autograd (no per-parameter accumulation kernels).  Only valid when nothing hooks the gradients (no DDP reducer):
 #     distributed.FlatParameters-style training loops switch it on, the default is off.
+#   staged_tiles: PosPool runs as the staged-tile tensor-core kernel (csrc/pospool_tiles.cu: 128 spatially adjacent rows
+#     per CTA, cp.async.bulk staging of the neighbour-row union, tcgen05 contraction) instead of the per-query gather.
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
-                    "prefetch_neighbors": True, "grads_in_place": False})
+                    "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True})
 
 
 def reset_config():

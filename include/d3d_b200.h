@@ -128,6 +128,27 @@ int d3d_pospool_bwd(const float* grad_out_cl, const float* query_xyz, const floa
                     int B, int M, int N, int C, int nsample, float radius, int reduction,
                     float* grad_feat_cl, void* stream);
 
+/* Processing order for the staged-tile kernels below: order (B, N) int32 = every cloud's point indices sorted along a
+ * Morton curve over the cloud's bounding box (64^3 cells, ties by index).  It only decides which rows share a CTA
+ * (spatially adjacent rows reference almost the same neighbour rows); results never depend on it beyond fp32
+ * summation order.  N <= 16384 (D3D_ERR_UNSUPPORTED beyond).  No reference counterpart. */
+int d3d_spatial_order(const float* xyz, int B, int N, int* order, void* stream);
+
+/* PosPool as a staged-tile kernel (same math and arguments as d3d_pospool_fwd / _bwd, which remain the path for sizes
+ * beyond the limits below): a CTA owns 128 spatially adjacent rows (query_order / support_order from
+ * d3d_spatial_order), stages the union of the rows their neighbourhoods reference with cp.async.bulk and contracts
+ * [128 x union] multiplicities with the staged rows on the tensor cores (tcgen05, exact 3-term bf16 split, fp32
+ * accumulation); the backward pass owns 128 SUPPORT rows and is a fixed-order reduction (no float atomics).
+ *   replaces ref: pt_custom_ops/_ext_src/src/group_points_gpu.cu:13-33,48-69 + models/local_aggregation_operators.py:140-183
+ * Limits: M, N <= 16384, nsample <= 64, C % 4 == 0 (D3D_ERR_UNSUPPORTED otherwise). */
+int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+                          const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
+                          int nsample, float radius, int reduction, float* out_cl, void* stream);
+int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+                          const int* rowptr, const int* entries, const int* nvalid, const int* query_mask,
+                          const int* support_order, int B, int M, int N, int C, int nsample, float radius, int reduction,
+                          float* grad_feat_cl, void* stream);
+
 #define D3D_KP_CONSTANT 0
 #define D3D_KP_LINEAR   1
 #define D3D_KP_GAUSSIAN 2
