@@ -20,7 +20,7 @@ SIGNATURES = {
     "d3d_error_string": (ctypes.c_char_p, [_i]),
     "d3d_kernel_launches": (ctypes.c_longlong, []),
     "d3d_ball_query_workspace_bytes": (_sz, [_i, _i, _i]),
-    "d3d_ball_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "d3d_ball_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_nearest_query_workspace_bytes": (_sz, [_i]),
     "d3d_nearest_query": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "d3d_grid_subsample_workspace_bytes": (_sz, [_i, _i]),
@@ -36,7 +36,8 @@ SIGNATURES = {
     "d3d_pospool_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "d3d_spatial_order": (_i, [_vp, _i, _i, _vp, _vp]),
     "d3d_pospool_tiles_fwd": (_i, [_vp] * 7 + [_i] * 5 + [_f, _i, _vp, _vp]),
-    "d3d_pospool_tiles_bwd": (_i, [_vp] * 9 + [_i] * 5 + [_f, _i, _vp, _vp]),
+    "d3d_pospool_tiles_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "d3d_pospool_tiles_bwd": (_i, [_vp] * 8 + [_i] * 5 + [_f, _i, _vp, _vp, _sz, _vp]),
     "d3d_pseudogrid_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _i, _vp, _vp]),
     "d3d_pseudogrid_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "d3d_pseudogrid_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_f, _i, _i, _vp, _vp, _vp, _sz, _vp]),

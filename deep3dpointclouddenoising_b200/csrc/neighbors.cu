@@ -235,7 +235,7 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
                   const int* __restrict__ query_mask, const int* __restrict__ vlen,
                   const float* __restrict__ best_d2, const int* __restrict__ best_k, int M, int N, int tile,
                   float radius, int nsample, int* __restrict__ idx, int* __restrict__ idx_mask,
-                  int* __restrict__ nvalid) {
+                  int* __restrict__ nvalid, int* __restrict__ idx_by_support) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cap = 3 * nsample;
   float* sx = reinterpret_cast<float*>(smem_raw);
@@ -403,6 +403,10 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
       }
     }
     // rank counting among the n_rank selected keys (unique): rank = number of smaller keys
+    // idx_by_support (optional): the same nsample-or-fewer winners in ASCENDING SUPPORT INDEX (the list is in that order
+    // already), each as (distance rank << 16) | index, -1 padded — what the staged-tile aggregation kernels walk
+    int* srow = idx_by_support != nullptr ? idx_by_support + ((size_t)b * M + j) * nsample : nullptr;
+    int emitted = 0;
     for (int t0 = 0; t0 < n_rank; t0 += 64) {
       const int ta = t0 + lane, tb = t0 + 32 + lane;
       const unsigned long long own_a = ta < n_rank ? list[ta] : ~0ull;
@@ -414,9 +418,18 @@ ball_query_kernel(const float* __restrict__ query_xyz, const float* __restrict__
         ra += (kj < own_a) ? 1 : 0;
         rb += (kj < own_b) ? 1 : 0;
       }
-      if (ta < n_rank && ra < nsample) sorted[ra] = (int)(unsigned)(own_a & 0xffffffffull);
-      if (tb < n_rank && rb < nsample) sorted[rb] = (int)(unsigned)(own_b & 0xffffffffull);
+      const bool ka = ta < n_rank && ra < nsample, kb = tb < n_rank && rb < nsample;
+      if (ka) sorted[ra] = (int)(unsigned)(own_a & 0xffffffffull);
+      if (kb) sorted[rb] = (int)(unsigned)(own_b & 0xffffffffull);
+      if (srow != nullptr) {
+        const unsigned ba = __ballot_sync(D3D_FULL_MASK, ka), bb = __ballot_sync(D3D_FULL_MASK, kb);
+        if (ka) srow[emitted + __popc(ba & lt_mask)] = (ra << 16) | (int)(unsigned)(own_a & 0xffffu);
+        if (kb) srow[emitted + __popc(ba) + __popc(bb & lt_mask)] = (rb << 16) | (int)(unsigned)(own_b & 0xffffu);
+        emitted += __popc(ba) + __popc(bb);
+      }
     }
+    if (srow != nullptr)
+      for (int i = emitted + lane; i < nsample; i += 32) srow[i] = -1;
     __syncwarp();
     const int qm = query_mask[(size_t)b * M + j];
     int* orow = idx + ((size_t)b * M + j) * nsample;
@@ -477,9 +490,20 @@ int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// experiment knobs, read ONCE per process (not per launch)
+struct BqKnobs {
+  int tile, warps, scanmin_n;
+  BqKnobs() : tile(env_int("D3D_BQ_TILE", kBqDefaultTile)), warps(env_int("D3D_BQ_WARPS", kBqDefaultWarps)),
+              scanmin_n(env_int("D3D_BQ_SCANMIN_N", kScanMinN)) {}
+};
+const BqKnobs& bq_knobs() {
+  static const BqKnobs k;
+  return k;
+}
+
 int bq_tile(int N) {
   const int t = (N + 31) & ~31;
-  const int mx = (env_int("D3D_BQ_TILE", kBqDefaultTile) + 31) & ~31;
+  const int mx = (bq_knobs().tile + 31) & ~31;
   return t < mx ? t : mx;
 }
 
@@ -491,14 +515,14 @@ size_t bq_smem_bytes(int warps, int qw, int nsample, int tile) {
 template <int QW, int WARPS, bool SCAN>
 int launch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, const float* best_d2,
                       const int* best_k, int B, int M, int N, float radius, int nsample, int* idx, int* idx_mask,
-                      int* nvalid, cudaStream_t st) {
+                      int* nvalid, int* by_support, cudaStream_t st) {
   const int tile = bq_tile(N);
   const size_t smem = bq_smem_bytes(WARPS, QW, nsample, tile);
   cudaError_t e = cudaFuncSetAttribute(ball_query_kernel<QW, WARPS, SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(d3d_ceil_div(M, WARPS * QW), B);
   ball_query_kernel<QW, WARPS, SCAN><<<grid, WARPS * 32, smem, st>>>(q, s, qm, vlen, best_d2, best_k, M, N, tile, radius, nsample,
-                                                             idx, idx_mask, nvalid);
+                                                             idx, idx_mask, nvalid, by_support);
   d3d_note_launches(1);
   return d3d_launch_status();
 }
@@ -506,15 +530,15 @@ int launch_ball_query(const float* q, const float* s, const int* qm, const int* 
 template <int WARPS, bool SCAN>
 int dispatch_ball_query(const float* q, const float* s, const int* qm, const int* vlen, const float* best_d2,
                         const int* best_k, int B, int M, int N, float radius, int nsample, int* idx, int* idx_mask,
-                        int* nvalid, cudaStream_t st) {
+                        int* nvalid, int* by_support, cudaStream_t st) {
   const size_t budget = 220 * 1024;  // opt-in shared memory per block on sm_100a is 227 KB
   const int tile = bq_tile(N);
   if (bq_smem_bytes(WARPS, 4, nsample, tile) <= budget / 2)
-    return launch_ball_query<4, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<4, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
   if (bq_smem_bytes(WARPS, 2, nsample, tile) <= budget / 2)
-    return launch_ball_query<2, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<2, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
   if (bq_smem_bytes(WARPS, 1, nsample, tile) <= budget)
-    return launch_ball_query<1, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    return launch_ball_query<1, WARPS, SCAN>(q, s, qm, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
   return D3D_ERR_UNSUPPORTED;
 }
 
@@ -539,7 +563,9 @@ size_t d3d_ball_query_workspace_bytes(int B, int M, int N) {
 
 int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
                    const int* support_mask, int B, int M, int N, float radius, int nsample, int* idx,
-                   int* idx_mask, int* nvalid, void* ws, size_t ws_bytes, void* stream) {
+                   int* idx_mask, int* nvalid, int* idx_by_support, void* ws, size_t ws_bytes, void* stream) {
+  int* by_support = (N <= 65536 && nsample <= 255) ? idx_by_support : nullptr;  // 16-bit index, 8-bit rank
+  if (idx_by_support != nullptr && by_support == nullptr) return D3D_ERR_UNSUPPORTED;
   D3D_REQUIRE(query_xyz && support_xyz && query_mask && support_mask && idx && idx_mask);
   D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE);
   if (B == 0 || M == 0) return 0;
@@ -553,12 +579,12 @@ int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* 
   float* best_d2 = (float*)p; p += bq_align((size_t)B * M * sizeof(float));
   int* best_k = (int*)p;
   d3d_launch_prefix_len(support_mask, B, N, vlen, st);
-  const int warps = env_int("D3D_BQ_WARPS", kBqDefaultWarps);
-  if (N <= env_int("D3D_BQ_SCANMIN_N", kScanMinN)) {  // small support set: one launch, the kernel finds the nearest itself
+  const int warps = bq_knobs().warps;
+  if (N <= bq_knobs().scanmin_n) {  // small support set: one launch, the kernel finds the nearest itself
     switch (warps) {
-      case 4: return dispatch_ball_query<4, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-      case 16: return dispatch_ball_query<16, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-      default: return dispatch_ball_query<8, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+      case 4: return dispatch_ball_query<4, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
+      case 16: return dispatch_ball_query<16, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
+      default: return dispatch_ball_query<8, true>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
     }
   }
   ball_grid_build_kernel<<<B, 1024, 0, st>>>(support_xyz, vlen, N, grids, cell_start, sorted);
@@ -566,9 +592,9 @@ int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* 
                                                                    best_k);
   d3d_note_launches(2);
   switch (warps) {
-    case 4: return dispatch_ball_query<4, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-    case 16: return dispatch_ball_query<16, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
-    default: return dispatch_ball_query<8, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, st);
+    case 4: return dispatch_ball_query<4, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
+    case 16: return dispatch_ball_query<16, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
+    default: return dispatch_ball_query<8, false>(query_xyz, support_xyz, query_mask, vlen, best_d2, best_k, B, M, N, radius, nsample, idx, idx_mask, nvalid, by_support, st);
   }
 }
 

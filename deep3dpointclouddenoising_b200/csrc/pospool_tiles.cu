@@ -9,7 +9,9 @@
 //   1. builds the UNION of the source rows their neighbourhoods reference (shared-memory bitmap + popcount ranks),
 //   2. stages the union 64 rows at a time with cp.async.bulk (global -> shared, no register write-back, completion
 //      counted on an mbarrier),
-//   3. turns the neighbourhood lists into a dense 128 x 64 multiplicity matrix A (0/1/2.. — exact in bf16),
+//   3. turns the neighbourhood lists into a dense 128 x 64 multiplicity matrix A (0/1/2.. — exact in bf16); every
+//      row walks its list with a cursor: the ball query also emits each query's winners in ascending support index
+//      (idx_by_support), union ranks are monotone in the index, so a chunk consumes a contiguous run of the list,
 //   4. contracts  Y1 = A . X  and  Y2 = A . (w * X)  on the tensor cores (tcgen05.mma, accumulators in TMEM), where
 //      w[u, c] = (P[u] - centre)[c mod 3] is the source row's own coordinate relative to the tile centre.
 // PosPool's weight (P[u] - P[owner])[c mod 3] is bilinear in the two positions, so
@@ -29,10 +31,10 @@ namespace {
 using namespace umma;
 
 constexpr int kTQ = 128;          // owner rows per CTA = MMA M = TMEM lanes
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;     // warps 0-3 fill A (thread = owner row), warps 4-7 start converting, 6-7 also select rows
 constexpr int kKC = 64;           // source rows per chunk (4 K-steps of 16)
 constexpr int kCB = 72;           // channels per CTA (multiple of 24: 8-channel groups and the c mod 3 phase line up)
-constexpr int kMaxPoints = 16384; // bitmap / owner table live in shared memory
+constexpr int kMaxPoints = 16384; // the source bitmap lives in shared memory
 constexpr int kMaxNs = 64;
 constexpr unsigned kASbo = (kKC / 8) * 128;      // A: K-major, 8-row groups 1024 B apart, K chunks 128 B apart
 constexpr unsigned kABytes = (kTQ / 8) * kASbo;  // 16 KB
@@ -42,25 +44,26 @@ struct TileArgs {
   float* out;                // (B, M, C) forward, (B, N, C) backward
   const float* query_xyz;    // (B, M, 3)
   const float* support_xyz;  // (B, N, 3)
-  const int* idx;            // (B, M, ns)
+  const int* by_support;     // (B, M, ns) forward: winners in ascending support index, (distance rank << 16) | index
   const int* nvalid;         // (B, M)
   const int* query_mask;     // (B, M)
   const int* rowptr;         // inverse map (backward)
   const int* entries;
+  int* rank_scratch;         // backward: one int per inverse-map entry (union rank of its query, -1 = masked slot)
   const int* order;          // (B, owners) processing order of the owner rows
   int M, N, C, nsample, reduction;
   float inv_radius;
 };
 
 struct Layout {
-  unsigned a, planes, plane_bytes, lbo_b, stage, row_bytes, ent, bitmap, prefix, owner_id, owner_neff, owner_rc, owner_rho,
+  unsigned a, planes, plane_bytes, lbo_b, stage, row_bytes, ent, bitmap, prefix, owner_id, owner_info, owner_xyz, owner_rho,
       src_id, src_w, src_scale, scan, bars, total;
   int W, np, tmem_cols;
 };
 
 __host__ __device__ inline unsigned align16(unsigned x) { return (x + 15u) & ~15u; }
 
-__host__ __device__ inline Layout make_layout(int cbn, int ns, int n_src, int n_own, bool backward) {
+__host__ __device__ inline Layout make_layout(int cbn, int ns, int n_src, bool backward) {
   Layout L;
   unsigned o = 0;
   L.a = o; o += kABytes;
@@ -69,18 +72,18 @@ __host__ __device__ inline Layout make_layout(int cbn, int ns, int n_src, int n_
   L.planes = o; o += 6 * L.plane_bytes + 128;  // +128: the MMA reads N rounded up to 16 channels
   L.row_bytes = (unsigned)cbn * 4u;
   L.stage = o; o += kKC * L.row_bytes;
-  L.ent = o; o += backward ? align16((unsigned)n_own) : align16((unsigned)(kTQ * ns * 2));
+  L.ent = o; o += backward ? 0u : align16((unsigned)(kTQ * ns * 2));
   L.W = (n_src + 31) / 32;
   L.bitmap = o; o += align16((unsigned)L.W * 4u);
   L.prefix = o; o += align16((unsigned)(L.W + 1) * 4u);
   L.owner_id = o; o += kTQ * 4;
-  L.owner_neff = o; o += kTQ * 4;
-  L.owner_rc = o; o += kTQ * 12;
+  L.owner_info = o; o += kTQ * 4;
+  L.owner_xyz = o; o += kTQ * 12;
   L.owner_rho = o; o += kTQ * 4;
-  L.src_id = o; o += kKC * 4;
-  L.src_w = o; o += kKC * 12;
-  L.src_scale = o; o += kKC * 4;
-  L.scan = o; o += 16 * 4;
+  L.src_id = o; o += 2 * kKC * 4;
+  L.src_w = o; o += 2 * kKC * 12;
+  L.src_scale = o; o += 2 * kKC * 4;
+  L.scan = o; o += 32 * 4;
   L.bars = o; o += 32;
   L.total = o;
   L.np = (cbn + 15) & ~15;
@@ -91,6 +94,13 @@ __host__ __device__ inline Layout make_layout(int cbn, int ns, int n_src, int n_
 
 __device__ __forceinline__ float rot3(float x, float y, float z, int r) { return r == 0 ? x : (r == 1 ? y : z); }
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// bf16 bit pattern of a small non-negative integer (exact up to 256)
+__device__ __forceinline__ unsigned short bf16_of_count(int m) { return (unsigned short)(__float_as_uint((float)m) >> 16); }
+
 template <bool kBackward>
 __global__ void __launch_bounds__(kThreads, 2)
 pospool_tiles_kernel(const TileArgs a) {
@@ -100,23 +110,24 @@ pospool_tiles_kernel(const TileArgs a) {
   const int c0 = blockIdx.y * kCB, cbn = min(kCB, a.C - c0);
   const int n_own = kBackward ? a.N : a.M, n_src = kBackward ? a.M : a.N;
   const int ns = a.nsample;
-  const Layout L = make_layout(cbn, ns, n_src, n_own, kBackward);
+  const Layout L = make_layout(cbn, ns, n_src, kBackward);
 
   unsigned char* sA = smem + L.a;
   unsigned char* sPlanes = smem + L.planes;
   unsigned char* sStage = smem + L.stage;
-  unsigned short* sEnt = reinterpret_cast<unsigned short*>(smem + L.ent);  // forward: union rank of every (row, slot)
-  unsigned char* sTable = smem + L.ent;                                    // backward: support -> row of this tile
+  unsigned short* sEnt = reinterpret_cast<unsigned short*>(smem + L.ent);  // forward: union rank of every list entry
   unsigned* sBitmap = reinterpret_cast<unsigned*>(smem + L.bitmap);
   unsigned* sPrefix = reinterpret_cast<unsigned*>(smem + L.prefix);
   int* sOwnerId = reinterpret_cast<int*>(smem + L.owner_id);
-  int* sOwnerNeff = reinterpret_cast<int*>(smem + L.owner_neff);
-  float* sOwnerRc = reinterpret_cast<float*>(smem + L.owner_rc);
+  int* sOwnerInfo = reinterpret_cast<int*>(smem + L.owner_info);  // forward: entries | nvalid << 8 | padded << 16
+  float* sOwnerXyz = reinterpret_cast<float*>(smem + L.owner_xyz);
   float* sOwnerRho = reinterpret_cast<float*>(smem + L.owner_rho);
-  int* sSrcId = reinterpret_cast<int*>(smem + L.src_id);
-  float* sSrcW = reinterpret_cast<float*>(smem + L.src_w);
-  float* sSrcScale = reinterpret_cast<float*>(smem + L.src_scale);
-  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);
+  int* sSrcId = reinterpret_cast<int*>(smem + L.src_id);           // [2][kKC]
+  float* sSrcW = reinterpret_cast<float*>(smem + L.src_w);         // [2][kKC][3]
+  float* sSrcScale = reinterpret_cast<float*>(smem + L.src_scale); // [2][kKC]
+  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);    // [0..8] scan, [12..14] centre sums x4 at [16..31], [9..10] task counters
+  float* sCtr = reinterpret_cast<float*>(smem + L.scan) + 16;      // 4 warps x (x, y, z)
+  int* sTask = reinterpret_cast<int*>(smem + L.scan) + 9;
   const unsigned bar_stage = smem_u32(smem + L.bars), bar_mma = bar_stage + 8, tmem_slot = bar_stage + 16;
 
   const float* own_xyz = (kBackward ? a.support_xyz : a.query_xyz) + (size_t)b * n_own * 3;
@@ -126,45 +137,56 @@ pospool_tiles_kernel(const TileArgs a) {
   const int n_rows = min(kTQ, n_own - row0);
   const size_t qbase = (size_t)b * a.M;
 
-  // ---- P0: owners, tile centre, barriers, TMEM ------------------------------------------------------------------
-  const int first = order[row0];
-  const float ctr_x = own_xyz[3 * (size_t)first], ctr_y = own_xyz[3 * (size_t)first + 1], ctr_z = own_xyz[3 * (size_t)first + 2];
-  if (warp == 0) tmem_alloc(tmem_slot, (unsigned)L.tmem_cols);
-  if (tid == 32) {
+  // ---- P0: owners, barriers, TMEM ---------------------------------------------------------------------------------
+  if (warp == 4) tmem_alloc(tmem_slot, (unsigned)L.tmem_cols);
+  if (tid == 160) {
     mbar_init(bar_stage, 1);
     mbar_init(bar_mma, 1);
     mbar_init_fence();
   }
   if (tid < kTQ) {
-    int own = -1, neff = 0;
-    float rx = 0.f, ry = 0.f, rz = 0.f, rho = 0.f;
+    int own = -1, info = 0;
+    float px = 0.f, py = 0.f, pz = 0.f, rho = 0.f;
     if (tid < n_rows) {
       own = order[row0 + tid];
-      rx = own_xyz[3 * (size_t)own] - ctr_x; ry = own_xyz[3 * (size_t)own + 1] - ctr_y; rz = own_xyz[3 * (size_t)own + 2] - ctr_z;
+      px = own_xyz[3 * (size_t)own]; py = own_xyz[3 * (size_t)own + 1]; pz = own_xyz[3 * (size_t)own + 2];
       if (kBackward) {
         rho = -1.0f;
       } else {
         // feature_mask = idx_mask + (1 - query_mask): a padded query uses all nsample slots (:171)
-        neff = a.query_mask[qbase + own] != 0 ? a.nvalid[qbase + own] : ns;
+        const int nv = min(a.nvalid[qbase + own], ns);
+        const bool padded = a.query_mask[qbase + own] == 0;
+        const int neff = padded ? ns : nv;
+        // list entries: the nv distinct winners; a padded query with none gathers row 0 nsample times
+        info = ((padded && nv == 0) ? 1 : nv) | (nv << 8) | ((padded ? 1 : 0) << 16);
         rho = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;  // :175-176
       }
     }
-    sOwnerId[tid] = own; sOwnerNeff[tid] = neff;
-    sOwnerRc[3 * tid] = rx; sOwnerRc[3 * tid + 1] = ry; sOwnerRc[3 * tid + 2] = rz;
+    sOwnerId[tid] = own; sOwnerInfo[tid] = info;
+    sOwnerXyz[3 * tid] = px; sOwnerXyz[3 * tid + 1] = py; sOwnerXyz[3 * tid + 2] = pz;
     sOwnerRho[tid] = rho;
+    // tile centre = mean owner position (any point works; the mean keeps |owner - centre| small)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      px += __shfl_xor_sync(D3D_FULL_MASK, px, o);
+      py += __shfl_xor_sync(D3D_FULL_MASK, py, o);
+      pz += __shfl_xor_sync(D3D_FULL_MASK, pz, o);
+    }
+    if (lane == 0) { sCtr[3 * warp] = px; sCtr[3 * warp + 1] = py; sCtr[3 * warp + 2] = pz; }
   }
   for (int w = tid; w < L.W; w += kThreads) sBitmap[w] = 0u;
-  if (kBackward)
-    for (int i = tid; i < (int)(align16((unsigned)n_own) >> 4); i += kThreads)
-      reinterpret_cast<uint4*>(sTable)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  if (tid == 0) { sTask[0] = 0; sTask[1] = 0; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *reinterpret_cast<volatile unsigned*>(smem + L.bars + 16);
+  const float inv_rows = 1.0f / (float)n_rows;
+  const float ctr_x = (sCtr[0] + sCtr[3] + sCtr[6] + sCtr[9]) * inv_rows, ctr_y = (sCtr[1] + sCtr[4] + sCtr[7] + sCtr[10]) * inv_rows,
+              ctr_z = (sCtr[2] + sCtr[5] + sCtr[8] + sCtr[11]) * inv_rows;
 
   // ---- P1: union of the referenced source rows --------------------------------------------------------------------
   if (kBackward) {
-    if (tid < n_rows) sTable[sOwnerId[tid]] = (unsigned char)tid;
+    // pass 1 over the owners' inverse-map segments: which queries gathered them through an unmasked slot
     for (int r = warp; r < n_rows; r += kThreads / 32) {
       const size_t srow = (size_t)b * a.N + sOwnerId[r];
       const int beg = a.rowptr[srow], end = a.rowptr[srow + 1];
@@ -172,20 +194,46 @@ pospool_tiles_kernel(const TileArgs a) {
         const int packed = a.entries[e];
         const int q = packed >> 8, k = packed & 255;
         const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
-        if (k < neff) atomicOr(&sBitmap[q >> 5], 1u << (q & 31));
+        const bool valid = k < neff;
+        if (valid) atomicOr(&sBitmap[q >> 5], 1u << (q & 31));
+        a.rank_scratch[e] = valid ? q : -1;
       }
     }
   } else {
-    for (int r = warp; r < n_rows; r += kThreads / 32) {
-      const int own = sOwnerId[r], neff = sOwnerNeff[r];
-      const int* irow = a.idx + (qbase + own) * ns;
-      for (int k = lane; k < ns; k += 32) {
-        unsigned v = 0xffffu;
-        if (k < neff) {
-          v = (unsigned)d3d_clamp_index(irow[k], a.N);
-          atomicOr(&sBitmap[v >> 5], 1u << (v & 31));
+    // the rows' lists (ascending support index), four rows of loads in flight per warp
+    for (int r4 = warp; r4 < n_rows; r4 += 4 * (kThreads / 32)) {
+      int v[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r4 + i * (kThreads / 32);
+        v[i][0] = v[i][1] = -1;
+        if (r < n_rows) {
+          const int* lrow = a.by_support + (qbase + sOwnerId[r]) * ns;
+          if (lane < ns) v[i][0] = lrow[lane];
+          if (lane + 32 < ns) v[i][1] = lrow[lane + 32];
         }
-        sEnt[r * ns + k] = (unsigned short)v;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r4 + i * (kThreads / 32);
+        if (r < n_rows) {
+          const int info = sOwnerInfo[r];
+          const int n_ent = info & 255;
+          const bool row0_only = ((info >> 16) & 1) && ((info >> 8) & 255) == 0;  // padded query without neighbours
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int k = lane + 32 * h;
+            if (k < ns) {
+              unsigned id = 0xffffu;
+              if (k < n_ent) {
+                id = row0_only ? 0u : (unsigned)(v[i][h] & 0xffff);
+                if (id >= (unsigned)a.N) id = 0u;
+                atomicOr(&sBitmap[id >> 5], 1u << (id & 31));
+              }
+              sEnt[r * ns + k] = (unsigned short)id;
+            }
+          }
+        }
       }
     }
   }
@@ -220,125 +268,167 @@ pospool_tiles_kernel(const TileArgs a) {
   }
   const int U = (int)sScan[8];
   __syncthreads();
-  if (!kBackward) {  // source id -> rank inside the union
+  // source id -> rank inside the union (ranks ascend along every row's list: the union is ordered by index)
+  if (kBackward) {
+    for (int r = warp; r < n_rows; r += kThreads / 32) {
+      const size_t srow = (size_t)b * a.N + sOwnerId[r];
+      const int beg = a.rowptr[srow], end = a.rowptr[srow + 1];
+      for (int e = beg + lane; e < end; e += 32) {
+        const int q = a.rank_scratch[e];
+        if (q >= 0) a.rank_scratch[e] = (int)(sPrefix[q >> 5] + __popc(sBitmap[q >> 5] & ((1u << (q & 31)) - 1u)));
+      }
+    }
+  } else {
     for (int e = tid; e < n_rows * ns; e += kThreads) {
       const unsigned v = sEnt[e];
       if (v != 0xffffu) sEnt[e] = (unsigned short)(sPrefix[v >> 5] + __popc(sBitmap[v >> 5] & ((1u << (v & 31)) - 1u)));
     }
   }
 
-  // ---- chunks of 64 union rows ---------------------------------------------------------------------------------
   const int n_chunks = (U + kKC - 1) / kKC;
   const unsigned idesc = idesc_bf16(L.np, false, true);  // A K-major, B MN-major, N = channels rounded up to 16
   const int n_groups = (cbn + 7) >> 3;
   const float* src_rows = a.src + (size_t)b * n_src * a.C + c0;
-  constexpr int kBuildThreads = kBackward ? kKC : kTQ;   // threads that fill A; the others convert the staged rows
+
+  // rows of chunk j -> src buffers [j & 1], bulk copies into the staging buffer (warps 6-7, one row per thread)
+  auto select_and_issue = [&](int j) {
+    const int t = tid - 192, pb = j & 1;
+    const int r = j * kKC + t;
+    int src = -1;
+    if (r < U) {
+      int lo = 0, hi = L.W - 1;
+      while (lo < hi) {  // last word whose prefix is <= r: it holds the set bit of rank r
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)sPrefix[mid] <= r) lo = mid; else hi = mid - 1;
+      }
+      src = lo * 32 + (int)__fns(sBitmap[lo], 0, r - (int)sPrefix[lo] + 1);
+      bulk_g2s(smem_u32(sStage + (size_t)t * L.row_bytes), src_rows + (size_t)src * a.C, L.row_bytes, bar_stage);
+      float* w = sSrcW + (pb * kKC + t) * 3;
+      w[0] = src_xyz[3 * (size_t)src] - ctr_x; w[1] = src_xyz[3 * (size_t)src + 1] - ctr_y; w[2] = src_xyz[3 * (size_t)src + 2] - ctr_z;
+      float scale = 1.0f;
+      if (kBackward) {
+        const int neff = a.query_mask[qbase + src] != 0 ? a.nvalid[qbase + src] : ns;
+        scale = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;
+      }
+      sSrcScale[pb * kKC + t] = scale;
+    }
+    sSrcId[pb * kKC + t] = src;
+    named_bar_sync(1, 64);  // every selector's writes precede the arrive below (which the converters acquire)
+    if (t == 0) mbar_arrive_expect_tx(bar_stage, (unsigned)min(kKC, U - j * kKC) * L.row_bytes);
+  };
+
+  // staged fp32 row piece -> 3 bf16 planes of X and 3 of w * X, MN-major operand layout; task = (row, 8 channels)
+  auto convert = [&](int task, int rows16, int pb) {
+    const int u = task % rows16, g = task / rows16;
+    unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
+    unsigned hx[3][4], hy[3][4];
+    if (sSrcId[pb * kKC + u] < 0) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hx[p][i] = hy[p][i] = 0u;
+    } else {
+      const float* row = reinterpret_cast<const float*>(sStage + (size_t)u * L.row_bytes) + 8 * g;
+      const float4 xa = *reinterpret_cast<const float4*>(row);
+      const float4 xb = (8 * g + 4 < cbn) ? *reinterpret_cast<const float4*>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+      const float* wv = sSrcW + (pb * kKC + u) * 3;
+      const float wx = wv[0], wy = wv[1], wz = wv[2];
+      const int base = (c0 + 8 * g) % 3;
+      const float w0 = rot3(wx, wy, wz, base), w1 = rot3(wy, wz, wx, base), w2 = rot3(wz, wx, wy, base);
+      if (kBackward) {
+        const float sc = sSrcScale[pb * kKC + u];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] *= sc;
+      }
+      const float y[8] = {x[0] * w0, x[1] * w1, x[2] * w2, x[3] * w0, x[4] * w1, x[5] * w2, x[6] * w0, x[7] * w1};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        split3_bf16x2(x[2 * i], x[2 * i + 1], hx[0][i], hx[1][i], hx[2][i]);
+        split3_bf16x2(y[2 * i], y[2 * i + 1], hy[0][i], hy[1][i], hy[2][i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      *reinterpret_cast<uint4*>(dst + (size_t)p * L.plane_bytes) = make_uint4(hx[p][0], hx[p][1], hx[p][2], hx[p][3]);
+      *reinterpret_cast<uint4*>(dst + (size_t)(3 + p) * L.plane_bytes) = make_uint4(hy[p][0], hy[p][1], hy[p][2], hy[p][3]);
+    }
+  };
+
+  // ---- chunks of 64 union rows ---------------------------------------------------------------------------------
+  if (n_chunks > 0 && warp >= 6) select_and_issue(0);
+  // A-build cursor of this thread's row
+  int cur = 0, cur_end = 0, row_info = 0;
+  const int* prow = nullptr;  // forward, padded rows only: the list with the distance ranks
+  if (tid < n_rows) {
+    if (kBackward) {
+      const size_t srow = (size_t)b * a.N + sOwnerId[tid];
+      cur = a.rowptr[srow]; cur_end = a.rowptr[srow + 1];
+    } else {
+      row_info = sOwnerInfo[tid];
+      cur_end = row_info & 255;
+      prow = a.by_support + (qbase + sOwnerId[tid]) * ns;
+    }
+  }
+  __syncthreads();  // ranks (forward: sEnt; backward: rank_scratch, written by other threads of this CTA) are in place
+
   for (int j = 0; j < n_chunks; ++j) {
+    const int pb = j & 1;
     const int rows_here = min(kKC, U - j * kKC);
     const int ksteps = (rows_here + 15) >> 4;
-    // a. which rows; issue their bulk copies (the staging buffer was released by the barrier ending the previous chunk)
-    if (tid < kKC) {
-      const int r = j * kKC + tid;
-      int src = -1;
-      if (r < U) {
-        int lo = 0, hi = L.W - 1;
-        while (lo < hi) {  // last word whose prefix is <= r: it holds the set bit of rank r
-          const int mid = (lo + hi + 1) >> 1;
-          if ((int)sPrefix[mid] <= r) lo = mid; else hi = mid - 1;
-        }
-        src = lo * 32 + (int)__fns(sBitmap[lo], 0, r - (int)sPrefix[lo] + 1);
-        sSrcW[3 * tid] = src_xyz[3 * (size_t)src] - ctr_x;
-        sSrcW[3 * tid + 1] = src_xyz[3 * (size_t)src + 1] - ctr_y;
-        sSrcW[3 * tid + 2] = src_xyz[3 * (size_t)src + 2] - ctr_z;
-        float scale = 1.0f;
-        if (kBackward) {
-          const int neff = a.query_mask[qbase + src] != 0 ? a.nvalid[qbase + src] : ns;
-          scale = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;
-        }
-        sSrcScale[tid] = scale;
-        bulk_g2s(smem_u32(sStage + (size_t)tid * L.row_bytes), src_rows + (size_t)src * a.C, L.row_bytes, bar_stage);
-      }
-      sSrcId[tid] = src;
-    }
-    if (tid == 0) mbar_arrive_expect_tx(bar_stage, (unsigned)rows_here * L.row_bytes);
-    // b. the previous chunk's MMAs are done reading A and the planes
-    if (j > 0) {
+    if (j > 0) {  // the previous chunk's MMAs are done reading A and the planes
       mbar_wait(bar_mma, (unsigned)((j - 1) & 1));
       tc_fence_after();
     }
-    for (int i = tid; i < (int)(kABytes >> 4); i += kThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-    if (tid < kBuildThreads) {
-      // c1. multiplicity matrix A[row][union rank - 64 j]; every element has ONE writer thread (its row forward, its
-      //     column backward), so the read-modify-write needs no atomics and the result does not depend on timing
+    if (warp < 4) {
+      // multiplicity matrix A[row][union rank - 64 j]: a thread owns its row — it clears it and writes the run of its
+      // list that falls into this chunk (ranks ascend along the list).  No atomics, no dependence on timing.
+      unsigned char* arow = sA + (tid >> 3) * kASbo + (tid & 7) * 16;
+#pragma unroll
+      for (int g = 0; g < kKC / 8; ++g) *reinterpret_cast<uint4*>(arow + g * 128) = make_uint4(0u, 0u, 0u, 0u);
+      const int limit = (j + 1) * kKC;
       if (kBackward) {
-        const int q = sSrcId[tid];
-        if (q >= 0) {
-          const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
-          const int* irow = a.idx + (qbase + q) * ns;
-          for (int k = 0; k < neff; ++k) {
-            const unsigned tl = sTable[d3d_clamp_index(irow[k], a.N)];
-            if (tl != 255u) {
-              unsigned short* p = reinterpret_cast<unsigned short*>(sA + (tl >> 3) * kASbo + (tid >> 3) * 128 + (tl & 7) * 16 + (tid & 7) * 2);
-              *p = (unsigned short)(__float_as_uint(__uint_as_float((unsigned)*p << 16) + 1.0f) >> 16);
-            }
-          }
-        }
-      } else if (tid < n_rows) {
-        const unsigned short* e = sEnt + tid * ns;
-        unsigned char* arow = sA + (tid >> 3) * kASbo + (tid & 7) * 16;
-        for (int k = 0; k < ns; ++k) {
-          const unsigned r = e[k];
-          if ((int)(r >> 6) == j) {  // 0xffff (masked slot) never matches: fewer than 1023 chunks
+        while (cur < cur_end) {
+          const int r = a.rank_scratch[cur];
+          if (r >= limit) break;
+          if (r >= 0) {  // equal ranks are adjacent (a padded query repeats its slots): add
             unsigned short* p = reinterpret_cast<unsigned short*>(arow + ((r & 63) >> 3) * 128 + (r & 7) * 2);
             *p = (unsigned short)(__float_as_uint(__uint_as_float((unsigned)*p << 16) + 1.0f) >> 16);
           }
+          ++cur;
+        }
+      } else {
+        const unsigned short* e = sEnt + tid * ns;
+        while (cur < cur_end) {
+          const int r = e[cur];
+          if (r >= limit) break;
+          int m = 1;
+          if (row_info >> 16) {  // padded query: slot k of the reference list repeats winner k % nvalid (cyclic padding)
+            const int nv = (row_info >> 8) & 255;
+            m = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
+          }
+          *reinterpret_cast<unsigned short*>(arow + ((r & 63) >> 3) * 128 + (r & 7) * 2) = bf16_of_count(m);
+          ++cur;
         }
       }
-    } else {
-      // c2. staged fp32 rows -> 3 bf16 planes of X and 3 of w * X, MN-major operand layout; task = (row, 8 channels)
-      mbar_wait(bar_stage, (unsigned)(j & 1));
-      const int n_tasks = ksteps * 16 * n_groups;
-      for (int task = tid - kBuildThreads; task < n_tasks; task += kThreads - kBuildThreads) {
-        const int u = task % (ksteps * 16), g = task / (ksteps * 16);
-        unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
-        unsigned hx[3][4], hy[3][4];
-        if (sSrcId[u] < 0) {
-#pragma unroll
-          for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) hx[p][i] = hy[p][i] = 0u;
-        } else {
-          const float* row = reinterpret_cast<const float*>(sStage + (size_t)u * L.row_bytes) + 8 * g;
-          const float4 xa = *reinterpret_cast<const float4*>(row);
-          const float4 xb = (8 * g + 4 < cbn) ? *reinterpret_cast<const float4*>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-          const float wx = sSrcW[3 * u], wy = sSrcW[3 * u + 1], wz = sSrcW[3 * u + 2];
-          const int base = (c0 + 8 * g) % 3;
-          const float w0 = rot3(wx, wy, wz, base), w1 = rot3(wy, wz, wx, base), w2 = rot3(wz, wx, wy, base);
-          if (kBackward) {
-            const float sc = sSrcScale[u];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] *= sc;
-          }
-          const float y[8] = {x[0] * w0, x[1] * w1, x[2] * w2, x[3] * w0, x[4] * w1, x[5] * w2, x[6] * w0, x[7] * w1};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            split3_bf16x2(x[2 * i], x[2 * i + 1], hx[0][i], hx[1][i], hx[2][i]);
-            split3_bf16x2(y[2 * i], y[2 * i + 1], hy[0][i], hy[1][i], hy[2][i]);
-          }
-        }
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {
-          *reinterpret_cast<uint4*>(dst + (size_t)p * L.plane_bytes) = make_uint4(hx[p][0], hx[p][1], hx[p][2], hx[p][3]);
-          *reinterpret_cast<uint4*>(dst + (size_t)(3 + p) * L.plane_bytes) = make_uint4(hy[p][0], hy[p][1], hy[p][2], hy[p][3]);
-        }
+    }
+    // staged rows -> operand planes: every warp takes 32 tasks at a time (the A warps join when their rows are done)
+    mbar_wait(bar_stage, (unsigned)(j & 1));
+    {
+      const int rows16 = ksteps * 16, n_tasks = rows16 * n_groups;
+      for (;;) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sTask[pb], 32);
+        base = __shfl_sync(D3D_FULL_MASK, base, 0);
+        if (base >= n_tasks) break;
+        if (base + lane < n_tasks) convert(base + lane, rows16, pb);
       }
     }
     fence_async_smem();
     tc_fence_before();
+    if (tid == 0) sTask[pb ^ 1] = 0;
     __syncthreads();
-    // d. Y1 += A . X planes, Y2 += A . (w X) planes
+    // Y1 += A . X planes, Y2 += A . (w X) planes
     if (tid == 0) {
       tc_fence_after();
       const unsigned a_addr = smem_u32(sA), p_addr = smem_u32(sPlanes);
@@ -353,6 +443,8 @@ pospool_tiles_kernel(const TileArgs a) {
       }
       mma_commit(bar_mma);
     }
+    // the staging buffer is free (all conversions ended before the barrier): next chunk's rows fly during the MMAs
+    if (warp >= 6 && j + 1 < n_chunks) select_and_issue(j + 1);
   }
 
   // ---- epilogue: thread = owner row (TMEM lane); the two warp groups split the 16-column pieces --------------------
@@ -363,7 +455,8 @@ pospool_tiles_kernel(const TileArgs a) {
   {
     const int lq = warp & 3, t = lq * 32 + lane;
     const int own = sOwnerId[t];
-    const float rcx = sOwnerRc[3 * t], rcy = sOwnerRc[3 * t + 1], rcz = sOwnerRc[3 * t + 2], rho = sOwnerRho[t];
+    const float rcx = sOwnerXyz[3 * t] - ctr_x, rcy = sOwnerXyz[3 * t + 1] - ctr_y, rcz = sOwnerXyz[3 * t + 2] - ctr_z;
+    const float rho = sOwnerRho[t];
     float* orow = a.out + ((size_t)b * n_own + (own >= 0 ? own : 0)) * a.C + c0;
     for (int ch = warp >> 2; ch * 16 < cbn; ch += 2) {
       unsigned y1[16], y2[16];
@@ -394,7 +487,7 @@ pospool_tiles_kernel(const TileArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, (unsigned)L.tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem_base, (unsigned)L.tmem_cols);
 }
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
@@ -404,7 +497,7 @@ int launch_tiles(const TileArgs& a, int B, cudaStream_t st) {
   const int n_own = kBackward ? a.N : a.M, n_src = kBackward ? a.M : a.N;
   if (n_own > kMaxPoints || n_src > kMaxPoints || a.nsample > kMaxNs || a.C % 4 != 0) return D3D_ERR_UNSUPPORTED;
   const int cbn_max = a.C < kCB ? a.C : kCB;
-  const Layout L = make_layout(cbn_max, a.nsample, n_src, n_own, kBackward);
+  const Layout L = make_layout(cbn_max, a.nsample, n_src, kBackward);
   auto kernel = pospool_tiles_kernel<kBackward>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) return (int)e;
@@ -418,36 +511,43 @@ int launch_tiles(const TileArgs& a, int B, cudaStream_t st) {
 
 extern "C" {
 
-int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx_by_support,
                           const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
                           int nsample, float radius, int reduction, float* out_cl, void* stream) {
-  D3D_REQUIRE(feat_cl && query_xyz && support_xyz && idx && nvalid && query_mask && query_order && out_cl);
+  D3D_REQUIRE(feat_cl && query_xyz && support_xyz && idx_by_support && nvalid && query_mask && query_order && out_cl);
   D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
   D3D_REQUIRE(reduction == D3D_REDUCE_SUM || reduction == D3D_REDUCE_AVG);
   if (!aligned16(feat_cl) || !aligned16(out_cl)) return D3D_ERR_UNSUPPORTED;
   if (B == 0 || M == 0) return 0;
   TileArgs a{};
-  a.src = feat_cl; a.out = out_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx; a.nvalid = nvalid;
-  a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
+  a.src = feat_cl; a.out = out_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.by_support = idx_by_support;
+  a.nvalid = nvalid; a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
   a.reduction = reduction; a.inv_radius = 1.0f / radius;
   return launch_tiles<false>(a, B, (cudaStream_t)stream);
 }
 
-int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* idx,
-                          const int* rowptr, const int* entries, const int* nvalid, const int* query_mask,
-                          const int* support_order, int B, int M, int N, int C, int nsample, float radius, int reduction,
-                          float* grad_feat_cl, void* stream) {
-  D3D_REQUIRE(grad_out_cl && query_xyz && support_xyz && idx && rowptr && entries && nvalid && query_mask);
+size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample) {
+  if (B <= 0 || M <= 0 || nsample <= 0) return 0;
+  return (size_t)B * M * nsample * sizeof(int);
+}
+
+int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* rowptr,
+                          const int* entries, const int* nvalid, const int* query_mask, const int* support_order, int B,
+                          int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl, void* ws,
+                          size_t ws_bytes, void* stream) {
+  D3D_REQUIRE(grad_out_cl && query_xyz && support_xyz && rowptr && entries && nvalid && query_mask);
   D3D_REQUIRE(support_order && grad_feat_cl);
   D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
   D3D_REQUIRE(reduction == D3D_REDUCE_SUM || reduction == D3D_REDUCE_AVG);
   if (!aligned16(grad_out_cl) || !aligned16(grad_feat_cl)) return D3D_ERR_UNSUPPORTED;
   if (B == 0) return 0;
   if (M == 0) return (int)cudaMemsetAsync(grad_feat_cl, 0, (size_t)B * N * C * sizeof(float), (cudaStream_t)stream);
+  if (!ws || ws_bytes < d3d_pospool_tiles_bwd_workspace_bytes(B, M, nsample)) return D3D_ERR_WORKSPACE;
   TileArgs a{};
-  a.src = grad_out_cl; a.out = grad_feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.idx = idx;
-  a.rowptr = rowptr; a.entries = entries; a.nvalid = nvalid; a.query_mask = query_mask; a.order = support_order;
-  a.M = M; a.N = N; a.C = C; a.nsample = nsample; a.reduction = reduction; a.inv_radius = 1.0f / radius;
+  a.src = grad_out_cl; a.out = grad_feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz;
+  a.rowptr = rowptr; a.entries = entries; a.rank_scratch = (int*)ws; a.nvalid = nvalid; a.query_mask = query_mask;
+  a.order = support_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample; a.reduction = reduction;
+  a.inv_radius = 1.0f / radius;
   return launch_tiles<true>(a, B, (cudaStream_t)stream);
 }
 

@@ -52,11 +52,12 @@ class _Produced:
 
 
 class NeighborList(_Produced):
-    __slots__ = ("idx", "idx_mask", "nvalid", "n_support", "_csr", "_keepalive", "_stream", "_event", "_csr_event",
-                 "_csr_stream")
+    __slots__ = ("idx", "idx_mask", "nvalid", "n_support", "by_support", "_csr", "_keepalive", "_stream", "_event",
+                 "_csr_event", "_csr_stream")
 
-    def __init__(self, idx, idx_mask, nvalid, n_support, keepalive=()):
+    def __init__(self, idx, idx_mask, nvalid, n_support, keepalive=(), by_support=None):
         self.idx, self.idx_mask, self.nvalid, self.n_support = idx, idx_mask, nvalid, n_support
+        self.by_support = by_support  # winners in ascending support index (staged-tile kernels), or None
         self._csr = None
         self._csr_event, self._csr_stream = None, None
         self._keepalive = keepalive  # the tensors the cache key points at must outlive the entry
@@ -128,9 +129,11 @@ def ball_neighbors(query_xyz, support_xyz, query_mask, support_mask, radius, nsa
     """Cached masked ordered ball query -> NeighborList."""
     def build():
         with torch.no_grad():
-            idx, msk, nv = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample,
-                                          want_nvalid=True)
-        return NeighborList(idx, msk, nv, support_xyz.shape[1], (query_xyz, support_xyz, query_mask, support_mask))
+            out = ops.ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_nvalid=True,
+                                 want_by_support=True)
+        idx, msk, nv = out[:3]
+        return NeighborList(idx, msk, nv, support_xyz.shape[1], (query_xyz, support_xyz, query_mask, support_mask),
+                            by_support=out[3] if len(out) > 3 else None)
 
     return cache.get("ball", (query_xyz, support_xyz, query_mask, support_mask), (float(radius), int(nsample)), build).sync()
 

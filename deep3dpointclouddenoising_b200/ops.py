@@ -54,8 +54,10 @@ def _p(t):
 # ------------------------------------------------------------------------------------------------
 # neighbourhood construction
 # ------------------------------------------------------------------------------------------------
-def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_nvalid=False):
-    """(idx, idx_mask[, nvalid]) — _ext.masked_ordered_ball_query (masked_ordered_ball_query.cpp:13-59)."""
+def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample, want_nvalid=False,
+               want_by_support=False):
+    """(idx, idx_mask[, nvalid][, idx_by_support]) — _ext.masked_ordered_ball_query (masked_ordered_ball_query.cpp:13-59).
+    idx_by_support: the winners of every query in ascending support index, (distance rank << 16) | index, -1 padded."""
     L = _lib.load()
     q, s = _f32(query_xyz, "query_xyz"), _f32(support_xyz, "support_xyz")
     qm, sm = _i32(query_mask, "query_mask"), _i32(support_mask, "support_mask")
@@ -64,11 +66,14 @@ def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample
         idx = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
         msk = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
         nv = torch.empty((B, M), dtype=torch.int32, device=q.device) if want_nvalid else None
+        want_by_support = want_by_support and N <= 65536
+        bys = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device) if want_by_support else None
         ws = _ws(L.d3d_ball_query_workspace_bytes(B, M, N), q.device)
         _lib.check(L.d3d_ball_query(_p(q), _p(s), _p(qm), _p(sm), B, M, N, float(radius), int(nsample), _p(idx),
-                                    _p(msk), _p(nv), _p(ws), ws.numel(), _stream()), "d3d_ball_query")
+                                    _p(msk), _p(nv), _p(bys), _p(ws), ws.numel(), _stream()), "d3d_ball_query")
     _count()
-    return (idx, msk, nv) if want_nvalid else (idx, msk)
+    out = (idx, msk) + ((nv,) if want_nvalid else ()) + ((bys,) if want_by_support else ())
+    return out
 
 
 def nearest_query(query_xyz, support_xyz, query_mask, support_mask):
@@ -197,40 +202,43 @@ def _tiles_ok(M, N, ns, C):
     return 0 < M <= TILE_MAX_POINTS and N <= TILE_MAX_POINTS and ns <= TILE_MAX_NSAMPLE and C % 4 == 0
 
 
-def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius, reduction, query_order=None):
-    """query_order (B, M) from `spatial_order`: the staged-tile tensor-core kernel; None: the per-query gather kernel."""
+def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius, reduction, query_order=None,
+                idx_by_support=None):
+    """query_order (B, M) from `spatial_order` + idx_by_support from `ball_query`: the staged-tile tensor-core kernel;
+    otherwise the per-query gather kernel."""
     L = _lib.load()
     f = _f32(feat_cl, "features")
     B, N, C = f.shape
     M, ns = idx.shape[1], idx.shape[2]
     with torch.cuda.device(f.device):
         out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
-        args = (_p(f), _p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")), _p(_i32(idx, "idx")),
-                _p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")))
-        if query_order is not None and _tiles_ok(M, N, ns, C):
-            _lib.check(L.d3d_pospool_tiles_fwd(*args, _p(_i32(query_order, "query_order")), B, M, N, C, ns, float(radius),
+        xyz = (_p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")))
+        tail = (_p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")))
+        if query_order is not None and idx_by_support is not None and _tiles_ok(M, N, ns, C):
+            _lib.check(L.d3d_pospool_tiles_fwd(_p(f), *xyz, _p(_i32(idx_by_support, "idx_by_support")), *tail,
+                                               _p(_i32(query_order, "query_order")), B, M, N, C, ns, float(radius),
                                                REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_tiles_fwd")
         else:
-            _lib.check(L.d3d_pospool_fwd(*args, B, M, N, C, ns, float(radius), REDUCTIONS[reduction], _p(out), _stream()),
-                       "d3d_pospool_fwd")
+            _lib.check(L.d3d_pospool_fwd(_p(f), *xyz, _p(_i32(idx, "idx")), *tail, B, M, N, C, ns, float(radius),
+                                         REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_fwd")
     _count()
     return out
 
 
 def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, query_mask, n_support, nsample, radius,
-                reduction, idx=None, support_order=None):
-    """idx + support_order (B, N): the staged-tile kernel; otherwise the per-support segmented reduction."""
+                reduction, support_order=None):
+    """support_order (B, N) from `spatial_order`: the staged-tile kernel; otherwise the per-support segmented reduction."""
     L = _lib.load()
     g = _f32(grad_out_cl, "grad_out")
     B, M, C = g.shape
     with torch.cuda.device(g.device):
         out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
-        if support_order is not None and idx is not None and _tiles_ok(M, int(n_support), int(nsample), C):
-            _lib.check(L.d3d_pospool_tiles_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(_i32(idx, "idx")), _p(rowptr),
-                                               _p(entries), _p(nvalid), _p(query_mask),
-                                               _p(_i32(support_order, "support_order")), B, M, int(n_support), C,
-                                               int(nsample), float(radius), REDUCTIONS[reduction], _p(out), _stream()),
-                       "d3d_pospool_tiles_bwd")
+        if support_order is not None and _tiles_ok(M, int(n_support), int(nsample), C):
+            ws = _ws(L.d3d_pospool_tiles_bwd_workspace_bytes(B, M, int(nsample)), g.device)
+            _lib.check(L.d3d_pospool_tiles_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
+                                               _p(query_mask), _p(_i32(support_order, "support_order")), B, M,
+                                               int(n_support), C, int(nsample), float(radius), REDUCTIONS[reduction],
+                                               _p(out), _p(ws), ws.numel(), _stream()), "d3d_pospool_tiles_bwd")
         else:
             _lib.check(L.d3d_pospool_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
                                          _p(query_mask), B, M, int(n_support), C, int(nsample), float(radius),

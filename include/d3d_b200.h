@@ -49,13 +49,16 @@ long long d3d_kernel_launches(void);
  *        (binding: _ext_src/src/bindings.cpp:11; Python caller: pt_custom_ops/pt_utils.py:71-72).
  * Out: idx, idx_mask (B, M, nsample) int32.  nvalid (B, M) int32 may be NULL; when given it receives
  * min(#in-radius supports, nsample) per query BEFORE the query mask is applied (the fused aggregation
- * kernels use it instead of the dense idx_mask).
+ * kernels use it instead of the dense idx_mask).  idx_by_support (B, M, nsample) int32 may be NULL; when given it
+ * receives the same min(#in-radius, nsample) winners of every query in ASCENDING SUPPORT INDEX, each as
+ * (distance rank << 16) | index (distance rank = its slot in idx), -1 padded — the order the staged-tile aggregation
+ * kernels walk (needs N <= 65536).
  * Workspace: d3d_ball_query_workspace_bytes(B, M, N).  Unlike the reference no (B, M, 3*nsample) scratch
  * tensors are needed (masked_ordered_ball_query.cpp:38-44). */
 size_t d3d_ball_query_workspace_bytes(int B, int M, int N);
 int d3d_ball_query(const float* query_xyz, const float* support_xyz, const int* query_mask,
                    const int* support_mask, int B, int M, int N, float radius, int nsample,
-                   int* idx, int* idx_mask, int* nvalid, void* ws, size_t ws_bytes, void* stream);
+                   int* idx, int* idx_mask, int* nvalid, int* idx_by_support, void* ws, size_t ws_bytes, void* stream);
 
 /* Replaces  _ext.masked_nearest_query(query_xyz, support_xyz, query_mask, support_mask)
  *   ref: _ext_src/src/masked_nearest_query.cpp:12-47, _ext_src/src/masked_nearest_query_gpu.cu:8-62
@@ -137,17 +140,20 @@ int d3d_spatial_order(const float* xyz, int B, int N, int* order, void* stream);
 /* PosPool as a staged-tile kernel (same math and arguments as d3d_pospool_fwd / _bwd, which remain the path for sizes
  * beyond the limits below): a CTA owns 128 spatially adjacent rows (query_order / support_order from
  * d3d_spatial_order), stages the union of the rows their neighbourhoods reference with cp.async.bulk and contracts
- * [128 x union] multiplicities with the staged rows on the tensor cores (tcgen05, exact 3-term bf16 split, fp32
+ * [128 x union] multiplicities (from idx_by_support of d3d_ball_query: every query's winners in ascending support
+ * index) with the staged rows on the tensor cores (tcgen05, exact 3-term bf16 split, fp32
  * accumulation); the backward pass owns 128 SUPPORT rows and is a fixed-order reduction (no float atomics).
  *   replaces ref: pt_custom_ops/_ext_src/src/group_points_gpu.cu:13-33,48-69 + models/local_aggregation_operators.py:140-183
  * Limits: M, N <= 16384, nsample <= 64, C % 4 == 0 (D3D_ERR_UNSUPPORTED otherwise). */
-int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx,
+int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx_by_support,
                           const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
                           int nsample, float radius, int reduction, float* out_cl, void* stream);
-int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* idx,
-                          const int* rowptr, const int* entries, const int* nvalid, const int* query_mask,
-                          const int* support_order, int B, int M, int N, int C, int nsample, float radius, int reduction,
-                          float* grad_feat_cl, void* stream);
+/* Workspace of the backward pass: one int per inverse-map entry (union ranks). */
+size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample);
+int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* rowptr,
+                          const int* entries, const int* nvalid, const int* query_mask, const int* support_order, int B,
+                          int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl, void* ws,
+                          size_t ws_bytes, void* stream);
 
 #define D3D_KP_CONSTANT 0
 #define D3D_KP_LINEAR   1

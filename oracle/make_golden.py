@@ -153,7 +153,46 @@ def aggregation_goldens():
     print("aggregation.npz", len(out), "arrays")
 
 
+def extra_goldens():
+    """Variants no head of the reference uses but its API offers (pt_utils.py:158-180, 227-234): MaskedUpsample
+    'max' / 'rbf' and MaskedNearestQueryAndGroup.forward, outputs and autograd gradients from the reference's Python."""
+    pt_utils, _ = install_reference_python()
+    torch.manual_seed(1)
+    # radius 0.06: every fine point has a coarse support inside the ball (with none the reference kernel computes
+    # `i % 0`, masked_ordered_ball_query_gpu.cu:83-86 — undefined on the GPU, SIGFPE in the host build)
+    B, N, C, ns, radius = 2, 384, 24, 20, 0.06
+    pts, mask = seeded_levels(29, B, N)
+    xyz, m = torch.from_numpy(pts), torch.from_numpy(mask)
+    sub_xyz, sub_mask = [torch.from_numpy(a) for a in cpu_index_ops.reference().grid_subsampling(pts, mask, 96, 0.00625)]
+    out = {"points": pts, "mask": mask, "sub_xyz": sub_xyz.numpy(), "sub_mask": sub_mask.numpy(),
+           "meta": np.array([B, N, C, ns], np.int64), "radius": np.float32(radius)}
+    coarse = torch.randn(B, C, 96)
+    out["coarse"] = coarse.numpy()
+    for mode in ("max", "rbf"):
+        up = pt_utils.MaskedUpsample(radius, ns, mode=mode)
+        cf = coarse.clone().requires_grad_(True)
+        y = up(xyz, sub_xyz, m, sub_mask, cf)
+        g = torch.randn_like(y)
+        out[f"up_{mode}_out"], out[f"up_{mode}_gout"] = y.detach().numpy(), g.numpy()
+        out[f"up_{mode}_gfeat"] = torch.autograd.grad(y, cf, g)[0].numpy()
+    for use_xyz in (True, False):
+        grouper = pt_utils.MaskedNearestQueryAndGroup(use_xyz=use_xyz, ret_grouped_xyz=True)
+        cf = coarse.clone().requires_grad_(True)
+        feats, gxyz, imask = grouper(xyz, sub_xyz, m, sub_mask, cf)
+        g = torch.randn_like(feats)
+        tag = "xyz" if use_xyz else "noxyz"
+        out[f"nqg_{tag}_feat"], out[f"nqg_{tag}_gxyz"], out[f"nqg_{tag}_mask"] = feats.detach().numpy(), gxyz.numpy(), imask.numpy()
+        out[f"nqg_{tag}_gout"], out[f"nqg_{tag}_gfeat"] = g.numpy(), torch.autograd.grad(feats, cf, g)[0].numpy()
+    grouper = pt_utils.MaskedNearestQueryAndGroup(use_xyz=True)
+    feats, imask = grouper(xyz, sub_xyz, m, sub_mask, None)
+    out["nqg_nofeat_feat"] = feats.numpy()
+    np.savez_compressed(os.path.join(OUT, "aggregation_extra.npz"), **out)
+    print("aggregation_extra.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    index_goldens()
-    aggregation_goldens()
+    if "--extra-only" not in sys.argv:
+        index_goldens()
+        aggregation_goldens()
+    extra_goldens()

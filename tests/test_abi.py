@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.d3d_abi_version() == 1
+    assert lib.d3d_abi_version() == 2
     assert lib.d3d_error_string(0) == b"ok"
     assert b"workspace" in lib.d3d_error_string(-3)
 
@@ -48,7 +48,7 @@ def test_workspace_queries_are_pure_host_functions(lib):
 
 
 def test_bad_arguments_are_rejected_without_touching_the_device(lib):
-    assert lib.d3d_ball_query(None, None, None, None, 1, 1, 1, 0.1, 4, None, None, None, None, 0, None) == -1
+    assert lib.d3d_ball_query(None, None, None, None, 1, 1, 1, 0.1, 4, None, None, None, None, None, 0, None) == -1
     assert lib.d3d_group_points(None, None, 1, 1, 1, 1, 1, None, None) == -1
 
 

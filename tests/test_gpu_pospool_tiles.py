@@ -45,6 +45,23 @@ def test_spatial_order_is_the_morton_permutation(cuda_device, N):
         assert np.array_equal(order[b], morton_order_numpy(pts[b]))
 
 
+def test_ball_query_winners_by_support_index(cuda_device):
+    """idx_by_support: the same winners as idx[:, :, :nvalid], ascending support index, distance rank in bits 16..23."""
+    from deep3dpointclouddenoising_b200 import ops
+    for (N, M, ns, radius) in ((2048, 2048, 52, 0.025), (8192, 8192, 52, 0.025), (1000, 1000, 7, 0.004), (600, 600, 64, 0.2)):
+        pts, mask, _, _ = synthetic.make_batch(5 + N, 2, N, ragged=True)
+        d, dm = dev(pts, cuda_device), dev(mask, cuda_device)
+        idx, msk, nv, bys = [t.cpu().numpy() for t in ops.ball_query(d, d, dm, dm, radius, ns, want_nvalid=True, want_by_support=True)]
+        for b in range(2):
+            for j in range(0, M, 37):
+                n = int(nv[b, j])
+                row = bys[b, j]
+                assert (row[n:] == -1).all() and (row[:n] >= 0).all()
+                ids, ranks = row[:n] & 0xffff, row[:n] >> 16
+                assert (np.diff(ids) > 0).all()
+                assert np.array_equal(idx[b, j, ranks], ids) and np.array_equal(np.sort(ranks), np.arange(n))
+
+
 def _case(oracle, seed, B, N, M, ns, radius, C):
     pts, mask, _, _ = synthetic.make_batch(seed, B, N, ragged=True)
     if M == N:
@@ -71,19 +88,22 @@ def test_staged_pospool_against_float_oracle(cuda_device, oracle, C, N, M, ns, r
     ref = agg.pospool(tf, *targs, radius, reduction)
     (ref_g,) = torch.autograd.grad(ref, tf, torch.from_numpy(gout))
     dq, ds, dqm, dsm = dev(q, cuda_device), dev(pts, cuda_device), dev(qm, cuda_device), dev(mask, cuda_device)
-    didx, dmsk, dnv = ops.ball_query(dq, ds, dqm, dsm, radius, ns, want_nvalid=True)
+    didx, dmsk, dnv, dbys = ops.ball_query(dq, ds, dqm, dsm, radius, ns, want_nvalid=True, want_by_support=True)
     assert np.array_equal(didx.cpu().numpy(), idx)
     f_cl = dev(f.transpose(0, 2, 1), cuda_device)
     g_cl = dev(gout.transpose(0, 2, 1), cuda_device)
     oq, os_ = ops.spatial_order(dq), ops.spatial_order(ds)
-    out = ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq)
+    out = ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq, idx_by_support=dbys)
+    # 'sum' is 'avg' times the neighbourhood size: the same relative accuracy means an absolute tolerance nsample times larger
+    FWD = dict(rtol=1e-5, atol=2e-6 * (ns if reduction == 'sum' else 1))
+    BWD = dict(rtol=1e-4, atol=2e-5 * (ns if reduction == 'sum' else 1))
     np.testing.assert_allclose(out.cpu().numpy().transpose(0, 2, 1), ref.detach().numpy(), **FWD)
     rowptr, entries = ops.build_inverse_map(didx, N)
-    gf = ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction, idx=didx, support_order=os_)
+    gf = ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction, support_order=os_)
     np.testing.assert_allclose(gf.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
     # same bits on a second run (fixed-order reduction, no atomics on floats), and close to the per-query gather kernels
-    assert torch.equal(out, ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq))
-    assert torch.equal(gf, ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction, idx=didx,
+    assert torch.equal(out, ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq, idx_by_support=dbys))
+    assert torch.equal(gf, ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction,
                                            support_order=os_))
     legacy = ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction)
     np.testing.assert_allclose(out.cpu().numpy(), legacy.cpu().numpy(), **FWD)
@@ -101,14 +121,14 @@ def test_staged_pospool_at_the_benched_level0_shape(cuda_device, oracle):
     ref = agg.pospool(tf, *targs, radius, 'avg')
     (ref_g,) = torch.autograd.grad(ref, tf, torch.from_numpy(gout))
     ds, dsm = dev(pts, cuda_device), dev(mask, cuda_device)
-    didx, dmsk, dnv = ops.ball_query(ds, ds, dsm, dsm, radius, ns, want_nvalid=True)
+    didx, dmsk, dnv, dbys = ops.ball_query(ds, ds, dsm, dsm, radius, ns, want_nvalid=True, want_by_support=True)
     assert np.array_equal(didx.cpu().numpy(), idx)
     order = ops.spatial_order(ds)
     f_cl, g_cl = dev(f.transpose(0, 2, 1), cuda_device), dev(gout.transpose(0, 2, 1), cuda_device)
-    out = ops.pospool_fwd(f_cl, ds, ds, didx, dnv, dsm, radius, 'avg', query_order=order)
+    out = ops.pospool_fwd(f_cl, ds, ds, didx, dnv, dsm, radius, 'avg', query_order=order, idx_by_support=dbys)
     np.testing.assert_allclose(out.cpu().numpy().transpose(0, 2, 1), ref.detach().numpy(), **FWD)
     rowptr, entries = ops.build_inverse_map(didx, N)
-    gf = ops.pospool_bwd(g_cl, ds, ds, rowptr, entries, dnv, dsm, N, ns, radius, 'avg', idx=didx, support_order=order)
+    gf = ops.pospool_bwd(g_cl, ds, ds, rowptr, entries, dnv, dsm, N, ns, radius, 'avg', support_order=order)
     np.testing.assert_allclose(gf.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
 
 
@@ -123,8 +143,8 @@ def test_staged_pospool_far_from_the_origin(cuda_device, oracle):
     targs = [torch.from_numpy(np.ascontiguousarray(a)) for a in (pts, pts, mask, idx, msk)]
     ref = agg.pospool(tf, *targs, radius, 'avg')
     ds, dsm = dev(pts, cuda_device), dev(mask, cuda_device)
-    didx, dmsk, dnv = ops.ball_query(ds, ds, dsm, dsm, radius, ns, want_nvalid=True)
+    didx, dmsk, dnv, dbys = ops.ball_query(ds, ds, dsm, dsm, radius, ns, want_nvalid=True, want_by_support=True)
     out = ops.pospool_fwd(dev(f.transpose(0, 2, 1), cuda_device), ds, ds, didx, dnv, dsm, radius, 'avg',
-                          query_order=ops.spatial_order(ds))
+                          query_order=ops.spatial_order(ds), idx_by_support=dbys)
     # coordinates ~5 carry an absolute rounding of 5e-7, i.e. ~2e-5 of radius: the reference's own fp32 result has it too
     np.testing.assert_allclose(out.cpu().numpy().transpose(0, 2, 1), ref.detach().numpy(), rtol=1e-5, atol=1e-5)

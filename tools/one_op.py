@@ -9,16 +9,19 @@ C = int(sys.argv[3]) if len(sys.argv) > 3 else 72
 dev = torch.device("cuda:0")
 B, N = 16, 8192
 pts, mask, feats, offs = [torch.from_numpy(a).to(dev) for a in synthetic.make_batch(1, B, N)]
-idx, msk, nv = ops.ball_query(pts, pts, mask, mask, 0.025, 52, want_nvalid=True)
+idx, msk, nv, bys = ops.ball_query(pts, pts, mask, mask, 0.025, 52, want_nvalid=True, want_by_support=True)
 f = torch.randn(B, N, C, device=dev)
 kp = torch.randn(15, 3, device=dev) * 0.006; w = torch.randn(15, C, device=dev)
 rowptr, entries = ops.build_inverse_map(idx, N)
+order = ops.spatial_order(pts)
 torch.cuda.synchronize()
 for _ in range(n):
     if op == "ball_query": ops.ball_query(pts, pts, mask, mask, 0.025, 52)
     elif op == "inverse_map": ops.build_inverse_map(idx, N)
     elif op == "pospool_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg')
     elif op == "pospool_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg')
+    elif op == "pospool_tiles_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys)
+    elif op == "pospool_tiles_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg', support_order=order)
     elif op == "pseudogrid_fwd": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 0)
     elif op == "pseudogrid_fwd_tc": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 1)
     elif op == "pseudogrid_bwd": ops.pseudogrid_bwd(f, f, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 0)

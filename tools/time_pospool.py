@@ -42,18 +42,18 @@ def main():
     for lq, ls, r, ns, C in shapes:
         (q, qm), (s, sm) = levels[lq], levels[ls]
         M, N = q.shape[1], s.shape[1]
-        idx, msk, nv = ops.ball_query(q, s, qm, sm, r, ns, want_nvalid=True)
+        idx, msk, nv, bys = ops.ball_query(q, s, qm, sm, r, ns, want_nvalid=True, want_by_support=True)
         rowptr, entries = ops.build_inverse_map(idx, N)
         oq, os_ = ops.spatial_order(q), ops.spatial_order(s)
         f = torch.randn(B, N, C, device=dev)
         g = torch.randn(B, M, C, device=dev)
         t = {}
         t["fwd gather"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg'))
-        t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq))
+        t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys))
         t["bwd gather"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg'))
-        t["bwd tiles"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg', idx=idx, support_order=os_))
+        t["bwd tiles"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg', support_order=os_))
         a = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg')
-        b = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq)
+        b = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys)
         err = ((a - b).abs().max() / a.abs().max()).item()
         print(f"M={M:5d} N={N:5d} ns={ns} C={C:4d}: " + "  ".join(f"{k} {v:7.1f} us" for k, v in t.items()) + f"   max rel diff {err:.1e}", flush=True)
 
