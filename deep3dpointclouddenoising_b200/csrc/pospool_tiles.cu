@@ -31,7 +31,7 @@ namespace {
 using namespace umma;
 
 constexpr int kTQ = 128;          // owner rows per CTA = MMA M = TMEM lanes
-constexpr int kThreads = 256;     // warps 0-3 fill A (thread = owner row), warps 4-7 start converting, 6-7 also select rows
+constexpr int kThreads = 384;     // warps 0-3 fill A (thread = owner row), the others start converting, the last two also select rows
 constexpr int kKC = 64;           // source rows per chunk (4 K-steps of 16)
 constexpr int kCB = 72;           // channels per CTA (multiple of 24: 8-channel groups and the c mod 3 phase line up)
 constexpr int kMaxPoints = 16384; // the source bitmap lives in shared memory
@@ -125,9 +125,9 @@ pospool_tiles_kernel(const TileArgs a) {
   int* sSrcId = reinterpret_cast<int*>(smem + L.src_id);           // [2][kKC]
   float* sSrcW = reinterpret_cast<float*>(smem + L.src_w);         // [2][kKC][3]
   float* sSrcScale = reinterpret_cast<float*>(smem + L.src_scale); // [2][kKC]
-  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);    // [0..8] scan, [12..14] centre sums x4 at [16..31], [9..10] task counters
-  float* sCtr = reinterpret_cast<float*>(smem + L.scan) + 16;      // 4 warps x (x, y, z)
-  int* sTask = reinterpret_cast<int*>(smem + L.scan) + 9;
+  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);    // [0..15] warp partials, [16] total
+  int* sTask = reinterpret_cast<int*>(smem + L.scan) + 17;         // [17..18] conversion task counters of the two parities
+  float* sCtr = reinterpret_cast<float*>(smem + L.scan) + 20;      // [20..31] 4 warps x (x, y, z) centre sums
   const unsigned bar_stage = smem_u32(smem + L.bars), bar_mma = bar_stage + 8, tmem_slot = bar_stage + 16;
 
   const float* own_xyz = (kBackward ? a.support_xyz : a.query_xyz) + (size_t)b * n_own * 3;
@@ -139,7 +139,7 @@ pospool_tiles_kernel(const TileArgs a) {
 
   // ---- P0: owners, barriers, TMEM ---------------------------------------------------------------------------------
   if (warp == 4) tmem_alloc(tmem_slot, (unsigned)L.tmem_cols);
-  if (tid == 160) {
+  if (tid == 160) {  // a warp that does not allocate TMEM
     mbar_init(bar_stage, 1);
     mbar_init(bar_mma, 1);
     mbar_init_fence();
@@ -194,9 +194,7 @@ pospool_tiles_kernel(const TileArgs a) {
         const int packed = a.entries[e];
         const int q = packed >> 8, k = packed & 255;
         const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
-        const bool valid = k < neff;
-        if (valid) atomicOr(&sBitmap[q >> 5], 1u << (q & 31));
-        a.rank_scratch[e] = valid ? q : -1;
+        if (k < neff) atomicOr(&sBitmap[q >> 5], 1u << (q & 31));
       }
     }
   } else {
@@ -259,14 +257,14 @@ pospool_tiles_kernel(const TileArgs a) {
         if (lane >= o) vi += up;
       }
       if (lane < kThreads / 32) sScan[lane] = vi - v;
-      if (lane == 31) sScan[8] = vi;
+      if (lane == 31) sScan[16] = vi;
     }
     __syncthreads();
     const unsigned base = sScan[warp] + incl - sum;
     if (w0 < L.W) sPrefix[w0] = base;
     if (w0 + 1 < L.W) sPrefix[w0 + 1] = base + p0;
   }
-  const int U = (int)sScan[8];
+  const int U = (int)sScan[16];
   __syncthreads();
   // source id -> rank inside the union (ranks ascend along every row's list: the union is ordered by index)
   if (kBackward) {
@@ -274,8 +272,12 @@ pospool_tiles_kernel(const TileArgs a) {
       const size_t srow = (size_t)b * a.N + sOwnerId[r];
       const int beg = a.rowptr[srow], end = a.rowptr[srow + 1];
       for (int e = beg + lane; e < end; e += 32) {
-        const int q = a.rank_scratch[e];
-        if (q >= 0) a.rank_scratch[e] = (int)(sPrefix[q >> 5] + __popc(sBitmap[q >> 5] & ((1u << (q & 31)) - 1u)));
+        // recomputed from the entry (not read back from the scratch): the CTAs of the other channel blocks write the
+        // very same values to the same scratch, so the race between them is benign
+        const int packed = a.entries[e];
+        const int q = packed >> 8, k = packed & 255;
+        const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
+        a.rank_scratch[e] = k < neff ? (int)(sPrefix[q >> 5] + __popc(sBitmap[q >> 5] & ((1u << (q & 31)) - 1u))) : -1;
       }
     }
   } else {
@@ -292,7 +294,7 @@ pospool_tiles_kernel(const TileArgs a) {
 
   // rows of chunk j -> src buffers [j & 1], bulk copies into the staging buffer (warps 6-7, one row per thread)
   auto select_and_issue = [&](int j) {
-    const int t = tid - 192, pb = j & 1;
+    const int t = tid - (kThreads - 64), pb = j & 1;
     const int r = j * kKC + t;
     int src = -1;
     if (r < U) {
@@ -318,8 +320,8 @@ pospool_tiles_kernel(const TileArgs a) {
   };
 
   // staged fp32 row piece -> 3 bf16 planes of X and 3 of w * X, MN-major operand layout; task = (row, 8 channels)
-  auto convert = [&](int task, int rows16, int pb) {
-    const int u = task % rows16, g = task / rows16;
+  auto convert = [&](int task, int pb) {
+    const int u = task & (kKC - 1), g = task >> 6;
     unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
     unsigned hx[3][4], hy[3][4];
     if (sSrcId[pb * kKC + u] < 0) {
@@ -356,7 +358,7 @@ pospool_tiles_kernel(const TileArgs a) {
   };
 
   // ---- chunks of 64 union rows ---------------------------------------------------------------------------------
-  if (n_chunks > 0 && warp >= 6) select_and_issue(0);
+  if (n_chunks > 0 && tid >= kThreads - 64) select_and_issue(0);
   // A-build cursor of this thread's row
   int cur = 0, cur_end = 0, row_info = 0;
   const int* prow = nullptr;  // forward, padded rows only: the list with the distance ranks
@@ -415,13 +417,13 @@ pospool_tiles_kernel(const TileArgs a) {
     // staged rows -> operand planes: every warp takes 32 tasks at a time (the A warps join when their rows are done)
     mbar_wait(bar_stage, (unsigned)(j & 1));
     {
-      const int rows16 = ksteps * 16, n_tasks = rows16 * n_groups;
+      const int rows16 = ksteps * 16, n_tasks = kKC * n_groups;  // task = (8-channel group, row): 32 rows per grab
       for (;;) {
         int base = 0;
         if (lane == 0) base = atomicAdd(&sTask[pb], 32);
         base = __shfl_sync(D3D_FULL_MASK, base, 0);
         if (base >= n_tasks) break;
-        if (base + lane < n_tasks) convert(base + lane, rows16, pb);
+        if ((base & (kKC - 1)) < rows16) convert(base + lane, pb);  // warp-uniform: rows beyond the last K-step are not read
       }
     }
     fence_async_smem();
@@ -444,7 +446,7 @@ pospool_tiles_kernel(const TileArgs a) {
       mma_commit(bar_mma);
     }
     // the staging buffer is free (all conversions ended before the barrier): next chunk's rows fly during the MMAs
-    if (warp >= 6 && j + 1 < n_chunks) select_and_issue(j + 1);
+    if (tid >= kThreads - 64 && j + 1 < n_chunks) select_and_issue(j + 1);
   }
 
   // ---- epilogue: thread = owner row (TMEM lane); the two warp groups split the 16-column pieces --------------------
@@ -458,7 +460,7 @@ pospool_tiles_kernel(const TileArgs a) {
     const float rcx = sOwnerXyz[3 * t] - ctr_x, rcy = sOwnerXyz[3 * t + 1] - ctr_y, rcz = sOwnerXyz[3 * t + 2] - ctr_z;
     const float rho = sOwnerRho[t];
     float* orow = a.out + ((size_t)b * n_own + (own >= 0 ? own : 0)) * a.C + c0;
-    for (int ch = warp >> 2; ch * 16 < cbn; ch += 2) {
+    for (int ch = warp >> 2; ch * 16 < cbn; ch += kThreads / 128) {
       unsigned y1[16], y2[16];
       if (n_chunks > 0) {
         const unsigned taddr = tmem_base + ((unsigned)(lq * 32) << 16) + (unsigned)(ch * 16);

@@ -62,8 +62,10 @@ class PosPoolFunction(Function):
     @staticmethod
     def forward(ctx, features, query_xyz, support_xyz, query_mask, nbr, radius, reduction):
         feat_cl, ctx.in_cl = _rows(features), is_channel_last(features)
+        staged = runtime.staged_tiles == 'always' or (runtime.staged_tiles and query_xyz.shape[1] == support_xyz.shape[1])
         out_cl = ops.pospool_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, radius, reduction,
-                                 query_order=_neighbors.spatial_order(query_xyz), idx_by_support=nbr.by_support)
+                                 query_order=_neighbors.spatial_order(query_xyz) if staged else None,
+                                 idx_by_support=nbr.by_support)
         ctx.nbr, ctx.radius, ctx.reduction = nbr, radius, reduction
         ctx.save_for_backward(query_xyz, support_xyz, query_mask)
         return _logical(out_cl, runtime.channel_last)
@@ -76,7 +78,7 @@ class PosPoolFunction(Function):
         g_cl = _rows(grad_out)
         gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,
                                 nbr.nsample, ctx.radius, ctx.reduction,
-                                support_order=_neighbors.spatial_order(support_xyz))
+                                support_order=_neighbors.spatial_order(support_xyz) if runtime.staged_tiles_backward else None)
         return _logical(gf_cl, ctx.in_cl), None, None, None, None, None, None
 
 

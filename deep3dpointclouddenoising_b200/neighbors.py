@@ -199,7 +199,7 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr):
                 lists.append(ball_neighbors(sx, px, sm, pm, r_in, ns_in))
                 lists.append(ball_neighbors(sx, sx, sm, sm, r_out, ns_out))
                 levels.append((sx, sm))
-            for lx, _ in levels:
+            for lx, _ in levels:  # every level runs a self query (PosPool forward, staged tiles)
                 spatial_order(lx)
             ups = [nearest_neighbors(levels[k - 1][0], levels[k][0], levels[k - 1][1], levels[k][1])
                    for k in range(len(levels) - 1, 0, -1)]

@@ -82,10 +82,14 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   grads_in_place: backward kernels ADD parameter gradients straight into existing .grad buffers and return None to
 #     autograd (no per-parameter accumulation kernels).  Only valid when nothing hooks the gradients (no DDP reducer):
 #     distributed.FlatParameters-style training loops switch it on, the default is off.
-#   staged_tiles: PosPool runs as the staged-tile tensor-core kernel (csrc/pospool_tiles.cu: 128 spatially adjacent rows
-#     per CTA, cp.async.bulk staging of the neighbour-row union, tcgen05 contraction) instead of the per-query gather.
+#   staged_tiles: PosPool forward runs as the staged-tile tensor-core kernel (csrc/pospool_tiles.cu: 128 spatially
+#     adjacent rows per CTA, cp.async.bulk staging of the neighbour-row union, tcgen05 contraction) where it is the
+#     faster one: self queries (M == N; measured on B200: 189 vs 268 us at the first level, tools/time_pospool.py).
+#     'always' forces it for every shape, False restores the per-query gather kernel everywhere.
+#   staged_tiles_backward: same for the backward pass (measured slower than the segmented reduction: off).
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
-                    "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True})
+                    "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
+                    "staged_tiles_backward": False})
 
 
 def reset_config():

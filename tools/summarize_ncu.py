@@ -13,7 +13,8 @@ KEEP = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tensor.sum", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+        "sm__inst_executed_pipe_tensor.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]
 
 
 def main(rep, dst, command, reading):
