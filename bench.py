@@ -39,7 +39,7 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--operator", default="pospool", choices=["pospool", "pseudo_grid"])
@@ -47,6 +47,9 @@ def parse():
     p.add_argument("--batch", type=int, default=BATCH)
     p.add_argument("--num-points", type=int, default=NUM_POINTS)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-extras", action="store_true",
+                   help="skip the other BASELINE configs (PseudoGrid step, 100k pyramid, 1M-point inference) and the "
+                        "reference-GPU-path timing that the default 1-GPU run appends under 'extra'")
     p.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                    help="replay the whole training step as one CUDA graph (auto: on)")
     return p.parse_args()
@@ -131,6 +134,21 @@ def algorithmic_bytes(op, s):
         return 4 * B * C * M + 4 * B * M * ns + 4 * B * N + 12 * B * (M + N) + 4 * B * C * N
     if op in ("nearest_gather_fwd", "nearest_gather_bwd"):
         return 4 * B * C * (M + N) + 4 * B * M
+    R = s.get("R", 0)
+    if op == "bn_act_cl_fwd":   # two passes over x (statistics, apply) + y out (+ residual in): minimum of a standalone BN
+        return 4 * R * C * (3 + s.get("res", 0))
+    if op == "bn_act_cl_bwd":   # dy and x twice (reduce, apply) + dx out (+ y in for the ReLU mask, + dres out)
+        return 4 * R * C * (5 + s.get("y", 0) + s.get("res", 0))
+    return 0
+
+
+def algorithmic_flops(op, s):
+    """1x1 convolutions as GEMMs: forward 2 R Cin Cout; backward = data gradient + weight gradient."""
+    R, ci, co = s.get("R", 0), s.get("Cin", 0), s.get("Cout", 0)
+    if op == "conv1x1_fwd":
+        return 2 * R * ci * co
+    if op == "conv1x1_bwd":
+        return 4 * R * ci * co
     return 0
 
 
@@ -170,6 +188,12 @@ class OpTimer:
                 return dict(B=t[0].shape[0], N=t[0].shape[1], C=t[0].shape[2], M=t[1].shape[1])
             if name == "nearest_gather_bwd":
                 return dict(B=t[0].shape[0], M=t[0].shape[1], C=t[0].shape[2], N=int(args[3]))
+            if name == "bn_act_cl_fwd":
+                x = args[0]
+                return dict(R=x.numel() // x.shape[-1], C=x.shape[-1], res=0 if args[1] is None else 1)
+            if name == "bn_act_cl_bwd":
+                x = args[0]
+                return dict(R=x.numel() // x.shape[-1], C=x.shape[-1], y=0 if args[2] is None else 1, res=1 if args[9] else 0)
         except Exception:
             pass
         return {}
@@ -177,7 +201,8 @@ class OpTimer:
     def __enter__(self):
         names = ["ball_query", "nearest_query", "grid_subsample", "build_inverse_map", "cm_to_cl", "cl_to_cm",
                  "pospool_fwd", "pospool_bwd", "pseudogrid_fwd", "pseudogrid_bwd", "gather_max_fwd", "gather_max_bwd",
-                 "nearest_gather_fwd", "nearest_gather_bwd", "group_points", "group_points_grad"]
+                 "nearest_gather_fwd", "nearest_gather_bwd", "group_points", "group_points_grad", "spatial_order",
+                 "bn_act_cl_fwd", "bn_act_cl_bwd"]
         for n in names:
             fn = getattr(self.ops, n)
             self.saved[n] = fn
@@ -191,11 +216,38 @@ class OpTimer:
                 return out
 
             setattr(self.ops, n, wrapped)
+        # the 1x1 convolutions (row-major GEMMs, models/blocks.py): forward / backward of the two autograd Functions
+        from deep3dpointclouddenoising_b200.models import blocks
+        self.conv_saved = []
+        for cls in (blocks.PointwiseConvRows, blocks.PointwiseConvCatRows):
+            for meth, tag in (("forward", "conv1x1_fwd"), ("backward", "conv1x1_bwd")):
+                fn = getattr(cls, meth)
+                self.conv_saved.append((cls, meth, fn))
+
+                def timed(ctx, *a, _fn=fn, _tag=tag, _cat=cls is blocks.PointwiseConvCatRows, _fwd=meth == "forward"):
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    out = _fn(ctx, *a)
+                    e.record()
+                    if _fwd:
+                        w = a[0] if _cat else a[1]
+                        rows = a[2:] if _cat else a[:1]
+                    else:
+                        saved = ctx.saved_tensors
+                        w = saved[0] if _cat else saved[1]
+                        rows = saved[1:] if _cat else saved[:1]
+                    shape = dict(R=rows[0].numel() // rows[0].shape[-1], Cin=sum(r.shape[-1] for r in rows), Cout=w.shape[0])
+                    self.records.append((_tag, shape, s, e))
+                    return out
+
+                setattr(cls, meth, staticmethod(timed))
         return self
 
     def __exit__(self, *exc):
         for n, fn in self.saved.items():
             setattr(self.ops, n, fn)
+        for cls, meth, fn in self.conv_saved:
+            setattr(cls, meth, staticmethod(fn))
 
     def summary(self, n_steps):
         torch.cuda.synchronize()
@@ -209,6 +261,7 @@ class OpTimer:
             d["ms_per_call"] = d["ms"] / d["calls"]
             d["ms_per_step"] = d["ms"] / n_steps
             d["bytes_per_call"] = algorithmic_bytes(d["op"], d["shape"])
+            d["flops_per_call"] = algorithmic_flops(d["op"], d["shape"])
         return per
 
 
@@ -247,13 +300,17 @@ def run_reference(args):
     from deep3dpointclouddenoising_b200 import synthetic
     cores = os.cpu_count() or 1
     total = args.steps + args.warmup
-    # one 8192-point patch costs ~13 s on 8 cores; keep the whole run within a few minutes
-    num_points, patches = args.num_points, 1
+    # the GPU arm's batch when the host can afford it (one 16 x 8192 step costs 5-10 s on 16 cores), else one patch per
+    # step (the metric is per point and patches are independent; BatchNorm statistics are then per patch);
+    # the whole run stays within a few minutes
+    num_points = args.num_points
     budget_s = 240.0
     step, kind, how = cpu_step_fn(args.operator, num_points)
     t0 = time.time()
-    step(synthetic.make_batch(999, patches, num_points))
-    probe = time.time() - t0
+    step(synthetic.make_batch(999, 1, num_points))
+    probe1 = time.time() - t0
+    patches = args.batch if probe1 * args.batch * 3 <= budget_s else 1
+    probe = probe1 * patches
     steps, warm = args.steps, args.warmup
     if probe * total > budget_s:  # shrink what a "step" executes, never the patch geometry
         warm = min(warm, 1)
@@ -275,6 +332,84 @@ def run_reference(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the other BASELINE configs and the reference's GPU path, appended to the same JSON line under "extra"
+# ------------------------------------------------------------------------------------------------------------
+def reference_gpu_step(args, dev, batch):
+    """The reference's own GPU path on this B200 (oracle/gpu_reference.py): its CUDA kernels rebuilt for sm_100a, its
+    eager aggregation, stock cuDNN / ATen modules — one full training step at the bench batch."""
+    from oracle import cuda_ref, gpu_reference
+    from deep3dpointclouddenoising_b200.utils import config as cfgmod
+    if not cuda_ref.available():
+        return {"unavailable": "oracle/_ref/libref_cuda.so did not travel (built where /root/reference exists)"}
+    rt = cfgmod.runtime
+    saved = dict(rt)
+    rt.fused_batchnorm, rt.channel_last, rt.prefetch_neighbors, rt.grads_in_place = False, False, False, False
+    try:
+        model, criterion, cfg = build_model(args.operator, args.num_points)
+        model = model.to(dev)
+        step = gpu_reference.make_step(model, criterion, cfg.base_learning_rate, cfg.weight_decay)
+        torch.cuda.reset_peak_memory_stats(dev)
+        step(*batch)  # warm-up (cuDNN autotune, allocator)
+        torch.cuda.synchronize()
+        n = 2
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            step(*batch)
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / n
+        B, N = batch[0].shape[0], batch[0].shape[1]
+        out = {"value": B * N / (ms / 1e3), "unit": UNIT, "ms_per_step": round(ms, 2), "steps": n, "batch": B,
+               "num_points": N, "peak_memory_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+               "what": "reference CUDA kernels (unmodified, rebuilt for sm_100a: one ball query per call, materialised "
+                       "gathers, atomicAdd scatter) + the reference's eager PyTorch aggregation and stock Conv1d / "
+                       "BatchNorm1d modules (TF32 convolutions), Adam; Python glue = the oracle port of the reference's "
+                       "call sequence (oracle/gpu_reference.py)"}
+        del model, step
+        return out
+    finally:
+        for k, v in saved.items():
+            rt[k] = v
+        torch.cuda.empty_cache()
+
+
+def run_extras(args, dev, batch):
+    extra = {}
+    try:
+        extra["reference_gpu"] = reference_gpu_step(args, dev, batch)
+    except Exception as e:  # never lose the headline line to an extra
+        extra["reference_gpu"] = {"error": f"{type(e).__name__}: {e}"}
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import pyramid_100k
+        extra["config1_pyramid_100k"] = pyramid_100k.run(dev, n_rep=5, cpu=True, single_thread=False)
+    except Exception as e:
+        extra["config1_pyramid_100k"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        import denoise_1m
+        extra["config5_inference_1m"] = denoise_1m.run(dev, 1_000_000, 8192, cpu=True)
+    except Exception as e:
+        extra["config5_inference_1m"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    if args.operator == "pospool":  # BASELINE config 3: the PseudoGrid step, both arithmetic modes, in a process of its own
+        for prec in ("bf16", "fp32"):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--operator", "pseudo_grid",
+                                    "--pseudo-grid-precision", prec, "--steps", "30", "--warmup", "5", "--no-extras",
+                                    "--no-cpu-baseline", "--batch", str(args.batch), "--num-points", str(args.num_points)],
+                                   capture_output=True, text=True, timeout=400)
+                line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+                extra[f"config3_pseudogrid_{prec}"] = {
+                    "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "steps": line["steps"],
+                    "e2e": line["e2e"]["value"], "workload": line["config"]["workload"],
+                    "top_kernels": dict(list(line["families"].items())[:4])}
+            except Exception as e:
+                extra[f"config3_pseudogrid_{prec}"] = {"error": f"{type(e).__name__}: {e}"}
+    return extra
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -413,7 +548,7 @@ def main():
 
     # ---- instrumented pass: where the step's device time goes, and the roofline of the dominant kernel ----
     # (every rank runs these steps — they contain the gradient all-reduce — only rank 0 reports them)
-    kernels, roofline = None, None
+    kernels, roofline, families = None, None, None
     n_inst = 3
     for s in range(2):  # eager again after graph replay: let the caching allocator settle before timing single ops
         train_step(*resident[s % n_host])
@@ -423,38 +558,68 @@ def main():
             train_step(*resident[s % n_host])
         per = timer.summary(n_inst)
     barrier()
+    rooflines = None
     if rank == 0:
         step_ms = ms / args.steps
-        kernels = {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / n_inst,
-                       "gbs": round(v["bytes_per_call"] / 1e6 / v["ms_per_call"], 1) if v["ms_per_call"] > 0 else None}
-                   for k, v in sorted(per.items(), key=lambda kv: -kv[1]["ms"])[:12]}
-        ours_ms = sum(v["ms_per_step"] for v in per.values())
-        top_key, top = max(per.items(), key=lambda kv: kv[1]["ms"])
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
-            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            pk = json.load(open(peaks_path))
+            peak, which = float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            # kind::tf32 runs at half the bf16 rate: half the measured sustained bf16 figure (the GEMMs run inside a long step)
+            tf32_peak, tf32_which = float(pk["bf16_tflops_sustained"]) / 2, "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32)"
         else:
             peak, which = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-        achieved = top["bytes_per_call"] / 1e6 / top["ms_per_call"]
-        # dram bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/), if there is one
-        traffic = None
+            tf32_peak, tf32_which = 1400.0 / 2, "fallback sustained bf16 / 2 (tf32)"
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top_key)
+        traffic_table = json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+        def roof(key, v):
+            if v["flops_per_call"]:
+                ach = v["flops_per_call"] / 1e9 / v["ms_per_call"]  # TFLOP/s
+                r = {"bound": "tensor", "achieved": round(ach, 2), "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": round(ach / tf32_peak, 4), "peak_source": tf32_which,
+                     "algorithmic_flops_per_launch": v["flops_per_call"]}
+            else:
+                ach = v["bytes_per_call"] / 1e6 / v["ms_per_call"]  # GB/s
+                r = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                     "peak_source": which, "algorithmic_bytes_per_launch": v["bytes_per_call"]}
+            r.update({"kernel": key, "traffic": traffic_table.get(key), "ms_per_launch": round(v["ms_per_call"], 4),
+                      "launches_per_step": v["calls"] / n_inst, "share_of_step": round(v["ms_per_step"] / step_ms, 4)})
+            return r
+
+        ranked = sorted(per.items(), key=lambda kv: -kv[1]["ms"])
+        kernels = {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / n_inst,
+                       "gbs": round(v["bytes_per_call"] / 1e6 / v["ms_per_call"], 1) if v["ms_per_call"] > 0 and v["bytes_per_call"] else None,
+                       "tflops": round(v["flops_per_call"] / 1e9 / v["ms_per_call"], 2) if v["flops_per_call"] else None}
+                   for k, v in ranked[:16]}
+        ours_ms = sum(v["ms_per_step"] for v in per.values() if not v["op"].startswith("conv1x1"))
+        # aggregate by op family as well: the step launches the same kernel at five resolutions
+        fam = {}
+        for k, v in per.items():
+            f = fam.setdefault(v["op"], {"ms_per_step": 0.0, "bytes": 0.0, "flops": 0.0, "launches": 0.0})
+            f["ms_per_step"] += v["ms_per_step"]
+            f["bytes"] += v["bytes_per_call"] * v["calls"] / n_inst
+            f["flops"] += v["flops_per_call"] * v["calls"] / n_inst
+            f["launches"] += v["calls"] / n_inst
+        families = {k: {"ms_per_step": round(f["ms_per_step"], 4), "launches_per_step": f["launches"],
+                        "share_of_step": round(f["ms_per_step"] / step_ms, 4),
+                        "gbs": round(f["bytes"] / 1e6 / f["ms_per_step"], 1) if f["bytes"] and f["ms_per_step"] > 0 else None,
+                        "frac_of_hbm_peak": round(f["bytes"] / 1e6 / f["ms_per_step"] / peak, 4) if f["bytes"] and f["ms_per_step"] > 0 else None,
+                        "tflops": round(f["flops"] / 1e9 / f["ms_per_step"], 2) if f["flops"] and f["ms_per_step"] > 0 else None,
+                        "frac_of_tf32_peak": round(f["flops"] / 1e9 / f["ms_per_step"] / tf32_peak, 4) if f["flops"] and f["ms_per_step"] > 0 else None}
+                    for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms_per_step"])}
+        rooflines = [roof(k, v) for k, v in ranked[:5] if v["ms_per_call"] > 0]
+        roofline = dict(rooflines[0])
+        top_key, top = ranked[0]
         sh = top["shape"]
-        gather = None
         if top["op"] in ("pospool_fwd", "pospool_bwd", "pseudogrid_fwd", "pseudogrid_bwd", "gather_max_fwd", "gather_max_bwd"):
             gb = 4 * sh["B"] * sh["M"] * max(sh.get("ns", 0), 1) * sh["C"]  # rows gathered through L2 (never materialised)
-            gather = {"l2_gather_bytes_per_launch": gb, "l2_gather_gbs": round(gb / 1e6 / top["ms_per_call"], 1)}
-        roofline = {"bound": "hbm", "kernel": top_key, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": which,
-                    "algorithmic_bytes_per_launch": top["bytes_per_call"], "ms_per_launch": round(top["ms_per_call"], 4),
-                    "share_of_step": round(top["ms_per_step"] / step_ms, 4),
-                    "our_kernels_share_of_step": round(ours_ms / step_ms, 4), "gather": gather,
-                    "note": "algorithmic bytes = compulsory HBM traffic (features + idx + xyz in, result out, DESIGN.md §3); "
-                            "the aggregation kernels are bound by the register write-back of the L2->SM gather of B*M*ns*C*4 "
-                            "bytes (reported under 'gather'; ncu: profiles/r01_pospool_fwd_ncu.md), the ball query by "
-                            "instruction issue (ordered prefix scan, profiles/r01_ball_query_v3_ncu.md)"}
+            roofline["gather"] = {"l2_gather_bytes_per_launch": gb, "l2_gather_gbs": round(gb / 1e6 / top["ms_per_call"], 1)}
+        roofline["our_kernels_share_of_step"] = round(ours_ms / step_ms, 4)
+        roofline["note"] = ("dominant op of the step by device time (CUDA events around every C-ABI call, every fused BatchNorm "
+                            "and every 1x1-convolution GEMM of an instrumented eager pass); algorithmic bytes = compulsory HBM "
+                            "traffic (DESIGN.md §3); 'rooflines' lists the top five, 'families' sums each op over the five "
+                            "resolutions; ncu evidence under profiles/")
 
     # ---- neighbour build alone (BASELINE.json metric, second figure): the full 5-level pyramid of one batch ----
     neighbor_build = None
@@ -498,12 +663,16 @@ def main():
         cores = os.cpu_count() or 1
         step_cpu, kind, how = cpu_step_fn(args.operator, N)
         t, n_cpu = time.time(), 0
-        while n_cpu < 64 and (time.time() - t < 12.0 or n_cpu < 2):  # ~10-30 s of CPU work
-            step_cpu(synthetic.make_batch(4242 + n_cpu, 1, N))
+        while n_cpu < 64 and (time.time() - t < 12.0 or n_cpu < 2):  # ~10-30 s of CPU work, at the GPU arm's batch
+            step_cpu(synthetic.make_batch(4242 + n_cpu, B, N))
             n_cpu += 1
         dt = time.time() - t
-        cpu_baseline = {"value": n_cpu * N / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": f"{n_cpu} steps of 1 x {N}-point patch fwd+bwd+Adam ({how}), {dt:.1f} s on {cores} host threads"}
+        cpu_baseline = {"value": n_cpu * B * N / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{n_cpu} steps of {B} x {N}-point patches fwd+bwd+Adam ({how}), {dt:.1f} s on {cores} host threads"}
+
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extra = run_extras(args, dev, resident[0])
 
     if rank == 0:
         pts_per_step = world * B * N
@@ -521,11 +690,14 @@ def main():
                            "several GB) exceeds the 126 MB L2; 4 rotating input batches"},
                 "e2e": {"value": pts_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "kernels": kernels}
+                "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "rooflines": rooflines,
+                "families": families, "kernels": kernels}
         if neighbor_build is not None:
             line["neighbor_build"] = neighbor_build
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         # process-group teardown after captured NCCL collectives can block; every rank is done: leave directly

@@ -62,7 +62,10 @@ class PosPoolFunction(Function):
     @staticmethod
     def forward(ctx, features, query_xyz, support_xyz, query_mask, nbr, radius, reduction):
         feat_cl, ctx.in_cl = _rows(features), is_channel_last(features)
-        staged = runtime.staged_tiles == 'always' or (runtime.staged_tiles and query_xyz.shape[1] == support_xyz.shape[1])
+        # staged tiles: self queries (where they are the faster kernel) with 'avg' (the bilinear split keeps the fp32
+        # parity tolerance of a mean; a plain sum of nsample terms is nsample times larger in absolute terms)
+        staged = runtime.staged_tiles == 'always' or (runtime.staged_tiles and reduction != 'sum'
+                                                      and query_xyz.shape[1] == support_xyz.shape[1])
         out_cl = ops.pospool_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, radius, reduction,
                                  query_order=_neighbors.spatial_order(query_xyz) if staged else None,
                                  idx_by_support=nbr.by_support)

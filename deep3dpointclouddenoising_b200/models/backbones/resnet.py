@@ -67,6 +67,9 @@ class ResNet(nn.Module):
         self.btnk1 = Bottleneck(half, width, bottleneck_ratio, radius, nsamples[0], config)
         # what one forward will ask neighbors.py for, with the very values handed to the modules below (cache keys)
         self._radius0, self._nsample0, self._stages = radius, nsamples[0], []
+        # the staged-tile PosPool kernels need a processing order per level (fused.PosPoolFunction)
+        self._with_order = (config.local_aggregation_type == 'pospool' and config.pospool.position_embedding == 'xyz'
+                            and config.pospool.reduction in ('avg', 'mean'))
         # four strided stages: each halves the resolution (grid cell x2) and doubles radius and width
         for stage in range(4):
             sampleDl *= 2
@@ -87,7 +90,8 @@ class ResNet(nn.Module):
         if runtime.prefetch_neighbors and xyz.is_cuda:
             # the whole pyramid (+ inverse maps when gradients are on) goes to a side stream and overlaps with the
             # convolutions / BatchNorm / aggregations below; consumers wait on per-item events (neighbors.py)
-            _neighbors.prebuild(xyz, mask, self._radius0, self._nsample0, self._stages, torch.is_grad_enabled())
+            _neighbors.prebuild(xyz, mask, self._radius0, self._nsample0, self._stages, torch.is_grad_enabled(),
+                                self._with_order)
         if not end_points:
             end_points = {}
         features = self.conv1(features)

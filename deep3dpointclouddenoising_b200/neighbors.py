@@ -181,7 +181,7 @@ def spatial_order(xyz):
     return cache.get("order", (xyz,), (), build).sync().order
 
 
-def prebuild(xyz, mask, radius, nsample0, stages, with_csr):
+def prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order=True):
     """Enqueues every neighbourhood structure of one U-Net forward on the side stream and fills the cache.
     stages: per strided stage (sample_dl, npoint, radius_in, nsample_in, radius_out, nsample_out) — the very values the
     modules were constructed with (resnet.py), so their cache keys match."""
@@ -192,15 +192,18 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr):
     _building_on_side[0] = True
     try:
         with torch.cuda.stream(side):
+            # in the order the forward pass consumes them (the side stream is in-order: a late item delays its consumer)
             levels, lists = [(xyz, mask)], [ball_neighbors(xyz, xyz, mask, mask, radius, nsample0)]
+            if with_order:  # every level runs a self query (PosPool forward as staged tiles)
+                spatial_order(xyz)
             for sample_dl, npoint, r_in, ns_in, r_out, ns_out in stages:
                 px, pm = levels[-1]
                 sx, sm = grid_subsample(px, pm, npoint, sample_dl)
                 lists.append(ball_neighbors(sx, px, sm, pm, r_in, ns_in))
                 lists.append(ball_neighbors(sx, sx, sm, sm, r_out, ns_out))
+                if with_order:
+                    spatial_order(sx)
                 levels.append((sx, sm))
-            for lx, _ in levels:  # every level runs a self query (PosPool forward, staged tiles)
-                spatial_order(lx)
             ups = [nearest_neighbors(levels[k - 1][0], levels[k][0], levels[k - 1][1], levels[k][1])
                    for k in range(len(levels) - 1, 0, -1)]
             if with_csr:  # in the order backward asks for them: decoder first, then coarse to fine

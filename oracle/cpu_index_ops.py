@@ -193,6 +193,28 @@ class _RefGridSubCPU:
         return out[:k].copy()
 
 
+class _RefNanoflann:
+    """oracle/_ref/libref_nanoflann.so: radius search over the reference's vendored nanoflann.hpp and its PointCloud
+    adaptor (cpp_wrappers/cpp_utils/nanoflann/nanoflann.hpp:1280, cpp_utils/cloud/cloud.h:151-175)."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing (built by `make -C oracle ref` where /root/reference exists)")
+        L = ctypes.CDLL(path)
+        L.ref_nanoflann_radius.argtypes = [_f32p, _c_int, _f32p, _c_int, _c_float, _c_int, _c_int, _i32p, _i32p]
+        L.ref_nanoflann_radius.restype = _c_int
+        self.L = L
+
+    def radius(self, support, query, radius, cap, threads=1):
+        """-> (idx (m, cap) int32 nearest-first, -1 padded; count (m,) neighbours inside the ball)."""
+        s, q = _f32(support), _f32(query)
+        idx = np.empty((q.shape[0], cap), np.int32)
+        cnt = np.empty((q.shape[0],), np.int32)
+        self.L.ref_nanoflann_radius(s, s.shape[0], q, q.shape[0], radius, cap, threads, idx, cnt)
+        return idx, cnt
+
+
 _cache = {}
 
 
@@ -216,3 +238,9 @@ def ref_gridsub_cpu():
     if "gridsub" not in _cache:
         _cache["gridsub"] = _RefGridSubCPU()
     return _cache["gridsub"]
+
+
+def ref_nanoflann():
+    if "nanoflann" not in _cache:
+        _cache["nanoflann"] = _RefNanoflann()
+    return _cache["nanoflann"]

@@ -1,6 +1,8 @@
 """GPU parity, row f2: patch centres, radius patches and vote averaging against the reference's own building blocks
 (its CPU grid_subsampling.cpp through oracle/_ref/libref_gridsub.so when present, sklearn's KDTree — the class the
 reference dataset uses — and numpy vote accumulation as in qualitative_inference_test.py:325-342)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -52,44 +54,58 @@ def test_voxel_barycentres_match_reference_cpu(cuda_device):
 
 
 def test_config0_pyramid_on_100k_cloud(cuda_device):
-    """BASELINE configs[0]: 5-level grid subsampling + radius neighbours of one 100k-point noisy shape.  Every level's
-    barycentres equal the reference's grid_subsampling.cpp bit for bit (as sets: the reference emits hash-map order),
-    and the radius neighbour lists equal sklearn's KDTree.query_radius (the reference's neighbour search on the host)."""
-    from deep3dpointclouddenoising_b200 import inference, ops
+    """BASELINE configs[0] at the geometry BASELINE.md §3 states (tools/pyramid_100k.py): subsampling at
+    dl = 0.0015625 * 2^l, the U-Net's nine radius lists (r = 0.025 * 2^(l-1) strided, 0.025 * 2^l self, nsample nearest)
+    of one 100k-point noisy shape.  Every level's barycentres equal the reference's grid_subsampling.cpp bit for bit (as
+    sets: the reference emits hash-map order); the radius lists equal the reference's vendored nanoflann radiusSearch
+    (oracle/_ref/libref_nanoflann.so) or, where that did not travel, sklearn's KDTree — the reference's host search."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import pyramid_100k as P
+    from deep3dpointclouddenoising_b200 import inference
     from oracle import cpu_index_ops
     pts = _cloud(100_000, 0)
     try:
         ref = cpu_index_ops.ref_gridsub_cpu()
     except (FileNotFoundError, OSError):
         ref = None
+    try:
+        nf = cpu_index_ops.ref_nanoflann()
+    except (FileNotFoundError, OSError):
+        nf = None
     key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
-    cur_gpu, cur_ref = torch.from_numpy(pts).to(cuda_device), pts
-    sizes = []
-    for level in range(5):
-        dl = 0.01 * 2 ** level
-        sub, counts = inference.voxel_barycentres(cur_gpu, dl)
+    levels_np, levels_gpu = [pts], [torch.from_numpy(pts).to(cuda_device)]
+    for l in range(1, 5):
+        dl = P.BASE_DL * 2 ** l
+        sub, counts = inference.voxel_barycentres(levels_gpu[-1], dl)
         got = sub.cpu().numpy()
-        assert int(counts.sum()) == cur_gpu.shape[0]
+        assert int(counts.sum()) == levels_gpu[-1].shape[0]
         if ref is not None:
-            cur_ref = ref.compute(cur_ref, dl)
-            assert np.array_equal(key(got), key(cur_ref)), level
-        radius = 2.5 * dl
-        idx, cnt = ops.radius_patches(sub, sub.contiguous(), radius, 64)
-        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
-        tree = KDTree(got)
-        probe = np.arange(0, len(got), max(len(got) // 300, 1))
-        ref_idx, ref_d = tree.query_radius(got[probe], r=radius, return_distance=True, sort_results=True)
-        for k, p_ in enumerate(probe):
-            assert cnt[p_] == len(ref_idx[k]), (level, p_)
-            take = min(cnt[p_], 64)
-            if not np.array_equal(idx[p_, :take], ref_idx[k][:take]):  # equal-distance groups may be ordered differently
-                d_got = np.linalg.norm(got[idx[p_, :take]].astype(np.float64) - got[p_], axis=1)
-                np.testing.assert_allclose(d_got, ref_d[k][:take], rtol=1e-12, atol=1e-12)
-        sizes.append(len(got))
-        # the next level sums points in input order (fp32): both sides continue from the SAME array, the reference's
-        # own output order when it is available
-        cur_gpu = torch.from_numpy(cur_ref).to(cuda_device) if ref is not None else sub.contiguous()
+            want = ref.compute(levels_np[-1], dl)
+            assert np.array_equal(key(got), key(want)), l
+            got = want  # the next level sums points in input order (fp32): both sides continue from the SAME array
+        levels_np.append(got)
+        levels_gpu.append(torch.from_numpy(got).to(cuda_device))
+    sizes = [len(a) for a in levels_np]
     assert sizes == sorted(sizes, reverse=True) and sizes[-1] >= 1
+    for lq, ls, radius, cap in P.list_specs():
+        q, s_ = levels_np[lq], levels_np[ls]
+        probe = np.arange(0, len(q), max(len(q) // 200, 1))
+        idx, cnt = P.radius_lists(levels_gpu[ls], levels_gpu[lq][torch.from_numpy(probe).to(cuda_device)].contiguous(), radius, cap)
+        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+        if nf is not None:
+            ref_idx, ref_cnt = nf.radius(s_, q[probe], radius, cap, 4)
+        else:
+            ri, _ = KDTree(s_).query_radius(q[probe], r=radius, return_distance=True, sort_results=True)
+            ref_cnt = np.array([len(r) for r in ri])
+            ref_idx = np.stack([np.pad(r[:cap], (0, max(cap - len(r), 0)), constant_values=-1) for r in ri])
+        assert np.abs(cnt - ref_cnt).max() <= 1, (lq, ls)  # a support exactly on the sphere may round either way
+        for k in range(len(probe)):
+            take = min(int(cnt[k]), int(ref_cnt[k]), cap)
+            if not np.array_equal(idx[k, :take], ref_idx[k, :take]):  # equal-distance groups may be ordered differently
+                d_got = np.linalg.norm(s_[idx[k, :take]].astype(np.float64) - q[probe[k]], axis=1)
+                d_ref = np.linalg.norm(s_[ref_idx[k, :take]].astype(np.float64) - q[probe[k]], axis=1)
+                np.testing.assert_allclose(d_got, d_ref, rtol=1e-5, atol=1e-9)
 
 
 def test_radius_patches_match_kdtree(cuda_device):

@@ -147,3 +147,26 @@ def test_maxpool_and_upsample_restatement_match_reference_python(oracle, gold_ag
     np.testing.assert_array_equal(y.detach().numpy(), g["upsample_out"])
     (gf,) = torch.autograd.grad(y, cf, _t(g["upsample_gout"]))
     np.testing.assert_allclose(gf.numpy(), g["upsample_gfeat"], rtol=1e-5, atol=1e-6)
+
+
+def test_nanoflann_harness_matches_brute_force():
+    """oracle/_ref/libref_nanoflann.so (the reference's vendored nanoflann.hpp + PointCloud adaptor): nearest-first radius
+    lists equal a float64 brute force (the CPU neighbour baseline of bench.py / tools/pyramid_100k.py)."""
+    from oracle import cpu_index_ops
+    try:
+        nf = cpu_index_ops.ref_nanoflann()
+    except (FileNotFoundError, OSError):
+        pytest.skip("libref_nanoflann.so not built (no /root/reference at build time)")
+    rng = np.random.default_rng(3)
+    s = rng.uniform(-1, 1, (2000, 3)).astype(np.float32)
+    q = rng.uniform(-1, 1, (150, 3)).astype(np.float32)
+    for threads in (1, 4):
+        idx, cnt = nf.radius(s, q, 0.3, 24, threads)
+        d2 = ((q[:, None, :].astype(np.float64) - s[None].astype(np.float64)) ** 2).sum(-1)
+        for j in range(len(q)):
+            inside = np.nonzero(d2[j] < np.float32(0.3) ** 2)[0]
+            assert abs(cnt[j] - len(inside)) <= 1  # a support exactly on the sphere may round either way in fp32
+            order = inside[np.argsort(d2[j, inside], kind="stable")][:24]
+            got = idx[j][idx[j] >= 0]
+            assert len(got) == min(cnt[j], 24)
+            np.testing.assert_allclose(d2[j, got], d2[j, order[:len(got)]], rtol=1e-5, atol=1e-9)
