@@ -201,9 +201,11 @@ nn_query_kernel(const float* __restrict__ q, int M, const GridParams* __restrict
     // The query (or, when it lies outside the grid box, its projection onto the box, which is never farther from a
     // support than the query itself) is inside the centre cell, so every support of shell r is farther than
     // (r - 1) * cell: once best <= ((r - 1) * cell)^2 no outer shell can win.
+    // Compared in fp64 with a 1e-6 relative margin (like ball_nearest_kernel): an fp32 bound can cut the search one
+    // shell short when the winner sits exactly on a cell boundary.
     if (r >= 1) {
-      const float reach = (float)(r - 1) * p.cell;
-      if (best <= reach * reach) break;
+      const double reach = (double)(r - 1) * (double)p.cell * (1.0 - 1e-6);
+      if ((double)best <= reach * reach) break;
     }
     if (cx - r < 0 && cx + r >= G && cy - r < 0 && cy + r >= G && cz - r < 0 && cz + r >= G) break;  // shell outside the grid
     for (int z = max(cz - r, 0); z <= min(cz + r, G - 1); ++z) {

@@ -157,7 +157,10 @@ class BatchNormActFunction(Function):
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu, counter=None):
         ctx.training, ctx.has_res = training, residual is not None
         ctx.wparam, ctx.bparam = weight, bias  # the Parameter objects (their .grad buffers, see runtime.grads_in_place)
-        ctx.rows = is_channel_last(x) and x.shape[1] % 4 == 0
+        # the channel-last kernels need 16-byte aligned rows and parameters (d3d_bn_act_cl_* reject anything else): a view
+        # at an odd storage offset takes the channel-major kernels instead
+        aligned = all(t is None or t.data_ptr() % 16 == 0 for t in (x, residual, weight, bias))
+        ctx.rows = is_channel_last(x) and x.shape[1] % 4 == 0 and aligned
         ctx.relu_mode = 0 if not relu else (2 if residual is not None else 1)
         if ctx.rows:  # channel-last view in, channel-last view out: no layout change anywhere
             xr = x.permute(0, 2, 1)

@@ -94,6 +94,15 @@ class ResNet(nn.Module):
                                 self._with_order)
         if not end_points:
             end_points = {}
+        try:
+            return self._forward(xyz, mask, features, end_points)
+        finally:
+            # the side-stream work of this forward is joined here — also when the backbone is used without the head and
+            # when the forward raises — so the stream is never left forked (a later graph capture would fail).  The
+            # pyramid is long finished by the time the last stage has run.
+            _neighbors.join()
+
+    def _forward(self, xyz, mask, features, end_points):
         features = self.conv1(features)
         features = self.la1(xyz, xyz, mask, mask, features)
         xyz, mask, features = self.btnk1(xyz, mask, features)

@@ -48,7 +48,15 @@ def _weight_grad(g2, x2, into=None):
     key = (S, g2.device)
     if key not in _ones:
         _ones[key] = torch.ones((1, S), dtype=g2.dtype, device=g2.device)
-    into.view(1, -1).addmm_(_ones[key], partial.view(S, -1))  # the sum over the chunks, accumulated into the buffer
+    # the sum over the chunks, accumulated into the buffer in ONE launch — in full fp32: this call runs inside
+    # _conv_math(), where matmul TF32 follows cudnn.allow_tf32, and TF32 would round every fp32 partial to 10 mantissa
+    # bits before the sum (the out-of-place path sums with partial.sum(0) in fp32)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        into.view(1, -1).addmm_(_ones[key], partial.view(S, -1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
     return None
 
 

@@ -18,17 +18,33 @@ from ... import ops
 
 
 def _nearest_rows(a, b, mask):
-    """b's row nearest to every row of a, per batch element, restricted to the valid prefix: (B, N, 3)."""
+    """b's row nearest to every row of a, per batch element, restricted to the valid prefix: (B, N, 3).
+    d3d_nearest_query follows the reference kernel (masked_nearest_query_gpu.cu:36-43): it stops at the first 0 of the
+    mask and only accepts squared distances below 100; the reference LOSS has neither restriction (boolean mask
+    selection + pytorch3d knn), so both are checked here instead of silently returning a different loss."""
     with torch.no_grad():
         idx, _ = ops.nearest_query(a.detach().contiguous(), b.detach().contiguous(), mask, mask)
-        idx = idx.view(a.shape[0], a.shape[1]).clamp(min=0).long()
+        idx = idx.view(a.shape[0], a.shape[1])
+        valid = mask != 0
+        if bool(((idx < 0) & valid).any()):
+            raise ValueError("chamfer loss: a valid point has no neighbour within squared distance 100 "
+                             "(masked_nearest_query's cap); rescale the clouds to the unit-size convention")
+        idx = idx.clamp(min=0).long()
     return torch.gather(b, 1, idx.unsqueeze(-1).expand(-1, -1, 3))
+
+
+def _check_prefix_mask(mask):
+    """The batched nearest query treats the mask as a valid PREFIX (the dataset guarantees it, offset_dataset.py:671-672)."""
+    m = mask != 0
+    if bool((m[:, 1:] & ~m[:, :-1]).any()):
+        raise ValueError("chamfer loss: mask must be a valid prefix (ones then zeros) for the batched nearest query")
 
 
 def masked_chamfer(clean_points, pred_points, mask, norm_type="L2"):
     """Mean over the batch of chamfer_distance(clean[valid], pred[valid], point_reduction='mean')."""
     if norm_type not in ("L2", "L1"):
         raise ValueError(f"Norm type {norm_type} not implemented")
+    _check_prefix_mask(mask)
     mask_i = mask.int().contiguous()
     w = mask.to(clean_points.dtype)
     total = 0

@@ -46,8 +46,7 @@ class _Produced:
         """Makes the current stream wait for the build if it happened on another stream."""
         ev = self._event
         if ev is not None and torch.cuda.current_stream() != self._stream:
-            torch.cuda.current_stream().wait_event(ev)
-            self._event = None
+            torch.cuda.current_stream().wait_event(ev)  # the event stays: a consumer on yet another stream waits too
         return self
 
 
@@ -76,7 +75,6 @@ class NeighborList(_Produced):
                 self._csr_event.record(self._csr_stream)
         elif self._csr_event is not None and torch.cuda.current_stream() != self._csr_stream:
             torch.cuda.current_stream().wait_event(self._csr_event)
-            self._csr_event = None
         return self._csr
 
 

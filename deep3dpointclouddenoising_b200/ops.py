@@ -342,9 +342,11 @@ _bn_workspaces = {}
 
 
 def _bn_ws(device, C):
-    """Zero-initialised, reused workspace of the split channel reductions (one per device and channel count; the
-    kernels leave the ticket counters zero; all launches of this process go to the current stream)."""
-    key = (device, C)
+    """Zero-initialised, reused workspace of the split channel reductions: one per (device, channel count, STREAM) — two
+    streams running BatchNorm layers of the same width concurrently must not share partial sums and ticket counters.
+    The kernels leave the counters zero.  (During CUDA-graph capture the capturing stream is the key; replays of the
+    graph are ordered among themselves.)"""
+    key = (device, C, torch.cuda.current_stream(device).cuda_stream)
     ws = _bn_workspaces.get(key)
     if ws is None:
         ws = torch.zeros(_lib.load().d3d_bn_act_workspace_bytes(C), dtype=torch.uint8, device=device)
