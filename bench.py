@@ -137,6 +137,8 @@ def algorithmic_bytes(op, s):
     R = s.get("R", 0)
     if op == "bn_act_cl_fwd":   # two passes over x (statistics, apply) + y out (+ residual in): minimum of a standalone BN
         return 4 * R * C * (3 + s.get("res", 0))
+    if op == "bn_from_stats":   # statistics came from the GEMM epilogue: one pass, x in, y out (+ residual in)
+        return 4 * R * C * (2 + s.get("res", 0))
     if op == "bn_act_cl_bwd":   # dy and x twice (reduce, apply) + dx out (+ y in for the ReLU mask, + dres out)
         return 4 * R * C * (5 + s.get("y", 0) + s.get("res", 0))
     return 0
@@ -191,6 +193,9 @@ class OpTimer:
             if name == "bn_act_cl_fwd":
                 x = args[0]
                 return dict(R=x.numel() // x.shape[-1], C=x.shape[-1], res=0 if args[1] is None else 1)
+            if name == "bn_from_stats":
+                x = args[0]
+                return dict(R=x.numel() // x.shape[-1], C=x.shape[-1], res=0 if args[1] is None else 1)
             if name == "bn_act_cl_bwd":
                 x = args[0]
                 return dict(R=x.numel() // x.shape[-1], C=x.shape[-1], y=0 if args[2] is None else 1, res=1 if args[9] else 0)
@@ -202,7 +207,7 @@ class OpTimer:
         names = ["ball_query", "nearest_query", "grid_subsample", "build_inverse_map", "cm_to_cl", "cl_to_cm",
                  "pospool_fwd", "pospool_bwd", "pseudogrid_fwd", "pseudogrid_bwd", "gather_max_fwd", "gather_max_bwd",
                  "nearest_gather_fwd", "nearest_gather_bwd", "group_points", "group_points_grad", "spatial_order",
-                 "bn_act_cl_fwd", "bn_act_cl_bwd"]
+                 "bn_act_cl_fwd", "bn_act_cl_bwd", "bn_from_stats"]
         for n in names:
             fn = getattr(self.ops, n)
             self.saved[n] = fn
@@ -231,7 +236,7 @@ class OpTimer:
                     e.record()
                     if _fwd:
                         w = a[0] if _cat else a[1]
-                        rows = a[2:] if _cat else a[:1]
+                        rows = a[3:] if _cat else a[:1]  # cat: (weight, bias, want_stats, *rows)
                     else:
                         saved = ctx.saved_tensors
                         w = saved[0] if _cat else saved[1]

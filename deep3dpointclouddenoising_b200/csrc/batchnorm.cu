@@ -811,6 +811,22 @@ int d3d_bn_act_cl_fwd(const float* x, const float* residual, const float* gamma,
   return d3d_launch_status();
 }
 
+/* Apply pass alone with statistics that already exist (d3d_bn_finalize from the GEMM epilogue's tile partials):
+ * y = act(gamma * (x - mean) * invstd + beta [+ residual]). */
+int d3d_bn_apply_cl(const float* x, const float* residual, const float* gamma, const float* beta, const float* save_mean,
+                    const float* save_invstd, long long R, int C, int relu, float* y, void* stream) {
+  D3D_REQUIRE(x && y && save_mean && save_invstd);
+  D3D_REQUIRE(R > 0 && C > 0 && C % 4 == 0);
+  D3D_REQUIRE(aligned16(x) && aligned16(residual) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
+              aligned16(save_mean) && aligned16(save_invstd));
+  const ClGeom g = cl_geom(C);
+  const long long apply_threads = ((R + kApplyRows - 1) / kApplyRows) * g.c4;
+  bn_apply_cl_kernel<<<(unsigned)d3d_ceil_div(apply_threads, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, residual, gamma, beta, save_mean, save_invstd, g.c4, R, relu, y);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
 int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* beta,
                       const float* save_mean, const float* save_invstd, long long R, int C, int training, int relu, float* dx,
                       float* dres, float* dgamma, float* dbeta, int accumulate_param_grads, void* ws, size_t ws_bytes,

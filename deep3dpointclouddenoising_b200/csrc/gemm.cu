@@ -1,0 +1,351 @@
+// The 1x1 convolutions of the U-Net as row-major GEMMs on the 5th-generation tensor cores: TMA-fed, tcgen05.mma
+// kind::tf32, accumulator in TMEM, BatchNorm statistics in the epilogue.
+//
+//   ref: u_net_arch/models/backbones/resnet.py:32-45,58-66; models/local_aggregation_operators.py:121-123;
+//        models/heads/multi_dimensional_head.py:40-59  (nn.Conv1d(kernel_size=1, bias=False) -> BatchNorm1d -> ReLU;
+//        cuDNN runs them in TF32 by default, torch.backends.cudnn.allow_tf32)
+//
+//   C[M x N] = A[M x K] . B[N x K]^T        A = activation rows (channel-last), B = conv weight (Cout x Cin), fp32 in / out
+//
+// * operands travel global -> shared with TMA (cp.async.bulk.tensor.2d, 128-byte swizzle: a [rows x 32 floats] box IS the
+//   canonical K-major SWIZZLE_128B operand tile), completion on mbarriers; a 4-stage ring, one producer thread;
+// * one thread issues tcgen05.mma (M = 128, N = column tile <= 144, K = 8 per instruction, 4 per stage), releases stages
+//   with tcgen05.commit; the accumulator lives in TMEM;
+// * four epilogue warps read TMEM (thread = output row), store the rows, and — for a convolution that feeds a BatchNorm —
+//   reduce per-column (count, mean, M2) partials of the tile through shared memory: the BatchNorm statistics pass over
+//   the convolution output (one full read of it) disappears, d3d_bn_finalize combines the tile partials in fp64
+//   (Chan's parallel variance), d3d_bn_apply_cl applies them;
+// * A may be the channel concatenation of TWO row tensors (the decoder's skip connections,
+//   heads/multi_dimensional_head.py:36) without materialising it: the K loop walks both tensor maps.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int kBM = 128;           // rows per CTA = MMA M = TMEM lanes
+constexpr int kBK = 32;            // floats per stage row = 128 bytes = one swizzle row
+constexpr int kBNMax = 144;        // column tile (multiple of 16): 72 -> 80, 144, 288 = 2 x 144, ...
+constexpr int kStages = 4;         // 4 x 34 KB ring + a 74 KB output staging tile: one persistent CTA per SM
+constexpr int kThreads = 320;      // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2-9: epilogue
+constexpr int kEpiThreads = kThreads - 64;
+constexpr int kMaxSlots = 8;       // row slots of the store loop (partial column sums per slot in shared memory)
+constexpr unsigned kABytes = kBM * kBK * 4;            // 16 KB
+constexpr unsigned kBBytes = kBNMax * kBK * 4;         // 18 KB
+constexpr unsigned kStageBytes = kABytes + kBBytes;    // 34 KB, a multiple of 1024
+constexpr int kCStride = kBNMax + 4;                   // fp32 staging of the output tile for the column statistics
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// row-major fp32 matrix [rows x cols], leading dimension ld (floats); box = [box_rows x 32 floats], 128-byte swizzle;
+// out-of-range elements read as zero (tails in M, N and K need no special code)
+int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return D3D_ERR_UNSUPPORTED;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : D3D_ERR_BAD_ARG;
+}
+
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+
+// K-major operand tile in the 128-byte-swizzle canonical layout: rows 128 bytes apart, 8-row groups 1024 bytes apart
+__device__ __forceinline__ unsigned long long sw128_desc(unsigned addr) {
+  return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+__device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc,
+                                         unsigned accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct GemmArgs {
+  float* C;
+  float* stats;   // (row tiles, 2, N): per-tile column mean and M2 (sum of squared deviations), or null
+  int M, N, K0, K1;  // A = [A0 (M x K0) | A1 (M x K1)]
+  int bn;            // column tile: multiple of 16, <= kBNMax
+  int accumulate;    // C += instead of C =
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: one CTA per SM walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles run
+// decoupled — the producer streams stages of whatever tile comes next, the MMA thread fills one of TWO TMEM accumulators
+// while the epilogue warps drain the other — so loads, tensor-core work and stores of consecutive tiles overlap.
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // the dynamic shared-memory window is only guaranteed 16-byte aligned: align the stage ring to 1024 by hand
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* sC = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);  // fp32 staging of one output tile
+  __shared__ __align__(8) unsigned long long bars[2 * kStages + 4];
+  __shared__ unsigned tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk0 = (g.K0 + kBK - 1) / kBK, nk1 = (g.K1 + kBK - 1) / kBK, nk = nk0 + nk1;
+  const int n_tiles = g.tiles_m * g.tiles_n;
+  const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kStages]);
+  const unsigned tfull0 = smem_u32(&bars[2 * kStages]), tempty0 = smem_u32(&bars[2 * kStages + 2]);
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, kEpiThreads); }
+    mbar_init_fence();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512u);  // two accumulators of up to 256 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer ----
+      const unsigned tx = kABytes + (unsigned)g.bn * kBK * 4;
+      int it_all = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / g.tiles_n) * kBM, n0 = (t % g.tiles_n) * g.bn;
+        for (int it = 0; it < nk; ++it, ++it_all) {
+          const int s = it_all % kStages;
+          mbar_wait_short(empty0 + 8 * s, (unsigned)(((it_all / kStages) & 1) ^ 1));
+          const unsigned sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
+          mbar_arrive_expect_tx(full0 + 8 * s, tx);
+          if (it < nk0) tma_load_2d(sa, &map_a0, it * kBK, m0, full0 + 8 * s);
+          else tma_load_2d(sa, &map_a1, (it - nk0) * kBK, m0, full0 + 8 * s);
+          tma_load_2d(sb, &map_b, it < nk0 ? it * kBK : g.K0 + (it - nk0) * kBK, n0, full0 + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ----
+      // D = f32, A = B = tf32, both K-major, N = bn, M = 128
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(g.bn >> 3) << 17) | ((128u >> 4) << 24);
+      int it_all = 0, n_local = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++n_local) {
+        const int acc = n_local & 1;
+        mbar_wait_short(tempty0 + 8 * acc, (unsigned)(((n_local >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const unsigned d = tmem_base + (unsigned)acc * 256u;
+        for (int it = 0; it < nk; ++it, ++it_all) {
+          const int s = it_all % kStages;
+          mbar_wait_short(full0 + 8 * s, (unsigned)((it_all / kStages) & 1));
+          tc_fence_after();
+          const unsigned sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
+#pragma unroll
+          for (int kk = 0; kk < kBK / 8; ++kk)
+            mma_tf32(d, sw128_desc(sa + kk * 32), sw128_desc(sb + kk * 32), idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          mma_commit(empty0 + 8 * s);  // the stage is free once these MMAs have read it
+        }
+        mma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    // ---- epilogue (8 warps): TMEM -> shared memory (thread = output row, TMEM lane = 32 * (warp % 4) + lane; the two
+    //      warps of a lane quarter take alternate 16-column pieces), then the tile goes out as contiguous row segments —
+    //      a thread keeps ONE float4 column and walks the rows, so the column statistics accumulate in its registers ----
+    const int q = warp & 3, r = q * 32 + lane, half = (warp - 2) >> 2;
+    const int te = tid - 64;
+    float* sP = sC + (size_t)kBM * kCStride;  // [row slot][2][kBNMax] partial column sums
+    int n_local = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++n_local) {
+      const int acc = n_local & 1;
+      const int tile_m = t / g.tiles_n, m0 = tile_m * kBM, n0 = (t % g.tiles_n) * g.bn;
+      mbar_wait_short(tfull0 + 8 * acc, (unsigned)((n_local >> 1) & 1));
+      tc_fence_after();
+      for (int c16 = 16 * half; c16 < g.bn; c16 += 32) {
+        unsigned v[16];
+        tmem_ld16(tmem_base + (unsigned)acc * 256u + ((unsigned)(q * 32) << 16) + (unsigned)c16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(sC + (size_t)r * kCStride + c16 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty0 + 8 * acc);  // accumulator read out: the MMA thread may start the tile after next in it
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // staging tile complete
+      const int rows_valid = min(kBM, g.M - m0);
+      const int nc4 = min(g.bn, g.N - n0) >> 2;  // N % 4 == 0
+      const int rows_per_pass = min(kEpiThreads / nc4, kMaxSlots);
+      const int slot = te / nc4, c4 = te - slot * nc4;
+      float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+      if (slot < rows_per_pass) {
+        const float4 shift = *reinterpret_cast<const float4*>(sC + 4 * c4);  // row 0 of the tile: common shift of the sums
+        float* cbase = g.C + (long long)m0 * g.N + n0 + 4 * c4;
+        const float* sbase = sC + 4 * c4;
+        for (int rr = slot; rr < rows_valid; rr += 4 * rows_per_pass) {
+          float4 o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (rr + u * rows_per_pass < rows_valid) o[u] = *reinterpret_cast<const float4*>(sbase + (size_t)(rr + u * rows_per_pass) * kCStride);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int row = rr + u * rows_per_pass;
+            if (row < rows_valid) {
+              float4 w = o[u];
+              float* dst = cbase + (long long)row * g.N;
+              if (g.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(dst);
+                w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+              }
+              *reinterpret_cast<float4*>(dst) = w;
+              const float dx = o[u].x - shift.x, dy = o[u].y - shift.y, dz = o[u].z - shift.z, dw = o[u].w - shift.w;
+              s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+              s2.x += dx * dx; s2.y += dy * dy; s2.z += dz * dz; s2.w += dw * dw;
+            }
+          }
+        }
+        if (g.stats) {
+          *reinterpret_cast<float4*>(sP + (size_t)slot * 2 * kBNMax + 4 * c4) = s1;
+          *reinterpret_cast<float4*>(sP + (size_t)slot * 2 * kBNMax + kBNMax + 4 * c4) = s2;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // staging tile consumed; partial sums in place
+      if (g.stats && te < 4 * nc4) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int p = 0; p < rows_per_pass; ++p) {  // fixed order: deterministic
+          a1 += sP[(size_t)p * 2 * kBNMax + te];
+          a2 += sP[(size_t)p * 2 * kBNMax + kBNMax + te];
+        }
+        const float inv = 1.0f / (float)rows_valid;
+        float* dst = g.stats + (size_t)tile_m * 2 * g.N + n0 + te;
+        dst[0] = sC[te] + a1 * inv;        // tile mean (sC row 0 = the shift; the next tile's staging starts after bar 2)
+        dst[g.N] = a2 - a1 * a1 * inv;     // tile M2
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+}
+
+// BatchNorm statistics from the GEMM's tile partials: Chan's combination in fp64, one thread per channel.
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int tiles, long long R, int C, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int t = 0; t < tiles; ++t) {
+    const double nb = (double)min((long long)kBM, R - (long long)t * kBM);
+    const double mb = (double)stats[(size_t)t * 2 * C + c], m2b = (double)stats[(size_t)t * 2 * C + C + c];
+    const double delta = mb - mean, tot = n + nb;
+    mean += delta * nb / tot;
+    m2 += m2b + delta * delta * n * nb / tot;
+    n = tot;
+  }
+  const double var = m2 / n > 0 ? m2 / n : 0.0;
+  save_mean[c] = (float)mean;
+  save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = n > 1 ? m2 / (n - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+  if (c == 0 && num_batches) *num_batches += 1;
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int d3d_gemm_row_tiles(long long M) { return (int)((M + kBM - 1) / kBM); }
+
+/* C[M x N] (+)= [A0 | A1] . B^T ;  A0 (M x K0), A1 (M x K1) or NULL, B (N x (K0 + K1)), all row-major fp32, TF32 tensor cores.
+ * stats (d3d_gemm_row_tiles(M), 2, N) or NULL: per row tile the column mean and M2 of the tile of C (for d3d_bn_finalize).
+ * Requires K0 % 4 == 0, K1 % 4 == 0, N % 4 == 0 and 16-byte aligned pointers (TMA). */
+int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1, int accumulate,
+                  float* stats, void* stream) {
+  D3D_REQUIRE(A0 && B && C && M > 0 && N > 0 && K0 > 0 && K1 >= 0 && (K1 == 0 || A1));
+  if (K0 % 4 || K1 % 4 || N % 4 || !aligned16(A0) || !aligned16(A1) || !aligned16(B) || !aligned16(C)) return D3D_ERR_UNSUPPORTED;
+  if (stats && accumulate) return D3D_ERR_BAD_ARG;
+  GemmArgs g{};
+  g.C = C; g.stats = stats; g.M = (int)M; g.N = N; g.K0 = K0; g.K1 = K1; g.accumulate = accumulate;
+  if (M > 0x7fffffffLL) return D3D_ERR_UNSUPPORTED;
+  const int n16 = (N + 15) & ~15;
+  g.bn = n16 < kBNMax ? n16 : kBNMax;
+  g.tiles_m = (int)((M + kBM - 1) / kBM);
+  // few row tiles (the coarse levels): narrower column tiles put more SMs to work
+  for (int cand : {96, 80, 48})
+    if ((long long)g.tiles_m * ((N + g.bn - 1) / g.bn) < 120 && cand < g.bn) g.bn = cand;
+  g.tiles_n = (N + g.bn - 1) / g.bn;
+  CUtensorMap ma0, ma1, mb;
+  int rc = make_map(&ma0, A0, M, K0, K0, kBM);
+  if (rc == 0) rc = K1 > 0 ? make_map(&ma1, A1, M, K1, K1, kBM) : make_map(&ma1, A0, M, K0, K0, kBM);
+  if (rc == 0) rc = make_map(&mb, B, N, (long long)K0 + K1, (long long)K0 + K1, g.bn);
+  if (rc != 0) return rc;
+  const size_t smem = (size_t)kStages * kStageBytes + (size_t)kBM * kCStride * 4 + (size_t)kMaxSlots * 2 * kBNMax * 4 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  const long long n_tiles = (long long)g.tiles_m * g.tiles_n;
+  const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
+  gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma0, ma1, mb, g);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
+/* mean / invstd (and the running statistics, momentum update like torch.nn.BatchNorm1d) of the R x C matrix whose tile
+ * partials `stats` d3d_gemm_tf32 wrote. */
+int d3d_bn_finalize(const float* stats, long long R, int C, float eps, float momentum, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, float* save_mean, float* save_invstd, void* stream) {
+  D3D_REQUIRE(stats && save_mean && save_invstd && R > 0 && C > 0);
+  bn_finalize_kernel<<<d3d_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, d3d_gemm_row_tiles(R), R, C, eps, momentum,
+                                                                           running_mean, running_var, num_batches_tracked,
+                                                                           save_mean, save_invstd);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
+}  // extern "C"

@@ -37,6 +37,19 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
+// the same without a suspend-time hint (the hardware's default, short time limit): for waits on a critical path
+__device__ __forceinline__ void mbar_wait_short(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // ---- bulk asynchronous copy global -> shared, completion counted in bytes on an mbarrier ------------------------
 // dst / src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void* src, unsigned bytes, unsigned bar) {

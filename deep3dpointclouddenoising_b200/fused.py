@@ -154,7 +154,8 @@ class BatchNormActFunction(Function):
     """y = act(BatchNorm1d(x) [+ residual]) in one statistics pass and one apply pass (csrc/batchnorm.cu)."""
 
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu, counter=None):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, eps, momentum, training, relu, counter=None,
+                stats=None):
         ctx.training, ctx.has_res = training, residual is not None
         ctx.wparam, ctx.bparam = weight, bias  # the Parameter objects (their .grad buffers, see runtime.grads_in_place)
         # the channel-last kernels need 16-byte aligned rows and parameters (d3d_bn_act_cl_* reject anything else): a view
@@ -165,8 +166,12 @@ class BatchNormActFunction(Function):
         if ctx.rows:  # channel-last view in, channel-last view out: no layout change anywhere
             xr = x.permute(0, 2, 1)
             rr = _rows(residual) if residual is not None else None
-            y, mean, invstd = ops.bn_act_cl_fwd(xr, rr, weight, bias, running_mean, running_var, eps, momentum, training,
-                                                relu, counter)  # num_batches_tracked += 1 rides on the statistics kernel
+            if stats is not None and training:  # statistics came out of the producing GEMM's epilogue: finalise + apply
+                y, mean, invstd = ops.bn_from_stats(xr, rr, stats, weight, bias, running_mean, running_var, eps, momentum,
+                                                    relu, counter)
+            else:
+                y, mean, invstd = ops.bn_act_cl_fwd(xr, rr, weight, bias, running_mean, running_var, eps, momentum,
+                                                    training, relu, counter)  # num_batches_tracked rides on the kernel
             ctx.save_for_backward(xr, y if ctx.relu_mode == 2 else None, weight, bias, mean, invstd)
             return y.permute(0, 2, 1)
         if counter is not None:
@@ -196,10 +201,10 @@ class BatchNormActFunction(Function):
             dx, dres, dgamma, dbeta = ops.bn_act_bwd(grad_out.contiguous(), x, y, weight, bias, mean, invstd,
                                                      ctx.training, ctx.relu_mode, need_res)
         return (dx, dres, dgamma if weight is not None else None, dbeta if bias is not None else None, None, None, None,
-                None, None, None, None)  # dgamma / dbeta are None when they were added in place
+                None, None, None, None, None)  # dgamma / dbeta are None when they were added in place
 
 
-def batch_norm_act(bn, x, relu, residual=None):
+def batch_norm_act(bn, x, relu, residual=None, stats=None):
     """Applies nn.BatchNorm1d module `bn` (its parameters, buffers, momentum, eps, training flag) with the fused kernel."""
     training = bn.training or bn.running_mean is None
     counter = bn.num_batches_tracked if (bn.training and bn.num_batches_tracked is not None) else None
@@ -211,4 +216,4 @@ def batch_norm_act(bn, x, relu, residual=None):
     else:
         momentum = bn.momentum
     return BatchNormActFunction.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, momentum,
-                                      training, relu, counter)
+                                      training, relu, counter, stats)

@@ -11,6 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.autograd import Function
 
+from .. import ops
 from ..fused import _is_grad_buffer, batch_norm_act, cat_channels, is_channel_last, rows_of
 from ..utils.config import runtime
 
@@ -60,26 +61,48 @@ def _weight_grad(g2, x2, into=None):
     return None
 
 
+def _own_gemm(k0, k1, n, *tensors):
+    """The TF32 tensor-core GEMM of this package (csrc/gemm.cu) serves a convolution when TF32 is the convolution
+    arithmetic (torch.backends.cudnn.allow_tf32, the reference's default) and TMA's alignment rules hold; otherwise
+    (exact-fp32 parity runs, 3-channel inputs / outputs) the GEMM goes to cuBLAS."""
+    return (runtime.own_gemm and torch.backends.cudnn.allow_tf32 and tensors[0].is_cuda
+            and ops.gemm_ok(k0, k1, n, *tensors))
+
+
+def _transposed(w):
+    """(Cout, Cin) -> contiguous (Cin, Cout) with the package's transposition kernel (B operand of the data gradient)."""
+    return ops.cm_to_cl(w.contiguous().view(1, w.shape[0], w.shape[1])).view(w.shape[1], w.shape[0])
+
+
 class PointwiseConvRows(Function):
-    """Conv1d(kernel_size=1) on channel-last rows: (B, N, Cin) x (Cout, Cin, 1) -> (B, N, Cout), three cuBLAS GEMMs
-    (forward, data gradient, weight gradient)."""
+    """Conv1d(kernel_size=1) on channel-last rows: (B, N, Cin) x (Cout, Cin, 1) -> (B, N, Cout).  Forward and data
+    gradient on the package's TF32 tensor-core GEMM (weight gradient: batched split-K GEMM).  want_stats: a second,
+    non-differentiable output carries the per-tile column statistics for the BatchNorm that follows (ops.bn_from_stats)."""
 
     @staticmethod
-    def forward(ctx, rows, weight, bias):
+    def forward(ctx, rows, weight, bias, want_stats=False):
         w = weight.squeeze(-1)
         ctx.save_for_backward(rows, w)
         ctx.has_bias = bias is not None
         ctx.wparam = weight  # the Parameter: its .grad buffer is written in place under runtime.grads_in_place
+        if bias is None and _own_gemm(w.shape[1], 0, w.shape[0], rows, w) and rows.is_contiguous():
+            out = ops.gemm_tf32(rows, w, want_stats=want_stats)
+            if want_stats:
+                ctx.mark_non_differentiable(out[1])
+            return out
         with _conv_math():
-            return F.linear(rows, w, bias)
+            y = F.linear(rows, w, bias)
+        return (y, None) if want_stats else y
 
     @staticmethod
-    def backward(ctx, grad):
+    def backward(ctx, grad, _grad_stats=None):
         rows, w = ctx.saved_tensors
         g2 = grad.contiguous().view(-1, grad.shape[-1])
         d_rows = d_w = d_b = None
+        if ctx.needs_input_grad[0] and _own_gemm(w.shape[0], 0, w.shape[1], g2, w):
+            d_rows = ops.gemm_tf32(g2, _transposed(w)).view_as(rows)
         with _conv_math():
-            if ctx.needs_input_grad[0]:
+            if ctx.needs_input_grad[0] and d_rows is None:
                 d_rows = (g2 @ w).view_as(rows)
             if ctx.needs_input_grad[1]:
                 into = ctx.wparam.grad.view(w.shape) if runtime.grads_in_place and _is_grad_buffer(ctx.wparam) else None
@@ -87,7 +110,7 @@ class PointwiseConvRows(Function):
                 d_w = d_w.unsqueeze(-1) if d_w is not None else None
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = g2.sum(0)
-        return d_rows, d_w, d_b
+        return d_rows, d_w, d_b, None
 
 
 class PointwiseConvCatRows(Function):
@@ -97,10 +120,16 @@ class PointwiseConvCatRows(Function):
     next kernel has to re-pack)."""
 
     @staticmethod
-    def forward(ctx, weight, bias, *rows_list):
+    def forward(ctx, weight, bias, want_stats, *rows_list):
         w = weight.squeeze(-1)
         ctx.save_for_backward(w, *rows_list)
         ctx.has_bias = bias is not None
+        if (bias is None and len(rows_list) == 2 and all(r.is_contiguous() for r in rows_list)
+                and _own_gemm(rows_list[0].shape[-1], rows_list[1].shape[-1], w.shape[0], rows_list[0], rows_list[1], w)):
+            out = ops.gemm_tf32(rows_list[0], w, a1=rows_list[1], want_stats=want_stats)  # both K segments in one kernel
+            if want_stats:
+                ctx.mark_non_differentiable(out[1])
+            return out
         with _conv_math():
             c0 = rows_list[0].shape[-1]
             y = F.linear(rows_list[0], w[:, :c0], bias)
@@ -109,23 +138,30 @@ class PointwiseConvCatRows(Function):
                 c1 = c0 + rows.shape[-1]
                 y2.addmm_(rows.reshape(-1, rows.shape[-1]), w[:, c0:c1].t())
                 c0 = c1
-        return y
+        return (y, None) if want_stats else y
 
     @staticmethod
-    def backward(ctx, grad):
+    def backward(ctx, grad, _grad_stats=None):
         w, *rows_list = ctx.saved_tensors
         g2 = grad.contiguous().view(-1, grad.shape[-1])
         d_rows, d_w, c0 = [], [], 0
+        own = _own_gemm(w.shape[0], 0, 4, g2, w) and all(r.shape[-1] % 4 == 0 for r in rows_list)
+        w_t = _transposed(w) if own and any(ctx.needs_input_grad[3:]) else None  # (Cin total, Cout): row blocks per input
         with _conv_math():
             for i, rows in enumerate(rows_list):
                 c1 = c0 + rows.shape[-1]
-                d_rows.append((g2 @ w[:, c0:c1]).view_as(rows) if ctx.needs_input_grad[2 + i] else None)
+                if not ctx.needs_input_grad[3 + i]:
+                    d_rows.append(None)
+                elif w_t is not None:
+                    d_rows.append(ops.gemm_tf32(g2, w_t[c0:c1]).view_as(rows))
+                else:
+                    d_rows.append((g2 @ w[:, c0:c1]).view_as(rows))
                 if ctx.needs_input_grad[0]:
                     d_w.append(_weight_grad(g2, rows.reshape(-1, rows.shape[-1])))
                 c0 = c1
         d_weight = torch.cat(d_w, 1).unsqueeze(-1) if ctx.needs_input_grad[0] else None
         d_b = g2.sum(0) if ctx.has_bias and ctx.needs_input_grad[1] else None
-        return (d_weight, d_b, *d_rows)
+        return (d_weight, d_b, None, *d_rows)
 
 
 def _is_pointwise(m):
@@ -137,16 +173,28 @@ class FusedSequential(nn.Sequential):
     def forward(self, x, residual=None, final_relu=False):
         """x: a (B, C, N) tensor, or a list of them standing for their channel concatenation."""
         mods = list(self._modules.values())
-        if isinstance(x, (list, tuple)):
-            parts = list(x)
-            if (parts[0].is_cuda and runtime.channel_last and _is_pointwise(mods[0])
-                    and all(is_channel_last(t) for t in parts)):
-                x = PointwiseConvCatRows.apply(mods[0].weight, mods[0].bias, *[t.permute(0, 2, 1) for t in parts])
+        parts = list(x) if isinstance(x, (list, tuple)) else None
+        on_gpu = parts[0].is_cuda if parts is not None else x.is_cuda
+        use_fused = on_gpu and runtime.fused_batchnorm
+
+        def feeds_training_bn(k):
+            """The convolution at position k is followed by a BatchNorm in training mode: its GEMM emits the tile
+            statistics and the BatchNorm skips its own statistics pass."""
+            nxt = mods[k + 1] if k + 1 < len(mods) else None
+            return (use_fused and isinstance(nxt, nn.BatchNorm1d) and (nxt.training or nxt.running_mean is None)
+                    and nxt.momentum is not None)
+
+        stats = None  # tile statistics of x from the GEMM that produced it (consumed by the BatchNorm right after)
+        if parts is not None:
+            if on_gpu and runtime.channel_last and _is_pointwise(mods[0]) and all(is_channel_last(t) for t in parts):
+                want = feeds_training_bn(0)
+                x = PointwiseConvCatRows.apply(mods[0].weight, mods[0].bias, want, *[t.permute(0, 2, 1) for t in parts])
+                if want:
+                    x, stats = x
                 x = x.permute(0, 2, 1)
                 mods = mods[1:]
             else:
                 x = cat_channels(parts)
-        use_fused = x.is_cuda and runtime.fused_batchnorm
         use_rows = x.is_cuda and runtime.channel_last and x.dim() == 3
         i = 0
         while i < len(mods):
@@ -155,13 +203,19 @@ class FusedSequential(nn.Sequential):
                 next_is_relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
                 is_last = i + (2 if next_is_relu else 1) == len(mods)
                 res = residual if is_last else None
-                x = batch_norm_act(m, x, relu=next_is_relu or (is_last and final_relu), residual=res)
+                x = batch_norm_act(m, x, relu=next_is_relu or (is_last and final_relu), residual=res, stats=stats)
+                stats = None
                 if is_last:
                     residual, final_relu = None, False
                 i += 2 if next_is_relu else 1
                 continue
+            stats = None
             if use_rows and _is_pointwise(m):
-                x = PointwiseConvRows.apply(rows_of(x), m.weight, m.bias).permute(0, 2, 1)
+                want = feeds_training_bn(i)
+                x = PointwiseConvRows.apply(rows_of(x), m.weight, m.bias, want)
+                if want:
+                    x, stats = x
+                x = x.permute(0, 2, 1)
             else:
                 x = m(x)
             i += 1

@@ -412,6 +412,49 @@ def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var,
     return y, mean, invstd
 
 
+def gemm_tf32(a0, b, a1=None, out=None, accumulate=False, want_stats=False):
+    """[a0 | a1] (.., K0 | K1) @ b (N, K0 + K1)^T -> (.., N) on the TF32 tensor cores (csrc/gemm.cu).
+    want_stats: also the per-tile column statistics for `bn_from_stats` (the convolution feeds a BatchNorm)."""
+    L = _lib.load()
+    a0, b = _f32(a0, "rows"), _f32(b, "weight")
+    K0, N = a0.shape[-1], b.shape[0]
+    M = a0.numel() // K0
+    K1 = 0 if a1 is None else _f32(a1, "rows").shape[-1]
+    with torch.cuda.device(a0.device):
+        c = out if out is not None else torch.empty(a0.shape[:-1] + (N,), dtype=torch.float32, device=a0.device)
+        stats = torch.empty((L.d3d_gemm_row_tiles(M), 2, N), dtype=torch.float32, device=a0.device) if want_stats else None
+        _lib.check(L.d3d_gemm_tf32(_p(a0), _p(a1), _p(b), _p(c), M, N, K0, K1, int(bool(accumulate)), _p(stats), _stream()),
+                   "d3d_gemm_tf32")
+    _count()
+    return (c, stats) if want_stats else c
+
+
+def gemm_ok(K0, K1, N, *tensors):
+    return K0 % 4 == 0 and K1 % 4 == 0 and N % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in tensors)
+
+
+def bn_from_stats(x_rows, residual_rows, stats, gamma, beta, running_mean, running_var, eps, momentum, relu,
+                  num_batches_tracked=None):
+    """Training-mode BatchNorm (+ residual) (+ ReLU) of x_rows whose tile statistics the producing GEMM already wrote:
+    finalise (Chan, fp64) + apply.  Returns (y, mean, invstd) like bn_act_cl_fwd."""
+    if num_batches_tracked is not None and num_batches_tracked.dtype != torch.int64:
+        num_batches_tracked = None
+    L = _lib.load()
+    x_rows = _f32(x_rows, "input")
+    C = x_rows.shape[-1]
+    R = x_rows.numel() // C
+    with torch.cuda.device(x_rows.device):
+        y = torch.empty_like(x_rows)
+        mean = torch.empty((C,), dtype=torch.float32, device=x_rows.device)
+        invstd = torch.empty((C,), dtype=torch.float32, device=x_rows.device)
+        _lib.check(L.d3d_bn_finalize(_p(stats), R, C, float(eps), float(momentum), _p(running_mean), _p(running_var),
+                                     _p(num_batches_tracked), _p(mean), _p(invstd), _stream()), "d3d_bn_finalize")
+        _lib.check(L.d3d_bn_apply_cl(_p(x_rows), _p(residual_rows), _p(gamma), _p(beta), _p(mean), _p(invstd), R, C,
+                                     int(bool(relu)), _p(y), _stream()), "d3d_bn_apply_cl")
+    _count()
+    return y, mean, invstd
+
+
 def bn_act_cl_bwd(dy_rows, x_rows, y_rows, gamma, beta, mean, invstd, training, relu_mode, need_res,
                   grad_gamma_into=None, grad_beta_into=None):
     """grad_gamma_into / grad_beta_into: the parameters' gradient buffers; when given, the kernel ADDS into them and the

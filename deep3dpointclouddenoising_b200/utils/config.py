@@ -86,10 +86,12 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #     adjacent rows per CTA, cp.async.bulk staging of the neighbour-row union, tcgen05 contraction) where it is the
 #     faster one: self queries (M == N; measured on B200: 189 vs 268 us at the first level, tools/time_pospool.py).
 #     'always' forces it for every shape, False restores the per-query gather kernel everywhere.
+#   own_gemm: the 1x1 convolutions (forward and data gradient) run on the package's TMA + tcgen05 TF32 GEMM
+#     (csrc/gemm.cu), whose epilogue also emits the BatchNorm statistics; False: cuBLAS through torch.
 #   staged_tiles_backward: same for the backward pass (measured slower than the segmented reduction: off).
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
                     "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
-                    "staged_tiles_backward": False})
+                    "staged_tiles_backward": False, "own_gemm": True})
 
 
 def reset_config():

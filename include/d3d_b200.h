@@ -225,6 +225,26 @@ int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const flo
                       size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 4b. The 1x1 convolutions as row-major TF32 GEMMs on the tensor cores (TMA + tcgen05, accumulator in TMEM) with the
+ *     BatchNorm statistics in the epilogue (ref: models/backbones/resnet.py:32-45,58-66,
+ *     models/local_aggregation_operators.py:121-123: nn.Conv1d(kernel_size=1, bias=False) -> BatchNorm1d -> ReLU, which
+ *     cuDNN runs in TF32 by default).
+ *       C[M x N] (+)= [A0 | A1] . B^T      A0 (M x K0), A1 (M x K1) or NULL (channel concatenation of two row tensors,
+ *                                          heads/multi_dimensional_head.py:36), B (N x (K0 + K1)); all row-major fp32
+ *     stats (d3d_gemm_row_tiles(M), 2, N) or NULL: per 128-row tile the column mean and sum of squared deviations of
+ *     the tile of C; d3d_bn_finalize combines them (Chan, fp64) into mean / invstd + running statistics, and
+ *     d3d_bn_apply_cl applies them: the statistics pass over the convolution output never runs.
+ *     Requires K0 % 4 == 0, K1 % 4 == 0, N % 4 == 0, 16-byte aligned pointers (D3D_ERR_UNSUPPORTED otherwise).
+ * ---------------------------------------------------------------------------------------------- */
+int d3d_gemm_row_tiles(long long M);
+int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1,
+                  int accumulate, float* stats, void* stream);
+int d3d_bn_finalize(const float* stats, long long R, int C, float eps, float momentum, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, void* stream);
+int d3d_bn_apply_cl(const float* x, const float* residual, const float* gamma, const float* beta, const float* save_mean,
+                    const float* save_invstd, long long R, int C, int relu, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * 5. Exact nearest neighbours on large clouds and the Chamfer distance
  *    ref: compute_cd.py:74-75; models/losses/chamfer_distance_aux.py:154-155,216-246 (pytorch3d knn_points, K = 1)
  * ---------------------------------------------------------------------------------------------- */

@@ -1,0 +1,110 @@
+"""GPU: the TF32 tensor-core GEMM of the 1x1 convolutions (csrc/gemm.cu: TMA + tcgen05 + TMEM) and the BatchNorm
+statistics its epilogue emits, against torch (fp64 reference; TF32 rounds both operands to 10 mantissa bits, so the
+stated tolerance is 2e-3 of the row-times-column magnitude — what cuDNN's default TF32 convolution has too;
+ref: u_net_arch/models/backbones/resnet.py:32-45)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(c, a, b, tol=2e-3):
+    ref = a.double() @ b.double().t()
+    scale = (a.double().abs() @ b.double().abs().t()).clamp_min(1e-30)
+    err = ((c.double() - ref).abs() / scale).max().item()
+    assert err <= tol, err
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 32, 16), (1000, 72, 72), (4096, 72, 144), (5000, 144, 288), (777, 288, 144),
+                                   (512, 1152, 2304), (130, 2304, 576), (3000, 8, 72), (257, 100, 36)])
+def test_gemm_tf32_matches_matmul(cuda_device, M, K, N):
+    from deep3dpointclouddenoising_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    b = torch.randn(N, K, generator=g).to(cuda_device)
+    c = ops.gemm_tf32(a, b)
+    assert c.shape == (M, N)
+    _check(c, a, b)
+    assert torch.equal(c, ops.gemm_tf32(a, b))  # deterministic
+    # batched leading dims are just more rows
+    c3 = ops.gemm_tf32(a.view(1, M, K), b)
+    assert torch.equal(c3.view(M, N), c)
+
+
+def test_gemm_two_row_tensors_and_accumulate(cuda_device):
+    """[A0 | A1] . B^T without the concatenation (decoder skip connections), K0 not a multiple of the 32-float stage."""
+    from deep3dpointclouddenoising_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for M, K0, K1, N in ((2048, 144, 72, 72), (900, 2304, 1152, 576), (640, 36, 100, 144)):
+        a0 = torch.randn(M, K0, generator=g).to(cuda_device)
+        a1 = torch.randn(M, K1, generator=g).to(cuda_device)
+        b = torch.randn(N, K0 + K1, generator=g).to(cuda_device)
+        c = ops.gemm_tf32(a0, b, a1=a1)
+        _check(c, torch.cat([a0, a1], 1), b)
+        base = torch.randn(M, N, generator=g).to(cuda_device)
+        acc = base.clone()
+        ops.gemm_tf32(a0, b[:, :K0].contiguous(), out=acc, accumulate=True)
+        ref = base.double() + a0.double() @ b[:, :K0].double().t()
+        assert ((acc.double() - ref).abs() / (1 + (a0.double().abs() @ b[:, :K0].double().abs().t()))).max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("M,K,N,relu,res", [(4096, 72, 144, True, False), (1000, 144, 72, True, True), (300, 288, 576, False, True),
+                                            (128 * 5 + 3, 72, 72, True, False)])
+def test_epilogue_statistics_give_batchnorm(cuda_device, M, K, N, relu, res):
+    """finalise + apply over the GEMM's tile partials == torch.nn.BatchNorm1d (training mode) on the same matrix."""
+    from deep3dpointclouddenoising_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N)
+    a = torch.randn(M, K, generator=g).to(cuda_device)
+    b = torch.randn(N, K, generator=g).to(cuda_device)
+    residual = torch.randn(M, N, generator=g).to(cuda_device) if res else None
+    c, stats = ops.gemm_tf32(a, b, want_stats=True)
+    assert torch.equal(c, ops.gemm_tf32(a, b))
+    bn = torch.nn.BatchNorm1d(N).to(cuda_device).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    counter = bn.num_batches_tracked.clone()
+    y, mean, invstd = ops.bn_from_stats(c, residual, stats, bn.weight.detach(), bn.bias.detach(), rm, rv, bn.eps, bn.momentum,
+                                        relu, counter)
+    want = bn(c)
+    if res:
+        want = want + residual
+    if relu:
+        want = want.relu()
+    torch.testing.assert_close(y, want, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(mean, c.mean(0), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(invstd, 1 / torch.sqrt(c.var(0, unbiased=False) + bn.eps), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv, bn.running_var, rtol=1e-5, atol=1e-6)
+    assert int(counter) == int(bn.num_batches_tracked)
+
+
+def test_conv_bn_block_on_own_gemm_matches_cublas_path(cuda_device):
+    """The conv -> BatchNorm -> ReLU block (models/blocks.py) with the package's GEMM + epilogue statistics against the
+    same block on cuBLAS TF32 + the fused BatchNorm's own statistics pass: outputs, input and parameter gradients,
+    running statistics.  Both sides compute in TF32, in different summation orders: 5e-3 of the tensor scale."""
+    from deep3dpointclouddenoising_b200.models import blocks
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    torch.manual_seed(0)
+    B, N, cin, cout = 4, 2048, 144, 288
+    x_rows = torch.randn(B, N, cin, device=cuda_device)
+    skip_rows = torch.randn(B, N, 72, device=cuda_device)
+    gout = torch.randn(B, cout, N, device=cuda_device)
+    results = []
+    for own in (True, False):
+        runtime.own_gemm = own
+        try:
+            torch.manual_seed(1)
+            blk = blocks.conv_bn(cin + 72, cout).to(cuda_device).train()
+            x = x_rows.clone().requires_grad_(True)
+            s_ = skip_rows.clone().requires_grad_(True)
+            y = blk([x.permute(0, 2, 1), s_.permute(0, 2, 1)])
+            gx, gs, gw, gg, gb = torch.autograd.grad(y, (x, s_, blk[0].weight, blk[1].weight, blk[1].bias), gout)
+            results.append((y.detach(), gx, gs, gw, gg, gb, blk[1].running_mean.clone(), blk[1].running_var.clone()))
+        finally:
+            runtime.own_gemm = True
+    for a, b in zip(*results):
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 5e-3 * scale, ((a - b).abs().max().item(), scale)

@@ -46,7 +46,7 @@ def test_pointwise_conv_over_concatenation_matches_cat_then_conv1d():
     torch.manual_seed(1)
     conv = nn.Conv1d(9, 5, 1, bias=True).double()
     a, b = _cl(2, 4, 6, grad=True), _cl(2, 5, 6, grad=True)
-    y = blocks.PointwiseConvCatRows.apply(conv.weight, conv.bias, a.permute(0, 2, 1), b.permute(0, 2, 1)).permute(0, 2, 1)
+    y = blocks.PointwiseConvCatRows.apply(conv.weight, conv.bias, False, a.permute(0, 2, 1), b.permute(0, 2, 1)).permute(0, 2, 1)
     ref = conv(torch.cat([a, b], 1))
     torch.testing.assert_close(y, ref)
     g = torch.randn_like(ref)

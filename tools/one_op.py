@@ -14,6 +14,7 @@ f = torch.randn(B, N, C, device=dev)
 kp = torch.randn(15, 3, device=dev) * 0.006; w = torch.randn(15, C, device=dev)
 rowptr, entries = ops.build_inverse_map(idx, N)
 order = ops.spatial_order(pts)
+wg = torch.randn(144, C, device=dev)
 torch.cuda.synchronize()
 for _ in range(n):
     if op == "ball_query": ops.ball_query(pts, pts, mask, mask, 0.025, 52)
@@ -22,6 +23,8 @@ for _ in range(n):
     elif op == "pospool_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg')
     elif op == "pospool_tiles_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys)
     elif op == "pospool_tiles_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg', support_order=order)
+    elif op == "gemm": ops.gemm_tf32(f.view(-1, C), wg)
+    elif op == "gemm_stats": ops.gemm_tf32(f.view(-1, C), wg, want_stats=True)
     elif op == "pseudogrid_fwd": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 0)
     elif op == "pseudogrid_fwd_tc": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 1)
     elif op == "pseudogrid_bwd": ops.pseudogrid_bwd(f, f, pts, pts, idx, rowptr, entries, nv, mask, kp, w, 0.01, 'linear', 0)
