@@ -257,22 +257,45 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
-// BatchNorm statistics from the GEMM's tile partials: Chan's combination in fp64, one thread per channel.
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int tiles, long long R, int C, float eps, float momentum,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ num_batches, float* __restrict__ save_mean,
-                                   float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int t = 0; t < tiles; ++t) {
-    const double nb = (double)min((long long)kBM, R - (long long)t * kBM);
-    const double mb = (double)stats[(size_t)t * 2 * C + c], m2b = (double)stats[(size_t)t * 2 * C + C + c];
-    const double delta = mb - mean, tot = n + nb;
-    mean += delta * nb / tot;
-    m2 += m2b + delta * delta * n * nb / tot;
-    n = tot;
-  }
+// BatchNorm statistics from the GEMM's tile partials (count, mean, M2 per 128-row tile), combined in fp64:
+//   mean = sum n_t mean_t / n,   M2 = sum (M2_t + n_t (mean_t - mean)^2)      (Chan et al., pairwise form summed up)
+// Block = 32 channels x 8 tile slices: tile rows are read as coalesced 128-byte segments, the slices are combined in a
+// fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ stats, int tiles, long long R, int C, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ num_batches,
+                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const bool ok = c < C;
+  const double n = (double)R;
+  double acc = 0.0;
+  if (ok)
+    for (int t = ty; t < tiles; t += 8) {
+      const double nb = (double)min((long long)kBM, R - (long long)t * kBM);
+      acc += nb * (double)stats[(size_t)t * 2 * C + c];
+    }
+  red[ty][cx] = acc;
+  __syncthreads();
+  double mean = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mean += red[k][cx];
+  mean /= n;
+  __syncthreads();
+  acc = 0.0;
+  if (ok)
+    for (int t = ty; t < tiles; t += 8) {
+      const double nb = (double)min((long long)kBM, R - (long long)t * kBM);
+      const double d = (double)stats[(size_t)t * 2 * C + c] - mean;
+      acc += (double)stats[(size_t)t * 2 * C + C + c] + nb * d * d;
+    }
+  red[ty][cx] = acc;
+  __syncthreads();
+  if (ty != 0 || !ok) return;
+  double m2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m2 += red[k][cx];
   const double var = m2 / n > 0 ? m2 / n : 0.0;
   save_mean[c] = (float)mean;
   save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -341,7 +364,7 @@ int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, lo
 int d3d_bn_finalize(const float* stats, long long R, int C, float eps, float momentum, float* running_mean, float* running_var,
                     long long* num_batches_tracked, float* save_mean, float* save_invstd, void* stream) {
   D3D_REQUIRE(stats && save_mean && save_invstd && R > 0 && C > 0);
-  bn_finalize_kernel<<<d3d_ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(stats, d3d_gemm_row_tiles(R), R, C, eps, momentum,
+  bn_finalize_kernel<<<d3d_ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(stats, d3d_gemm_row_tiles(R), R, C, eps, momentum,
                                                                            running_mean, running_var, num_batches_tracked,
                                                                            save_mean, save_invstd);
   d3d_note_launches(1);
