@@ -259,43 +259,61 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 
 // BatchNorm statistics from the GEMM's tile partials (count, mean, M2 per 128-row tile), combined in fp64:
 //   mean = sum n_t mean_t / n,   M2 = sum (M2_t + n_t (mean_t - mean)^2)      (Chan et al., pairwise form summed up)
-// Block = 32 channels x 8 tile slices: tile rows are read as coalesced 128-byte segments, the slices are combined in a
-// fixed order (deterministic).
-__global__ void __launch_bounds__(256)
+// Block = 8 channels x 32 tile slices (many small blocks: the kernel is pure latency), four loads in flight per thread;
+// the slices are combined in a fixed order (deterministic).
+constexpr int kFinCh = 8, kFinSlices = 32;
+
+__device__ __forceinline__ double fin_reduce(double (*red)[kFinCh], int cx, int ty, double v) {
+  red[ty][cx] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < kFinSlices; ++k) s += red[k][cx];
+  __syncthreads();
+  return s;
+}
+
+__global__ void __launch_bounds__(kFinCh * kFinSlices)
 bn_finalize_kernel(const float* __restrict__ stats, int tiles, long long R, int C, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ num_batches,
                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  __shared__ double red[8][33];
-  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  const bool ok = c < C;
+  __shared__ double red[kFinSlices][kFinCh];
+  const int cx = threadIdx.x % kFinCh, ty = threadIdx.x / kFinCh;
+  const int c = min(blockIdx.x * kFinCh + cx, C - 1);  // surplus lanes of the last block repeat channel C - 1
   const double n = (double)R;
-  double acc = 0.0;
-  if (ok)
-    for (int t = ty; t < tiles; t += 8) {
-      const double nb = (double)min((long long)kBM, R - (long long)t * kBM);
-      acc += nb * (double)stats[(size_t)t * 2 * C + c];
-    }
-  red[ty][cx] = acc;
-  __syncthreads();
-  double mean = 0.0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) mean += red[k][cx];
-  mean /= n;
-  __syncthreads();
-  acc = 0.0;
-  if (ok)
-    for (int t = ty; t < tiles; t += 8) {
-      const double nb = (double)min((long long)kBM, R - (long long)t * kBM);
-      const double d = (double)stats[(size_t)t * 2 * C + c] - mean;
-      acc += (double)stats[(size_t)t * 2 * C + C + c] + nb * d * d;
-    }
-  red[ty][cx] = acc;
-  __syncthreads();
-  if (ty != 0 || !ok) return;
-  double m2 = 0.0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) m2 += red[k][cx];
+  const double last_n = (double)(R - (long long)(tiles - 1) * kBM);  // rows of the last tile; all others hold kBM
+  const float* pm = stats + c;
+  // pass 1: mean = sum n_t mean_t / n
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int t = ty;
+  for (; t + 3 * kFinSlices < tiles - 1; t += 4 * kFinSlices) {
+    const float v0 = pm[(size_t)t * 2 * C], v1 = pm[(size_t)(t + kFinSlices) * 2 * C], v2 = pm[(size_t)(t + 2 * kFinSlices) * 2 * C],
+                v3 = pm[(size_t)(t + 3 * kFinSlices) * 2 * C];
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+  }
+  double acc = (a0 + a1 + a2 + a3) * (double)kBM;
+  for (; t < tiles; t += kFinSlices) acc += (t == tiles - 1 ? last_n : (double)kBM) * (double)pm[(size_t)t * 2 * C];
+  const double mean = fin_reduce(red, cx, ty, acc) / n;
+  // pass 2: M2 = sum (M2_t + n_t (mean_t - mean)^2)
+  a0 = a1 = a2 = a3 = 0.0;
+  t = ty;
+  for (; t + 3 * kFinSlices < tiles - 1; t += 4 * kFinSlices) {
+    const float* p0 = pm + (size_t)t * 2 * C;
+    const float* p1 = pm + (size_t)(t + kFinSlices) * 2 * C;
+    const float* p2 = pm + (size_t)(t + 2 * kFinSlices) * 2 * C;
+    const float* p3 = pm + (size_t)(t + 3 * kFinSlices) * 2 * C;
+    const float m0 = p0[0], q0 = p0[C], m1 = p1[0], q1 = p1[C], m2 = p2[0], q2 = p2[C], m3 = p3[0], q3 = p3[C];
+    const double d0 = (double)m0 - mean, d1 = (double)m1 - mean, d2 = (double)m2 - mean, d3 = (double)m3 - mean;
+    a0 += (double)q0 + (double)kBM * d0 * d0; a1 += (double)q1 + (double)kBM * d1 * d1;
+    a2 += (double)q2 + (double)kBM * d2 * d2; a3 += (double)q3 + (double)kBM * d3 * d3;
+  }
+  acc = a0 + a1 + a2 + a3;
+  for (; t < tiles; t += kFinSlices) {
+    const double d = (double)pm[(size_t)t * 2 * C] - mean;
+    acc += (double)pm[(size_t)t * 2 * C + C] + (t == tiles - 1 ? last_n : (double)kBM) * d * d;
+  }
+  const double m2 = fin_reduce(red, cx, ty, acc);
+  if (ty != 0 || blockIdx.x * kFinCh + cx >= C) return;
   const double var = m2 / n > 0 ? m2 / n : 0.0;
   save_mean[c] = (float)mean;
   save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -364,7 +382,7 @@ int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, lo
 int d3d_bn_finalize(const float* stats, long long R, int C, float eps, float momentum, float* running_mean, float* running_var,
                     long long* num_batches_tracked, float* save_mean, float* save_invstd, void* stream) {
   D3D_REQUIRE(stats && save_mean && save_invstd && R > 0 && C > 0);
-  bn_finalize_kernel<<<d3d_ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(stats, d3d_gemm_row_tiles(R), R, C, eps, momentum,
+  bn_finalize_kernel<<<d3d_ceil_div(C, kFinCh), kFinCh * kFinSlices, 0, (cudaStream_t)stream>>>(stats, d3d_gemm_row_tiles(R), R, C, eps, momentum,
                                                                            running_mean, running_var, num_batches_tracked,
                                                                            save_mean, save_invstd);
   d3d_note_launches(1);

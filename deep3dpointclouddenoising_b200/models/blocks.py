@@ -85,6 +85,7 @@ class PointwiseConvRows(Function):
         ctx.save_for_backward(rows, w)
         ctx.has_bias = bias is not None
         ctx.wparam = weight  # the Parameter: its .grad buffer is written in place under runtime.grads_in_place
+        ctx.set_materialize_grads(False)  # no zero tensor for the (non-differentiable) statistics output
         if bias is None and _own_gemm(w.shape[1], 0, w.shape[0], rows, w) and rows.is_contiguous():
             out = ops.gemm_tf32(rows, w, want_stats=want_stats)
             if want_stats:
@@ -97,6 +98,8 @@ class PointwiseConvRows(Function):
     @staticmethod
     def backward(ctx, grad, _grad_stats=None):
         rows, w = ctx.saved_tensors
+        if grad is None:
+            return None, None, None, None
         g2 = grad.contiguous().view(-1, grad.shape[-1])
         d_rows = d_w = d_b = None
         if ctx.needs_input_grad[0] and _own_gemm(w.shape[0], 0, w.shape[1], g2, w):
@@ -124,6 +127,7 @@ class PointwiseConvCatRows(Function):
         w = weight.squeeze(-1)
         ctx.save_for_backward(w, *rows_list)
         ctx.has_bias = bias is not None
+        ctx.set_materialize_grads(False)
         if (bias is None and len(rows_list) == 2 and all(r.is_contiguous() for r in rows_list)
                 and _own_gemm(rows_list[0].shape[-1], rows_list[1].shape[-1], w.shape[0], rows_list[0], rows_list[1], w)):
             out = ops.gemm_tf32(rows_list[0], w, a1=rows_list[1], want_stats=want_stats)  # both K segments in one kernel
@@ -143,6 +147,8 @@ class PointwiseConvCatRows(Function):
     @staticmethod
     def backward(ctx, grad, _grad_stats=None):
         w, *rows_list = ctx.saved_tensors
+        if grad is None:
+            return (None,) * (3 + len(rows_list))
         g2 = grad.contiguous().view(-1, grad.shape[-1])
         d_rows, d_w, c0 = [], [], 0
         own = _own_gemm(w.shape[0], 0, 4, g2, w) and all(r.shape[-1] % 4 == 0 for r in rows_list)
