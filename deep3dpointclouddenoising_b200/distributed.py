@@ -76,6 +76,8 @@ class FlatGradAllReduce:
         self.flat.zero_()  # grads stay views of the bucket (use instead of optimizer.zero_grad(set_to_none=True))
 
     def reduce(self):
+        from .models.blocks import join_weight_grads
+        join_weight_grads()  # weight gradients computed on the side stream are part of the bucket
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
             self.flat.div_(self.world)

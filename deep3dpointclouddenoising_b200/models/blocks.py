@@ -29,6 +29,40 @@ def _conv_math():
 
 
 _ones = {}
+_wgrad_streams, _wgrad_pending = {}, set()
+
+
+def _wgrad_side(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _wgrad_streams:
+        _wgrad_streams[key] = torch.cuda.Stream(device=key)
+    return key, _wgrad_streams[key]
+
+
+def join_weight_grads():
+    """Makes the current stream wait for the weight-gradient GEMMs that backward passes put on the side stream
+    (runtime.wgrad_side_stream).  Call before anything reads the gradient buffers — distributed.FlatParameters.reduce()
+    does; inside a CUDA-graph capture this is the join of the forked branch."""
+    for key in list(_wgrad_pending):
+        torch.cuda.current_stream(key).wait_stream(_wgrad_streams[key])
+        _wgrad_pending.discard(key)
+
+
+def _weight_grad_into(g2, x2, into):
+    """dW accumulated into the parameter's gradient buffer.  The weight gradient of a layer is a leaf of the backward
+    graph — nothing downstream waits for it before the optimiser — so it runs on a side stream, concurrently with the data
+    gradients / BatchNorm / aggregation kernels of the layers below (measured on B200: these GEMMs are 0.76 ms of
+    single-kernel time per step otherwise)."""
+    if not (runtime.wgrad_side_stream and g2.is_cuda):
+        _weight_grad(g2, x2, into)
+        return
+    key, side = _wgrad_side(g2.device)
+    side.wait_stream(torch.cuda.current_stream())
+    g2.record_stream(side)  # both die when this backward node returns: keep their memory until the side stream is done
+    x2.record_stream(side)
+    with torch.cuda.stream(side):
+        _weight_grad(g2, x2, into)
+    _wgrad_pending.add(key)
 
 
 def _weight_grad(g2, x2, into=None):
@@ -109,8 +143,10 @@ class PointwiseConvRows(Function):
                 d_rows = (g2 @ w).view_as(rows)
             if ctx.needs_input_grad[1]:
                 into = ctx.wparam.grad.view(w.shape) if runtime.grads_in_place and _is_grad_buffer(ctx.wparam) else None
-                d_w = _weight_grad(g2, rows.reshape(-1, rows.shape[-1]), into)
-                d_w = d_w.unsqueeze(-1) if d_w is not None else None
+                if into is not None:
+                    _weight_grad_into(g2, rows.reshape(-1, rows.shape[-1]), into)
+                else:
+                    d_w = _weight_grad(g2, rows.reshape(-1, rows.shape[-1])).unsqueeze(-1)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             d_b = g2.sum(0)
         return d_rows, d_w, d_b, None

@@ -88,10 +88,12 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #     'always' forces it for every shape, False restores the per-query gather kernel everywhere.
 #   own_gemm: the 1x1 convolutions (forward and data gradient) run on the package's TMA + tcgen05 TF32 GEMM
 #     (csrc/gemm.cu), whose epilogue also emits the BatchNorm statistics; False: cuBLAS through torch.
+#   wgrad_side_stream: with grads_in_place, the weight-gradient GEMMs run on a side stream (models/blocks.py); the
+#     training loop joins them with distributed.FlatParameters.reduce() / blocks.join_weight_grads() before the optimiser.
 #   staged_tiles_backward: same for the backward pass (measured slower than the segmented reduction: off).
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
                     "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
-                    "staged_tiles_backward": False, "own_gemm": True})
+                    "staged_tiles_backward": False, "own_gemm": True, "wgrad_side_stream": True})
 
 
 def reset_config():

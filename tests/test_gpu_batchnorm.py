@@ -128,16 +128,18 @@ def test_model_channel_last_matches_channel_major(cuda_device):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def test_in_place_parameter_gradients_match_autograd_accumulation(cuda_device):
+@pytest.mark.parametrize("num_points", [2048, 4096])  # 4 x 4096 = 16384 rows: the split-K weight-gradient path
+def test_in_place_parameter_gradients_match_autograd_accumulation(cuda_device, num_points):
     """runtime.grads_in_place: BN and 1x1-conv backward add the parameter gradients straight into the (flat) gradient
-    buffers and return None to autograd — the buffers must equal what autograd's own accumulation produces."""
+    buffers and return None to autograd — the buffers must equal what autograd's own accumulation produces.  The
+    weight-gradient GEMMs run on a side stream then; FlatParameters.reduce() joins them."""
     from deep3dpointclouddenoising_b200 import distributed, synthetic
     from deep3dpointclouddenoising_b200.utils.config import runtime
     import bench
-    model, criterion, cfg = bench.build_model("pospool", 2048)
+    model, criterion, cfg = bench.build_model("pospool", num_points)
     model = model.to(cuda_device)
     flat = distributed.FlatParameters(model)
-    batch = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(9, 4, 2048, ragged=True)]
+    batch = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(9, 4, num_points, ragged=True)]
     grads = []
     try:
         for flag in (False, True, True):  # twice in place: the second pass checks that the buffers really accumulate
@@ -146,6 +148,7 @@ def test_in_place_parameter_gradients_match_autograd_accumulation(cuda_device):
                 flat.zero()
             loss = criterion(model(batch[0], batch[1], batch[2]).transpose(1, 2), batch[3], batch[1])
             loss.backward()
+            flat.reduce()  # world size 1: only the join of the side-stream weight gradients
             grads.append(flat.flat.clone())
     finally:
         runtime.grads_in_place = False

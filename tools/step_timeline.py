@@ -40,6 +40,7 @@ def main():
         bucket.zero()
         loss = criterion(model(batch[0], batch[1], batch[2]).transpose(1, 2), batch[3], batch[1])
         loss.backward()
+        bucket.reduce()
         torch.nn.utils.clip_grad_norm_([bucket.param], 10)
         opt.step()
         return loss
@@ -84,14 +85,33 @@ def main():
           f"(median {sorted(g[0] for g in gaps)[len(gaps) // 2]:.1f} us)")
     for g, a, b, at in sorted(gaps, reverse=True)[:args.gaps]:
         print(f"    {g:7.1f} us at +{at / 1e3:6.3f} ms  after {a}  before {b}")
-    agg = defaultdict(lambda: [0.0, 0])
+    # exposure: time during which a kernel runs ALONE (nothing else on the device) — what shortening it would save — and
+    # the time the device sits idle between kernels
+    points = sorted({e["ts"] for e in ev} | {e["ts"] + e["dur"] for e in ev})
+    alone = defaultdict(float)
+    idle = 0.0
+    starts = sorted(ev, key=lambda e: e["ts"])
+    active, si = [], 0
+    for a, b in zip(points, points[1:]):
+        while si < len(starts) and starts[si]["ts"] <= a:
+            active.append(starts[si])
+            si += 1
+        active = [e for e in active if e["ts"] + e["dur"] > a]
+        if not active:
+            idle += b - a
+        elif len(active) == 1:
+            alone[active[0]["name"]] += b - a
+    print(f"device idle inside the step: {idle / 1e3:.3f} ms; time with exactly one kernel running: {sum(alone.values()) / 1e3:.3f} ms")
+    agg = defaultdict(lambda: [0.0, 0, 0.0])
     for e in ev:
         k = e["name"].replace("(anonymous namespace)::", "").replace("void ", "")[:90]
         agg[k][0] += e["dur"]
         agg[k][1] += 1
-    print("per kernel (this replay):")
-    for k, (d, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.top]:
-        print(f"  {d / 1e3:7.3f} ms x{n:<4d} {k}")
+    for name, d in alone.items():
+        agg[name.replace("(anonymous namespace)::", "").replace("void ", "")[:90]][2] += d
+    print("per kernel (this replay): total, launches, of which running alone")
+    for k, (d, n, al) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.top]:
+        print(f"  {d / 1e3:7.3f} ms x{n:<4d} alone {al / 1e3:6.3f} ms  {k}")
 
 
 if __name__ == "__main__":
