@@ -659,6 +659,99 @@ bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x
     }
 }
 
+// ---- backward reduction, second generation: row-range partials + a parallel finaliser (no tickets, no serial tail) ----
+// A block streams a contiguous range of rows; a thread keeps ONE float4 channel group (block size = a multiple of the
+// group count, so consecutive threads read consecutive 16-byte pieces of the row-major matrix — fully coalesced) and
+// accumulates its rows in registers; the row lanes of the block are combined in shared memory and the block writes one
+// fp32 partial per channel.  bn_bwd_finalize_kernel adds the <= 592 partials per channel in fp64 in a fixed order.
+constexpr int kRedBlocks = 148 * 4;
+
+struct RedGeom {
+  int c4, lanes, threads;
+};
+__host__ __device__ inline RedGeom red_geom(int C) {
+  RedGeom g;
+  g.c4 = C / 4;
+  g.lanes = 256 / g.c4 > 0 ? 256 / g.c4 : 1;
+  g.threads = g.c4 * g.lanes;
+  return g;
+}
+
+__global__ void __launch_bounds__(640)
+bn_bwd_partial_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, long long R, int c4, int lanes, long long rows_per_block, int relu,
+                         float* __restrict__ partial /* (gridDim.x, 2, 4 * c4) */) {
+  extern __shared__ float4 red_sh[];  // [2][lanes][c4]
+  const int group = threadIdx.x % c4, rl = threadIdx.x / c4;
+  const long long row_beg = (long long)blockIdx.x * rows_per_block;
+  const long long row_end = row_beg + rows_per_block < R ? row_beg + rows_per_block : R;
+  float4 m, is, scale, offset;
+  cl_scale_offset(gamma, beta, mean, invstd, group, m, is, scale, offset);
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1;
+  const float4* dy4 = reinterpret_cast<const float4*>(dy);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long r = row_beg + rl; r < row_end; r += 4LL * lanes) {  // 8 independent loads in flight; predicated tail
+    float4 dv[4], xv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r + (long long)j * lanes < row_end) {
+        const long long e = (r + (long long)j * lanes) * c4 + group;
+        dv[j] = __ldg(dy4 + e);
+        xv[j] = __ldg(x4 + e);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (r + (long long)j * lanes < row_end) {
+        const long long e = (r + (long long)j * lanes) * c4 + group;
+        const float4 d = cl_masked_dy(dv[j], xv[j], y, e, relu, scale, offset);
+        s1.x += d.x; s1.y += d.y; s1.z += d.z; s1.w += d.w;
+        s2.x += d.x * (xv[j].x - m.x); s2.y += d.y * (xv[j].y - m.y); s2.z += d.z * (xv[j].z - m.z); s2.w += d.w * (xv[j].w - m.w);
+      }
+  }
+  red_sh[rl * c4 + group] = s1;
+  red_sh[(lanes + rl) * c4 + group] = s2;
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < lanes; ++k) {  // fixed order: deterministic
+      const float4 a = red_sh[k * c4 + group], b = red_sh[(lanes + k) * c4 + group];
+      s1.x += a.x; s1.y += a.y; s1.z += a.z; s1.w += a.w;
+      s2.x += b.x; s2.y += b.y; s2.z += b.z; s2.w += b.w;
+    }
+    float4* dst = reinterpret_cast<float4*>(partial) + (size_t)blockIdx.x * 2 * c4;
+    dst[group] = s1;
+    dst[c4 + group] = s2;
+  }
+}
+
+constexpr int kRedFinCh = 8, kRedFinSlices = 32;
+
+__global__ void __launch_bounds__(kRedFinCh * kRedFinSlices)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, const float* __restrict__ invstd, int accumulate,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ sums) {
+  __shared__ double red[2][kRedFinSlices][kRedFinCh];
+  const int cx = threadIdx.x % kRedFinCh, ty = threadIdx.x / kRedFinCh;
+  const int c = min(blockIdx.x * kRedFinCh + cx, C - 1);
+  double a1 = 0.0, a2 = 0.0;
+  for (int t = ty; t < nblk; t += kRedFinSlices) {
+    a1 += (double)partial[(size_t)t * 2 * C + c];
+    a2 += (double)partial[(size_t)t * 2 * C + C + c];
+  }
+  red[0][ty][cx] = a1;
+  red[1][ty][cx] = a2;
+  __syncthreads();
+  if (ty != 0 || blockIdx.x * kRedFinCh + cx >= C) return;
+  double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < kRedFinSlices; ++k) { t1 += red[0][k][cx]; t2 += red[1][k][cx]; }
+  const double g2 = t2 * (double)invstd[c];
+  // accumulate != 0: dgamma / dbeta ARE the parameters' gradient buffers (+=, one thread per channel: no race)
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)t1;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)g2;
+  sums[2 * c] = (float)t1;
+  sums[2 * c + 1] = (float)g2;
+}
+
 constexpr int kClBlocks = 148 * 4;  // four 8-warp blocks per SM, 8 independent 16-byte loads in flight per thread;
                                     // more splits only lengthen the finaliser's chain of L2 round trips
 
@@ -704,7 +797,13 @@ static size_t partial_doubles(int C) {
 
 size_t d3d_bn_act_workspace_bytes(int C) {
   if (C <= 0) return 0;
-  return align256((size_t)C * 2 * sizeof(float)) + align256(partial_doubles(C) * sizeof(double)) + align256((size_t)C * sizeof(unsigned));
+  return align256((size_t)C * 2 * sizeof(float)) + align256(partial_doubles(C) * sizeof(double)) +
+         align256((size_t)C * sizeof(unsigned)) + align256((size_t)kRedBlocks * 2 * C * sizeof(float));
+}
+
+static float* row_partials(void* ws, int C) {  // after [sums][partials][counters]: (kRedBlocks, 2, C) fp32
+  return (float*)((unsigned char*)ws + align256((size_t)C * 2 * sizeof(float)) + align256(partial_doubles(C) * sizeof(double)) +
+                  align256((size_t)C * sizeof(unsigned)));
 }
 
 static void carve(void* ws, int C, float** sums, double** partials, unsigned** counters) {
@@ -841,9 +940,26 @@ int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const flo
   float* sums; double* partials; unsigned* counters;
   carve(ws, C, &sums, &partials, &counters);
   const ClGeom g = cl_geom(C);
-  const int S = cl_splits(g, R);
-  bn_bwd_reduce_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, R, C, S, relu,
-                                                                accumulate_param_grads, dgamma, dbeta, sums, partials, counters);
+  const RedGeom rg = red_geom(C);
+  if (rg.threads <= 640) {
+    long long nblk = (R + 4LL * rg.lanes - 1) / (4LL * rg.lanes);  // at least four rows per thread
+    if (nblk > kRedBlocks) nblk = kRedBlocks;
+    const long long rows_per_block = (R + nblk - 1) / nblk;
+    nblk = (R + rows_per_block - 1) / rows_per_block;
+    float* part = row_partials(ws, C);
+    bn_bwd_partial_cl_kernel<<<(unsigned)nblk, rg.threads, (size_t)rg.threads * 32, st>>>(dy, x, y, gamma, beta, save_mean,
+                                                                                       save_invstd, R, rg.c4, rg.lanes,
+                                                                                       rows_per_block, relu, part);
+    bn_bwd_finalize_kernel<<<d3d_ceil_div(C, kRedFinCh), kRedFinCh * kRedFinSlices, 0, st>>>(part, (int)nblk, C, save_invstd,
+                                                                                          accumulate_param_grads, dgamma,
+                                                                                          dbeta, sums);
+    d3d_note_launches(1);
+  } else {
+    const int S = cl_splits(g, R);
+    bn_bwd_reduce_cl_kernel<<<dim3(g.gx, S), kClThreads, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd, R, C, S, relu,
+                                                                  accumulate_param_grads, dgamma, dbeta, sums, partials,
+                                                                  counters);
+  }
   const long long apply_threads = ((R + kApplyRows - 1) / kApplyRows) * g.c4;
   bn_bwd_apply_cl_kernel<<<(unsigned)d3d_ceil_div(apply_threads, 256), 256, 0, st>>>(dy, x, y, gamma, beta, save_mean, save_invstd,
                                                                                     sums, g.c4, R, 1.0f / (float)R, relu, training,

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--precision", default="fp32")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--gaps", type=int, default=15)
+    ap.add_argument("--list", default=None, help="comma-separated substrings: print every launch of matching kernels (start, us, grid)")
     args = ap.parse_args()
     for kv in filter(None, os.environ.get("D3D_RUNTIME", "").split(",")):
         k, v = kv.split("=")
@@ -85,6 +86,10 @@ def main():
           f"(median {sorted(g[0] for g in gaps)[len(gaps) // 2]:.1f} us)")
     for g, a, b, at in sorted(gaps, reverse=True)[:args.gaps]:
         print(f"    {g:7.1f} us at +{at / 1e3:6.3f} ms  after {a}  before {b}")
+    if args.list:
+        for pat in args.list.split(","):
+            sel = [e for e in ev if pat in e["name"]]
+            print(f"launches of *{pat}*: " + " ".join(f"{(e['ts'] - t0) / 1e3:.2f}:{e['dur']:.1f}us:{e['args'].get('grid', '')}" for e in sel))
     # exposure: time during which a kernel runs ALONE (nothing else on the device) — what shortening it would save — and
     # the time the device sits idle between kernels
     points = sorted({e["ts"] for e in ev} | {e["ts"] + e["dur"] for e in ev})
