@@ -71,16 +71,80 @@ class FlatGradAllReduce:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._done_upto = total
 
     def zero(self):
         self.flat.zero_()  # grads stay views of the bucket (use instead of optimizer.zero_grad(set_to_none=True))
+        self._done_upto = self.flat.numel()  # everything at or above this offset has been all-reduced in this step
+
+    def _avg(self, lo, hi):
+        """Average of the bucket slice [lo, hi) over the ranks (sum all-reduce; the division by the world size is folded
+        into the collective where the backend can: NCCL's AVG)."""
+        if hi <= lo:
+            return
+        piece = self.flat[lo:hi]
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(piece, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+            piece.div_(self.world)
+
+    def overlap_with_backward(self, module):
+        """Splits the one all-reduce into contiguous slices of the bucket, issued DURING backward: the backbone marks
+        the points where backward leaves a stage (fused.stage_marker); every parameter laid out behind that stage's first
+        parameter is final then (parameters sit in the bucket in forward order, backward runs in reverse), so that tail
+        of the bucket goes out on a communication stream while the earlier stages still compute.  reduce() sends what
+        is left and joins.  ref: train_dist.py:375 (DistributedDataParallel overlaps its buckets the same way)."""
+        from . import fused
+        if self.world <= 1:
+            return self
+        starts = {}
+        off = 0
+        ids = {id(p): i for i, p in enumerate(self.params)}
+        offsets = []
+        for p in self.params:
+            offsets.append(off)
+            off += self._padded(p)
+        for tag, sub in fused.stage_modules(module).items():
+            first = next((p for p in sub.parameters() if p.requires_grad and id(p) in ids), None)
+            if first is not None:
+                starts[tag] = offsets[ids[id(first)]]
+        self._stage_start = starts
+        self._comm = torch.cuda.Stream() if self.flat.is_cuda else None
+        fused.set_stage_callback(self._stage_done)
+        return self
+
+    def _padded(self, p):
+        return p.numel()
+
+    def _stage_done(self, tag):
+        lo = getattr(self, "_stage_start", {}).get(tag)
+        if lo is None or lo >= self._done_upto:
+            return
+        hi, self._done_upto = self._done_upto, lo
+        if self._comm is None:
+            self._avg(lo, hi)
+            return
+        from .models.blocks import wait_weight_grads
+        self._comm.wait_stream(torch.cuda.current_stream())
+        wait_weight_grads(self._comm)  # this stage's weight gradients come from the side stream
+        with torch.cuda.stream(self._comm):
+            self._avg(lo, hi)
 
     def reduce(self):
         from .models.blocks import join_weight_grads
         join_weight_grads()  # weight gradients computed on the side stream are part of the bucket
         if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(self.world)
+            upto = getattr(self, "_done_upto", self.flat.numel())
+            comm = getattr(self, "_comm", None)
+            if comm is not None and upto < self.flat.numel():
+                comm.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(comm):
+                    self._avg(0, upto)
+                torch.cuda.current_stream().wait_stream(comm)
+            else:
+                self._avg(0, upto)
+            self._done_upto = 0
 
 
 class FlatParameters(FlatGradAllReduce):
@@ -110,3 +174,7 @@ class FlatParameters(FlatGradAllReduce):
         self.param = torch.nn.Parameter(flat_param)
         self.param.grad = self.flat
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self._done_upto = total
+
+    def _padded(self, p):
+        return (p.numel() + 3) // 4 * 4

@@ -20,6 +20,48 @@ from . import ops
 from .utils.config import runtime
 
 
+# ---- backward stage markers (data-parallel gradient overlap, distributed.FlatParameters.overlap_with_backward) ----------
+_stage_callback = [None]
+
+
+def set_stage_callback(fn):
+    """fn(tag) is called during backward when the gradient has passed the marker `tag` (None switches it off)."""
+    _stage_callback[0] = fn
+
+
+class _StageMarker(Function):
+    @staticmethod
+    def forward(ctx, x, tag):
+        ctx.tag = tag
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        if _stage_callback[0] is not None:
+            _stage_callback[0](ctx.tag)
+        return grad, None
+
+
+def stage_marker(x, tag):
+    """Identity in the forward pass; in the backward pass it reports that everything computed FROM x in the forward pass
+    has finished its backward.  Free when no callback is registered (single-GPU runs skip the autograd node entirely)."""
+    if _stage_callback[0] is None or not torch.is_grad_enabled() or not x.requires_grad:
+        return x
+    return _StageMarker.apply(x, tag)
+
+
+def stage_modules(model):
+    """tag -> the first module whose parameters are final once the marker `tag` fires (markers: ResNet._forward)."""
+    bb = getattr(model, "backbone", model)
+    out = {}
+    for tag in ("layer2", "layer3", "layer4"):
+        if hasattr(bb, tag):
+            out[tag] = getattr(bb, tag)
+    if hasattr(model, "segmentation_head"):
+        out["head"] = model.segmentation_head
+    return out
+
+
 def _is_grad_buffer(p):
     """A parameter whose gradient buffer exists and can be written by a kernel (runtime.grads_in_place)."""
     g = getattr(p, "grad", None)

@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 
 from ... import neighbors as _neighbors
+from ...fused import stage_marker
 from ...utils.config import runtime
 from ...pt_custom_ops.pt_utils import MaskedMaxPool
 from ..blocks import conv_bn
@@ -108,7 +109,11 @@ class ResNet(nn.Module):
         xyz, mask, features = self.btnk1(xyz, mask, features)
         end_points['res1_xyz'], end_points['res1_mask'], end_points['res1_features'] = xyz, mask, features
         for stage in range(4):
-            xyz, mask, features = getattr(self, f"layer{stage + 1}")(xyz, mask, features)
+            # backward leaves layer{stage+1} when the gradient passes this marker: with data parallelism the gradients of
+            # the stage (and of everything after it) go to the all-reduce then (distributed.overlap_with_backward)
+            xyz, mask, features = getattr(self, f"layer{stage + 1}")(xyz, mask, stage_marker(features, f"layer{stage + 1}"))
             tag = f"res{stage + 2}"
             end_points[tag + '_xyz'], end_points[tag + '_mask'], end_points[tag + '_features'] = xyz, mask, features
+        # the head's first op consumes res5: its backward is the head's last
+        end_points['res5_features'] = stage_marker(end_points['res5_features'], "head")
         return end_points

@@ -48,6 +48,12 @@ def join_weight_grads():
         _wgrad_pending.discard(key)
 
 
+def wait_weight_grads(stream):
+    """Makes `stream` wait for the weight gradients enqueued so far, without ending the fork (the join stays pending)."""
+    for key in list(_wgrad_pending):
+        stream.wait_stream(_wgrad_streams[key])
+
+
 def _weight_grad_into(g2, x2, into):
     """dW accumulated into the parameter's gradient buffer.  The weight gradient of a layer is a leaf of the backward
     graph — nothing downstream waits for it before the optimiser — so it runs on a side stream, concurrently with the data

@@ -107,3 +107,72 @@ def test_flat_parameters_match_per_tensor_adam_and_clipping():
     for a, b in zip(flat_model.parameters(), ref.parameters()):
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
     assert set(flat_model.state_dict()) == set(ref.state_dict())
+
+
+class _FakeUNet(torch.nn.Module):
+    """CPU stand-in with the stage layout of the U-Net (backbone.layer1..4, segmentation_head) and the same markers."""
+
+    def __init__(self):
+        super().__init__()
+        bb = torch.nn.Module()
+        bb.conv1 = torch.nn.Conv1d(3, 6, 1)
+        for i in range(1, 5):
+            setattr(bb, f"layer{i}", torch.nn.Conv1d(6, 6, 1))
+        self.backbone = bb
+        self.segmentation_head = torch.nn.Sequential(torch.nn.Conv1d(12, 5, 1), torch.nn.Conv1d(5, 3, 1))
+
+    def forward(self, x):
+        from deep3dpointclouddenoising_b200.fused import stage_marker
+        f = self.backbone.conv1(x)
+        skips = []
+        for i in range(1, 5):
+            f = getattr(self.backbone, f"layer{i}")(stage_marker(f, f"layer{i}")).relu()
+            skips.append(f)
+        last = stage_marker(skips[-1], "head")
+        return self.segmentation_head(torch.cat([last, skips[0]], 1))
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from deep3dpointclouddenoising_b200 import distributed, fused
+    distributed.init("gloo")
+    torch.manual_seed(0)
+    model = _FakeUNet()
+    flat = distributed.FlatParameters(model).overlap_with_backward(model)
+    calls = []
+    inner = fused._stage_callback[0]
+    fused.set_stage_callback(lambda tag: (calls.append((tag, flat._done_upto)), inner(tag)))
+    torch.manual_seed(100 + rank)
+    x = torch.randn(4, 3, 32)
+    for step in range(2):
+        flat.zero()
+        model(x).square().sum().backward()
+        flat.reduce()
+    fused.set_stage_callback(None)
+    torch.manual_seed(0)
+    ref = _FakeUNet()
+    ref(x).square().sum().backward()
+    local = torch.cat([torch.nn.functional.pad(p.grad.flatten(), (0, (-p.numel()) % 4)) for p in ref.parameters()])
+    torch.save({"flat": flat.flat.clone(), "local": local, "calls": calls}, os.path.join(out_dir, f"ov{rank}.pt"))
+    torch.distributed.destroy_process_group()
+
+
+def test_gradient_allreduce_overlapped_with_backward(tmp_path):
+    """distributed.FlatParameters.overlap_with_backward: the bucket goes out in slices as backward leaves the stages
+    (head first, then layer4, 3, 2, the rest in reduce()); the result equals the plain average of the local gradients."""
+    world = 2
+    for attempt in range(3):
+        try:
+            mp.spawn(_overlap_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+            break
+        except Exception:
+            if attempt == 2:
+                raise
+    r0, r1 = [torch.load(tmp_path / f"ov{r}.pt") for r in range(world)]
+    assert torch.equal(r0["flat"], r1["flat"])
+    torch.testing.assert_close(r0["flat"], (r0["local"] + r1["local"]) / 2, rtol=1e-5, atol=1e-7)
+    tags = [t for t, _ in r0["calls"]]
+    assert tags[:4] == ["head", "layer4", "layer3", "layer2"], tags  # backward order; layer1's marker has no slice of its own
+    ends = [e for _, e in r0["calls"][:4]]
+    assert ends == sorted(ends, reverse=True) and ends[0] == r0["flat"].numel()  # contiguous slices from the tail down
