@@ -440,7 +440,7 @@ def main():
     cfgmod.runtime.pseudo_grid_precision = args.pseudo_grid_precision
     for kv in filter(None, os.environ.get("D3D_RUNTIME", "").split(",")):  # experiments: D3D_RUNTIME=own_gemm=0,staged_tiles=0
         k, v = kv.split("=")
-        cfgmod.runtime[k] = {"0": False, "1": True}.get(v, v)
+        cfgmod.runtime[k] = {"0": False, "1": True}.get(v, int(v) if v.isdigit() else v)
 
     model, criterion, cfg = build_model(args.operator, args.num_points)
     model = model.to(dev)

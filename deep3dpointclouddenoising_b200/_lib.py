@@ -60,6 +60,8 @@ SIGNATURES = {
     "d3d_bn_act_cl_fwd": (_i, [_vp] * 7 + [_ll, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_gemm_row_tiles": (_i, [_ll]),
     "d3d_gemm_tf32": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp]),
+    "d3d_wgrad_workspace_bytes": (_sz, [_ll, _i, _i]),
+    "d3d_wgrad_tf32": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp, _sz, _vp]),
     "d3d_bn_finalize": (_i, [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "d3d_bn_apply_cl": (_i, [_vp] * 6 + [_ll, _i, _i, _vp, _vp]),
     "d3d_bn_act_cl_bwd": (_i, [_vp] * 7 + [_ll, _i, _i, _i] + [_vp] * 4 + [_i, _vp, _sz, _vp]),

@@ -56,7 +56,8 @@ EncodeTiledFn encode_fn() {
 
 // row-major fp32 matrix [rows x cols], leading dimension ld (floats); box = [box_rows x 32 floats], 128-byte swizzle;
 // out-of-range elements read as zero (tails in M, N and K need no special code)
-int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, long long ld, int box_rows) {
+int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, long long ld, int box_rows,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return D3D_ERR_UNSUPPORTED;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -64,7 +65,7 @@ int make_map(CUtensorMap* m, const float* p, long long rows, long long cols, lon
   const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : D3D_ERR_BAD_ARG;
 }
 
@@ -325,6 +326,203 @@ bn_finalize_kernel(const float* __restrict__ stats, int tiles, long long R, int 
   if (c == 0 && num_batches) *num_batches += 1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient  dW[Cout x Cin] (+)= dY[R x Cout]^T . X[R x Cin]   (the reduction runs over the R rows)
+//
+// Both operands are "MN-major" for the tensor core: the M index (Cout) and the N index (Cin) are the contiguous ones
+// in memory, the K index (row) strides.  For 32-bit MN-major operands tcgen05 knows ONE shared-memory layout, the
+// 128-byte swizzle with 32-byte atomicity (descriptor layout type 1; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows (K)
+// 128 bytes apart, the four 32-byte chunks of a row permuted by (row mod 4), 4-row groups 512 bytes apart (SBO), the
+// next 32 channels one TMA box further (LBO).  A box of [32 rows x 32 channels] is one column block of that tile.  M tile = 128 output channels = 4 boxes, N tile <= 160 input
+// channels = 5 boxes, one stage = 32 rows.  The rows are split over the CTAs (split-K): every CTA accumulates its row
+// range in TMEM and writes an fp32 partial; wgrad_reduce_kernel adds the partials in a fixed order (deterministic) and
+// stores or accumulates into the gradient buffer.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWBK = 32;                                  // rows per stage
+constexpr int kWBoxBytes = kWBK * 128;                    // one [32 rows x 32 channels] box
+constexpr int kWNMaxBoxes = 5;                            // N tile <= 160 input channels
+constexpr unsigned kWStageBytes = (4 + kWNMaxBoxes) * kWBoxBytes;  // 36 KB
+constexpr int kWStages = 3;                               // 3 x 36 KB: two CTAs per SM
+constexpr int kWThreads = 192;                            // warp 0 producer, warp 1 MMA, warps 2-5 epilogue
+
+int make_map_rows(CUtensorMap* m, const float* p, long long rows, long long cols) {  // box = [kWBK rows x 32 floats]
+  return make_map(m, p, rows, cols, cols, kWBK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+// MN-major 32-bit operand, SWIZZLE_128B_BASE32B: LBO = byte distance between 32-channel column blocks, SBO = 512
+// (4 rows of 128 bytes)
+__device__ __forceinline__ unsigned long long sw128_mn_desc(unsigned addr, unsigned lbo) {
+  return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)((lbo >> 4) & 0x3fffu) << 16) |
+         ((unsigned long long)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+struct WgradArgs {
+  float* partial;       // (splits, Mdim, Ndim)
+  long long R, rows_per_split;
+  int Cout, Cin, bn;    // here: Cout = the M-side channel count, Cin = the N-side one (the host may swap dY and X so that
+                        // the operand with fewer 128-channel tiles sits on the M side); bn: N tile (multiple of 16, <= 160)
+  int n_boxes;          // 32-channel boxes per N tile
+  float* direct;        // one split only: the epilogue writes dW itself (no partials, no reduction kernel)
+  int direct_transposed, direct_accumulate;
+};
+
+__global__ void __launch_bounds__(kWThreads, 2)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgradArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) unsigned long long bars[2 * kWStages + 1];
+  __shared__ unsigned tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * g.bn, split = blockIdx.z;
+  const long long r_beg = (long long)split * g.rows_per_split;
+  const long long r_end = r_beg + g.rows_per_split < g.R ? r_beg + g.rows_per_split : g.R;
+  const int nk = (int)((r_end - r_beg + kWBK - 1) / kWBK);
+  const unsigned full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kWStages]), tmem_full = smem_u32(&bars[2 * kWStages]);
+  const unsigned tmem_cols = g.bn <= 32 ? 32u : (g.bn <= 64 ? 64u : (g.bn <= 128 ? 128u : 256u));
+
+  if (tid == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init_fence();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer: 4 boxes of dY (128 output channels) + n_boxes of X per stage ----
+      const unsigned tx = (unsigned)(4 + g.n_boxes) * kWBoxBytes;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % kWStages;
+        mbar_wait_short(empty0 + 8 * s, (unsigned)(((it / kWStages) & 1) ^ 1));
+        const unsigned sa = smem_u32(smem + (size_t)s * kWStageBytes), sb = sa + 4 * kWBoxBytes;
+        mbar_arrive_expect_tx(full0 + 8 * s, tx);
+        // rows beyond this split's range are NOT read: the box is clipped by loading a second, zero... (ranges are
+        // multiples of kWBK except the last split, whose tail rows are out of bounds of the tensor and read as zero)
+        const int row = (int)(r_beg + (long long)it * kWBK);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(sa + b * kWBoxBytes, &map_dy, m0 + 32 * b, row, full0 + 8 * s);
+        for (int b = 0; b < g.n_boxes; ++b) tma_load_2d(sb + b * kWBoxBytes, &map_x, n0 + 32 * b, row, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ----
+      // D = f32, A = B = tf32, both MN-major, N = bn, M = 128
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((unsigned)(g.bn >> 3) << 17) |
+                             ((128u >> 4) << 24);
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % kWStages;
+        mbar_wait_short(full0 + 8 * s, (unsigned)((it / kWStages) & 1));
+        tc_fence_after();
+        const unsigned sa = smem_u32(smem + (size_t)s * kWStageBytes), sb = sa + 4 * kWBoxBytes;
+#pragma unroll
+        for (int kk = 0; kk < kWBK / 8; ++kk)
+          mma_tf32(tmem_base, sw128_mn_desc(sa + kk * 1024, kWBoxBytes), sw128_mn_desc(sb + kk * 1024, kWBoxBytes), idesc,
+                   (it > 0 || kk > 0) ? 1u : 0u);
+        mma_commit(empty0 + 8 * s);
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    // ---- epilogue: thread = output channel (TMEM lane); partial[split][cout][cin] ----
+    mbar_wait_short(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3, r = q * 32 + lane;
+    const int cout = m0 + r;
+    float* prow = g.partial + ((size_t)split * g.Cout + (cout < g.Cout ? cout : 0)) * g.Cin + n0;
+    for (int c16 = 0; c16 < g.bn; c16 += 16) {
+      unsigned v[16];
+      if (nk > 0) {
+        tmem_ld16(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)c16, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (g.direct != nullptr) {
+        if (cout < g.Cout) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c16 + j;
+            if (n < g.Cin) {
+              float* dst = g.direct_transposed ? g.direct + (size_t)n * g.Cout + cout : g.direct + (size_t)cout * g.Cin + n;
+              *dst = (g.direct_accumulate ? *dst : 0.f) + __uint_as_float(v[j]);
+            }
+          }
+        }
+      } else if (cout < g.Cout) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n0 + c16 + 4 * j < g.Cin)  // Cin % 4 == 0
+            *reinterpret_cast<uint4*>(prow + c16 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// Sum of the split partials into dW, fixed order (deterministic).  Block = 64 consecutive elements x 4 split lanes: a
+// lane adds every fourth partial (coalesced 256-byte rows), the four lane sums are combined through shared memory.
+// transposed: the partials are (Cin x Cout) — dY and X were swapped in the GEMM — while dW is (Cout x Cin).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Cin, int transposed, int accumulate,
+                    float* __restrict__ dw) {
+  __shared__ float sh[4][64];
+  const long long n = (long long)Cout * Cin;
+  const int e = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const long long i = (long long)blockIdx.x * 64 + e;  // index into the partial's own layout
+  float a0 = 0.f, a1 = 0.f;
+  if (i < n) {
+    int s = sl;
+    for (; s + 4 < splits; s += 8) {
+      a0 += __ldg(partial + (size_t)s * n + i);
+      a1 += __ldg(partial + (size_t)(s + 4) * n + i);
+    }
+    if (s < splits) a0 += __ldg(partial + (size_t)s * n + i);
+  }
+  sh[sl][e] = a0 + a1;
+  __syncthreads();
+  if (sl != 0 || i >= n) return;
+  const float v = (sh[0][e] + sh[1][e]) + (sh[2][e] + sh[3][e]);
+  long long o = i;
+  if (transposed) {  // i = ci * Cout + co
+    const long long ci = i / Cout, co = i - ci * Cout;
+    o = co * Cin + ci;
+  }
+  dw[o] = (accumulate ? dw[o] : 0.f) + v;
+}
+
+struct WgradPlan {
+  bool swapped;   // X on the M side, dY on the N side (the partials are then Cin x Cout)
+  int m_dim, n_dim, bn, splits;
+};
+
+WgradPlan wgrad_plan(long long R, int Cout, int Cin) {
+  auto bn_of = [](int n) { const int n16 = (n + 15) & ~15; return n16 < 160 ? n16 : 160; };
+  // floats read per row of the reduction: every N tile re-reads the M operand and vice versa
+  auto traffic = [&](int m, int n) { return (long long)((n + bn_of(n) - 1) / bn_of(n)) * m + (long long)((m + kBM - 1) / kBM) * n; };
+  WgradPlan p;
+  p.swapped = traffic(Cin, Cout) < traffic(Cout, Cin);
+  p.m_dim = p.swapped ? Cin : Cout;
+  p.n_dim = p.swapped ? Cout : Cin;
+  p.bn = bn_of(p.n_dim);
+  const long long tiles = (long long)((p.m_dim + kBM - 1) / kBM) * ((p.n_dim + p.bn - 1) / p.bn);
+  long long s = (148 * 2 + tiles - 1) / tiles;              // about two CTAs per SM
+  const long long cap = (16LL << 20) / (4LL * Cout * Cin);  // the partials are re-read by the reduction: <= 16 MB of them
+  if (s > cap) s = cap;
+  const long long max_s = (R + 4 * kWBK - 1) / (4 * kWBK);  // at least four stages per split
+  if (s > max_s) s = max_s;
+  if (s < 1 || tiles >= 96) s = 1;  // enough tiles to fill the machine: one split, the epilogue writes dW directly
+  p.splits = (int)s;
+  return p;
+}
+
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace
@@ -374,6 +572,53 @@ int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, lo
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
   gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma0, ma1, mb, g);
   d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
+/* dW (Cout x Cin) = or += dY (R x Cout)^T . X (R x Cin), fp32 in / out, TF32 tensor cores, split over the rows with a
+ * deterministic reduction.  Workspace: d3d_wgrad_workspace_bytes.  Requires Cout % 4 == 0, Cin % 4 == 0, aligned pointers. */
+size_t d3d_wgrad_workspace_bytes(long long R, int Cout, int Cin) {
+  if (R <= 0 || Cout <= 0 || Cin <= 0) return 0;
+  return (size_t)wgrad_plan(R, Cout, Cin).splits * Cout * Cin * sizeof(float);
+}
+
+int d3d_wgrad_tf32(const float* dY, const float* X, float* dW, long long R, int Cout, int Cin, int accumulate, void* ws,
+                   size_t ws_bytes, void* stream) {
+  D3D_REQUIRE(dY && X && dW && R > 0 && Cout > 0 && Cin > 0);
+  if (Cout % 4 || Cin % 4 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || R > 0x7fffffffLL) return D3D_ERR_UNSUPPORTED;
+  if (!ws || ws_bytes < d3d_wgrad_workspace_bytes(R, Cout, Cin)) return D3D_ERR_WORKSPACE;
+  const WgradPlan plan = wgrad_plan(R, Cout, Cin);
+  WgradArgs g{};
+  g.bn = plan.bn;
+  g.n_boxes = (g.bn + 31) / 32;
+  g.Cout = plan.m_dim; g.Cin = plan.n_dim; g.R = R; g.partial = (float*)ws;
+  long long rps = (R + plan.splits - 1) / plan.splits;
+  rps = (rps + kWBK - 1) / kWBK * kWBK;  // whole stages, so that a split never reads another split's rows
+  g.rows_per_split = rps;
+  const int used = (int)((R + rps - 1) / rps);
+  if (used == 1) {
+    g.direct = dW;
+    g.direct_transposed = plan.swapped ? 1 : 0;
+    g.direct_accumulate = accumulate;
+  }
+  CUtensorMap mm, mn;
+  int rc = make_map_rows(&mm, plan.swapped ? X : dY, R, plan.m_dim);
+  if (rc == 0) rc = make_map_rows(&mn, plan.swapped ? dY : X, R, plan.n_dim);
+  if (rc != 0) return rc;
+  const size_t smem = (size_t)kWStages * kWStageBytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((plan.m_dim + kBM - 1) / kBM), (unsigned)((plan.n_dim + g.bn - 1) / g.bn), (unsigned)used);
+  wgrad_tf32_kernel<<<grid, kWThreads, smem, (cudaStream_t)stream>>>(mm, mn, g);
+  const long long n = (long long)Cout * Cin;
+  if (used > 1)
+    wgrad_reduce_kernel<<<d3d_ceil_div(n, 64), 256, 0, (cudaStream_t)stream>>>((const float*)ws, used, Cout, Cin,
+                                                                              plan.swapped ? 1 : 0, accumulate, dW);
+  d3d_note_launches(used > 1 ? 2 : 1);
   return d3d_launch_status();
 }
 

@@ -72,11 +72,17 @@ def _weight_grad_into(g2, x2, into):
 
 
 def _weight_grad(g2, x2, into=None):
-    """dW = g^T x for (R, Cout), (R, Cin) with R >> Cout, Cin.  One cuBLAS GEMM with a 131072-long reduction and a
+    """dW = g^T x for (R, Cout), (R, Cin) with R >> Cout, Cin: the package's tensor-core weight-gradient GEMM
+    (csrc/gemm.cu: both operands MN-major, rows split over the CTAs, deterministic reduction) when TF32 is the
+    convolution arithmetic; otherwise torch / cuBLAS:  One cuBLAS GEMM with a 131072-long reduction and a
     72 x 72 result runs on a handful of CTAs (114 us measured on B200, tools/wgrad_probe.py); split into R / 1024
     independent row chunks (bmm) plus a reduction it takes 32 us.
     into: a (Cout, Cin) gradient buffer to ADD the result to (runtime.grads_in_place); returns None then."""
     R = g2.shape[0]
+    if (runtime.own_wgrad and g2.is_cuda and torch.backends.cudnn.allow_tf32 and R >= runtime.own_wgrad_min_rows
+            and ops.gemm_ok(g2.shape[1], 0, x2.shape[1], g2, x2, into) and g2.is_contiguous() and x2.is_contiguous()):
+        out = ops.wgrad_tf32(g2, x2, into=into)
+        return None if into is not None else out
     S = min(R // 1024, 128)
     if R < 16384 or R % S:
         if into is None:

@@ -429,6 +429,22 @@ def gemm_tf32(a0, b, a1=None, out=None, accumulate=False, want_stats=False):
     return (c, stats) if want_stats else c
 
 
+def wgrad_tf32(dy_rows, x_rows, into=None):
+    """dW (Cout, Cin) = dy (.., Cout)^T @ x (.., Cin) over all rows, on the TF32 tensor cores (csrc/gemm.cu).
+    into: a (Cout, Cin) gradient buffer to ADD the result to; returns it (or a new tensor)."""
+    L = _lib.load()
+    dy, x = _f32(dy_rows, "grad_out"), _f32(x_rows, "rows")
+    Cout, Cin = dy.shape[-1], x.shape[-1]
+    R = dy.numel() // Cout
+    with torch.cuda.device(dy.device):
+        out = into if into is not None else torch.empty((Cout, Cin), dtype=torch.float32, device=dy.device)
+        ws = _ws(L.d3d_wgrad_workspace_bytes(R, Cout, Cin), dy.device)
+        _lib.check(L.d3d_wgrad_tf32(_p(dy), _p(x), _p(out), R, Cout, Cin, int(into is not None), _p(ws), ws.numel(),
+                                    _stream()), "d3d_wgrad_tf32")
+    _count()
+    return out
+
+
 def gemm_ok(K0, K1, N, *tensors):
     return K0 % 4 == 0 and K1 % 4 == 0 and N % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in tensors)
 

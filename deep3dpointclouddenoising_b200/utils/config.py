@@ -88,12 +88,18 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #     'always' forces it for every shape, False restores the per-query gather kernel everywhere.
 #   own_gemm: the 1x1 convolutions (forward and data gradient) run on the package's TMA + tcgen05 TF32 GEMM
 #     (csrc/gemm.cu), whose epilogue also emits the BatchNorm statistics; False: cuBLAS through torch.
+#   own_wgrad: weight gradients of the 1x1 convolutions on the package's tensor-core GEMM (d3d_wgrad_tf32) for layers with
+#     at least own_wgrad_min_rows rows; False (default): torch's batched split-K bmm (cuBLAS).  Measured on B200: the own
+#     kernel is at parity on the memory-bound first levels (22 / 37 / 42 us against 20 / 30 / 40 us) and 2-3x slower on
+#     the deep levels (128 x 160 tiles re-read the operands through L2; cuBLAS uses 256-wide 2-SM tiles), and the step
+#     is 0.1-0.4 ms slower with it — the weight gradients run on a side stream either way.
 #   wgrad_side_stream: with grads_in_place, the weight-gradient GEMMs run on a side stream (models/blocks.py); the
 #     training loop joins them with distributed.FlatParameters.reduce() / blocks.join_weight_grads() before the optimiser.
 #   staged_tiles_backward: same for the backward pass (measured slower than the segmented reduction: off).
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
                     "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
-                    "staged_tiles_backward": False, "own_gemm": True, "wgrad_side_stream": True})
+                    "staged_tiles_backward": False, "own_gemm": True, "wgrad_side_stream": True,
+                    "own_wgrad": False, "own_wgrad_min_rows": 0})
 
 
 def reset_config():

@@ -239,6 +239,12 @@ int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const flo
 int d3d_gemm_row_tiles(long long M);
 int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1,
                   int accumulate, float* stats, void* stream);
+/* Weight gradient of the same convolution: dW (Cout x Cin) = or += dY (R x Cout)^T . X (R x Cin)  (both operands MN-major for
+ * the tensor core; the rows are split over the CTAs and the fp32 partials are added in a fixed order: deterministic).
+ *   replaces the cuBLAS GEMMs behind torch's Conv1d weight gradient (ref: models/backbones/resnet.py:32-45 backward) */
+size_t d3d_wgrad_workspace_bytes(long long R, int Cout, int Cin);
+int d3d_wgrad_tf32(const float* dY, const float* X, float* dW, long long R, int Cout, int Cin, int accumulate, void* ws,
+                   size_t ws_bytes, void* stream);
 int d3d_bn_finalize(const float* stats, long long R, int C, float eps, float momentum, float* running_mean,
                     float* running_var, long long* num_batches_tracked, float* save_mean, float* save_invstd, void* stream);
 int d3d_bn_apply_cl(const float* x, const float* residual, const float* gamma, const float* beta, const float* save_mean,

@@ -111,3 +111,22 @@ def test_conv_bn_block_on_own_gemm_matches_cublas_path(cuda_device):
         scale = b.abs().max().item()
         assert ((a - b).norm() / b.norm()).item() <= 5e-3
         assert (a - b).abs().max().item() <= 5e-3 * scale
+
+
+@pytest.mark.parametrize("R,cout,cin", [(4096, 72, 72), (16 * 8192, 144, 72), (5000, 288, 144), (1024, 2304, 1152), (333, 72, 216),
+                                        (64, 16, 8), (40000, 144, 144)])
+def test_weight_gradient_gemm(cuda_device, R, cout, cin):
+    """dW = dY^T X on the tensor cores (both operands MN-major, split over the rows, deterministic reduction)."""
+    from deep3dpointclouddenoising_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(R + cout)
+    dy = torch.randn(R, cout, generator=g).to(cuda_device)
+    x = torch.randn(R, cin, generator=g).to(cuda_device)
+    dw = ops.wgrad_tf32(dy, x)
+    ref = dy.double().t() @ x.double()
+    scale = (dy.double().abs().t() @ x.double().abs()).clamp_min(1e-30)
+    assert ((dw.double() - ref).abs() / scale).max().item() <= 2e-3
+    assert torch.equal(dw, ops.wgrad_tf32(dy, x))
+    base = torch.randn(cout, cin, generator=g).to(cuda_device)
+    acc = base.clone()
+    ops.wgrad_tf32(dy, x, into=acc)
+    assert ((acc.double() - base.double() - ref).abs() / (1 + scale)).max().item() <= 2e-3

@@ -27,7 +27,7 @@ def main():
     args = ap.parse_args()
     for kv in filter(None, os.environ.get("D3D_RUNTIME", "").split(",")):
         k, v = kv.split("=")
-        cfgmod.runtime[k] = {"0": False, "1": True}.get(v, v)
+        cfgmod.runtime[k] = {"0": False, "1": True}.get(v, int(v) if v.isdigit() else v)
     cfgmod.runtime.pseudo_grid_precision = args.precision
     dev = torch.device("cuda:0")
     model, criterion, cfg = bench.build_model(args.operator, 8192)

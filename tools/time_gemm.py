@@ -53,6 +53,20 @@ def main():
         tot_o += t_o
         tot_t += t_t
     print(f"sum: ours {tot_o:.1f} us, cuBLAS {tot_t:.1f} us")
+    print("weight gradients dW = dY^T X (ours: tensor-core split-K + reduce; torch: the batched split-K bmm + sum of models/blocks.py)")
+    from deep3dpointclouddenoising_b200.models import blocks
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    runtime.own_wgrad = False  # the torch leg below must be torch's
+    tot_o = tot_t = 0.0
+    for M, K, N in shapes:
+        dy = torch.randn(M, N, device=dev)
+        x = torch.randn(M, K, device=dev)
+        t_o = timeit(lambda: ops.wgrad_tf32(dy, x))
+        t_t = timeit(lambda: blocks._weight_grad(dy, x))
+        print(f"R={M:6d} Cin={K:4d} Cout={N:4d}: ours {t_o:7.1f} us ({4.0 * M * (K + N) / t_o / 1e3:6.0f} GB/s)  torch {t_t:7.1f} us", flush=True)
+        tot_o += t_o
+        tot_t += t_t
+    print(f"sum: ours {tot_o:.1f} us, torch {tot_t:.1f} us")
 
 
 if __name__ == "__main__":
