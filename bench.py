@@ -485,6 +485,25 @@ def main():
         opt.step()
         return loss
 
+    # one-step software pipeline (graph mode): the neighbourhood pyramid of batch k+1 is built on the side stream while
+    # the backward pass of batch k runs (it depends on coordinates only), and handed over at fixed addresses at the end
+    # of the step; every replay trains on the batch the previous replay received.  D3D_PIPELINE=0: build inside forward.
+    pipelined = use_graph and os.environ.get("D3D_PIPELINE", "1") != "0"
+
+    def train_step_pipelined(cur, nxt):
+        from deep3dpointclouddenoising_b200 import neighbors
+        bucket.zero()
+        loss = criterion(net(cur[0], cur[1], cur[2]).transpose(1, 2), cur[3], cur[1])
+        model.prefetch_neighbors(nxt[0], nxt[1])
+        loss.backward()
+        bucket.reduce()
+        torch.nn.utils.clip_grad_norm_(opt_params, 10)
+        opt.step()
+        neighbors.fold_pending_into_current()  # next batch's pyramid -> the addresses the next replay's forward reads
+        for d, src in zip(cur, nxt):
+            d.copy_(src)
+        return loss
+
     def barrier():
         distributed.barrier(dev)
 
@@ -492,6 +511,7 @@ def main():
     host = [host_batch(s) for s in range(n_host)]
     resident = [[t.to(dev) for t in hb] for hb in host]
     static = [t.clone() for t in resident[0]]  # the step always reads these buffers (CUDA-graph friendly)
+    static_next = [t.clone() for t in resident[0]] if pipelined else None  # where the next batch lands
 
     # ---- warm-up (eager, on a side stream as graph capture requires), launch count of one step, capture ----
     side = torch.cuda.Stream()
@@ -510,12 +530,22 @@ def main():
     graph, static_loss = None, None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = train_step(*static)
+        if pipelined:
+            from deep3dpointclouddenoising_b200 import neighbors
+            model.prefetch_neighbors(static[0], static[1])  # the pyramid the first replay's forward finds
+            neighbors.settle()
+            # the step's own kernels are captured at high priority: the prefetch (side stream, default priority) fills the
+            # SM slots they leave free instead of queueing ahead of them
+            hi = torch.cuda.Stream(priority=-1) if os.environ.get("D3D_PIPELINE_PRIORITY", "1") != "0" else None
+            with torch.cuda.graph(graph, stream=hi):
+                static_loss = train_step_pipelined(static, static_next)
+        else:
+            with torch.cuda.graph(graph):
+                static_loss = train_step(*static)
         barrier()
 
     def run_step(batch, non_blocking=False):
-        for d, src in zip(static, batch):
+        for d, src in zip(static_next if (pipelined and graph is not None) else static, batch):
             d.copy_(src, non_blocking=non_blocking)
         if graph is not None:
             graph.replay()
@@ -700,6 +730,8 @@ def main():
                                ("flat bucket, 5 NCCL all-reduce slices overlapped with backward" if getattr(bucket, "_comm", None) is not None
                                 else "flat bucket, 1 NCCL all-reduce") if bucket is not None else "DDP"),
                            "cuda_graph": graph is not None,
+                           "pyramid": ("next batch's neighbourhood pyramid built during this batch's backward (one-step pipeline, "
+                                       "one pyramid per step)") if (pipelined and graph is not None) else "built inside forward on a side stream",
                            "layout": "channel-last activations end to end" if cfgmod.runtime.channel_last else "channel-major",
                            "conv_math": "tf32" if torch.backends.cudnn.allow_tf32 else "fp32", "l2": "per-step working set (activations, "
                            "several GB) exceeds the 126 MB L2; 4 rotating input batches"},

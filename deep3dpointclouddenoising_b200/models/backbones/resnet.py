@@ -87,12 +87,14 @@ class ResNet(nn.Module):
             setattr(self, f"layer{stage + 1}", layer)
 
     def forward(self, xyz, mask, features, end_points=None):
-        _neighbors.cache.clear()  # neighbour lists are valid for one forward only
-        if runtime.prefetch_neighbors and xyz.is_cuda:
-            # the whole pyramid (+ inverse maps when gradients are on) goes to a side stream and overlaps with the
-            # convolutions / BatchNorm / aggregations below; consumers wait on per-item events (neighbors.py)
-            _neighbors.prebuild(xyz, mask, self._radius0, self._nsample0, self._stages, torch.is_grad_enabled(),
-                                self._with_order)
+        # a pyramid prefetched for exactly these tensors during the previous step (prefetch_neighbors) is adopted as is
+        if not _neighbors.adopt(xyz, mask):
+            _neighbors.cache.clear()  # neighbour lists are valid for one forward only
+            if runtime.prefetch_neighbors and xyz.is_cuda:
+                # the whole pyramid (+ inverse maps when gradients are on) goes to a side stream and overlaps with the
+                # convolutions / BatchNorm / aggregations below; consumers wait on per-item events (neighbors.py)
+                _neighbors.prebuild(xyz, mask, self._radius0, self._nsample0, self._stages, torch.is_grad_enabled(),
+                                    self._with_order)
         if not end_points:
             end_points = {}
         try:
@@ -102,6 +104,11 @@ class ResNet(nn.Module):
             # when the forward raises — so the stream is never left forked (a later graph capture would fail).  The
             # pyramid is long finished by the time the last stage has run.
             _neighbors.join()
+
+    def prefetch_neighbors(self, xyz, mask):
+        """Builds the pyramid of the NEXT batch now, on the side stream (call it between this step's forward and its
+        backward): the next forward on these very tensors adopts it instead of building its own (neighbors.prefetch)."""
+        _neighbors.prefetch(xyz, mask, self._radius0, self._nsample0, self._stages, True, self._with_order)
 
     def _forward(self, xyz, mask, features, end_points):
         features = self.conv1(features)

@@ -92,6 +92,7 @@ class _Cache:
 
     def __init__(self, max_entries=64):
         self.entries = {}
+        self.arena = None  # the ops.Arena the entries were carved from (prefetched pyramids only)
         self.max_entries = max_entries
         self.enabled = True
         self.hits = 0
@@ -102,7 +103,8 @@ class _Cache:
         return (t.data_ptr(), t._version, tuple(t.shape))
 
     def clear(self):
-        self.entries.clear()
+        self.entries = {}  # a new dict: an adopted pyramid's dict may still be referenced by its producer
+        self.arena = None
 
     def get(self, kind, tensors, scalars, build):
         if not self.enabled:
@@ -212,6 +214,115 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order=True):
     finally:
         _building_on_side[0] = False
     _final_events[key] = final
+
+
+# ------------------------------------------------------------------------------------------------
+# cross-step pipelining: the pyramid of the NEXT batch, built while this batch's backward runs
+# ------------------------------------------------------------------------------------------------
+_pending = {}     # device index -> (source key, entries, final event, keepalive, arena): adopted by the next forward on it
+_persistent = []  # pyramids a captured graph reads and overwrites at fixed addresses: never freed
+_arena_bytes = {}  # (shapes, geometry) -> bytes of one pyramid's outputs, measured by the first build
+
+
+def _source_key(xyz, mask):
+    return (cache._tid(xyz), cache._tid(mask))
+
+
+def prefetch(xyz, mask, radius, nsample0, stages, with_csr=True, with_order=True):
+    """Builds the whole pyramid of (xyz, mask) NOW on the side stream, into a pending cache that the next backbone forward
+    on these very tensors adopts instead of building its own (ResNet.prefetch_neighbors is the caller with the module's
+    geometry).  Called between a step's forward and its backward, the latency-bound neighbourhood kernels of batch k+1
+    (the reference rebuilds them inside every forward, resnet.py:47-68) overlap the backward pass of batch k — the
+    pyramid depends on coordinates only, never on the weights, so the training arithmetic is unchanged."""
+    if not (cache.enabled and xyz.is_cuda):
+        return
+    key, side = _side_stream(xyz.device)
+    # every output of the build comes out of ONE block (ops.Arena): the graph form of the hand-over is then one copy.
+    # The block's size follows from the shapes and the geometry; the first build of a kind measures it (and is redone).
+    spec = (tuple(xyz.shape), float(radius), int(nsample0), tuple(stages), bool(with_csr), bool(with_order))
+    for attempt in range(2):
+        nbytes = _arena_bytes.get(spec, 0)
+        side.wait_stream(torch.cuda.current_stream())  # fork first: under a graph capture the block must come from the graph's pool
+        with torch.cuda.stream(side):  # the block belongs to the side stream's pool, like the tensors of a plain build
+            arena = ops.Arena(nbytes, xyz.device)
+        saved, cache.entries = cache.entries, {}
+        try:
+            with arena:
+                prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order)
+            built = cache.entries
+        finally:
+            cache.entries = saved
+        if nbytes:
+            break
+        _arena_bytes[spec] = arena.need
+    _pending[key] = (_source_key(xyz, mask), built, _final_events.pop(key, None), (xyz, mask), arena)
+
+
+def adopt(xyz, mask):
+    """True if a prefetched pyramid of exactly these tensors was pending: it becomes the forward's cache."""
+    if not xyz.is_cuda:
+        return False
+    key, _ = _side_stream(xyz.device)
+    pending = _pending.pop(key, None)
+    if pending is None or pending[0] != _source_key(xyz, mask):
+        return False
+    cache.entries, cache.arena = pending[1], pending[4]
+    if pending[2] is not None:
+        _final_events[key] = pending[2]  # the forward's join() waits for the build as a whole
+    return True
+
+
+def _tensors(item):
+    if isinstance(item, NeighborList):
+        csr = item._csr if item._csr is not None else (None, None)
+        return [item.idx, item.idx_mask, item.nvalid, item.by_support, csr[0], csr[1]]
+    if isinstance(item, _Subsampled):
+        return [item.sub_xyz, item.sub_mask]
+    return [item.order]
+
+
+def settle(device=None):
+    """Waits (host side) for the pending pyramid and drops its events: what a CUDA-graph capture needs of a pyramid that
+    was built before the capture began (a captured stream must not wait on events recorded outside the capture)."""
+    key, _ = _side_stream(torch.cuda.current_device() if device is None else device)
+    pending = _pending.get(key)
+    if pending is None:
+        return
+    torch.cuda.synchronize(key)
+    for item in pending[1].values():
+        item._event = None
+        if isinstance(item, NeighborList):
+            item._csr_event = None
+    _pending[key] = (pending[0], pending[1], None, pending[3], pending[4])
+
+
+def fold_pending_into_current(device=None):
+    """CUDA-graph form of the hand-over: copies every tensor of the pending pyramid (next batch) INTO the tensors of the
+    pyramid the current forward used (same shapes: all sizes follow from B, the level sizes and nsample), after joining
+    the side stream.  Captured at the end of a step, every replay then reads the pyramid the previous replay built, at
+    fixed addresses.  The current pyramid is kept alive for the life of the process (the graph owns its addresses)."""
+    key, _ = _side_stream(torch.cuda.current_device() if device is None else device)
+    pending = _pending.pop(key, None)
+    if pending is None:
+        raise RuntimeError("fold_pending_into_current: nothing was prefetched")
+    if pending[2] is not None:
+        torch.cuda.current_stream().wait_event(pending[2])
+    cur, new = list(cache.entries.values()), list(pending[1].values())
+    if len(cur) != len(new) or any(type(a) is not type(b) for a, b in zip(cur, new)):
+        raise RuntimeError("fold_pending_into_current: the pending pyramid has another structure than the current one")
+    a_cur, a_new = getattr(cache, "arena", None), pending[4]
+    whole = (a_cur is not None and a_cur.buf is not None and a_new.buf is not None and a_cur.need == a_new.need
+             and a_cur.off == a_new.off == a_cur.need)  # both pyramids lie entirely inside equal blocks
+    with torch.no_grad():
+        for a, b in zip(cur, new):
+            for ta, tb in zip(_tensors(a), _tensors(b)):
+                if (ta is None) != (tb is None) or (ta is not None and ta.shape != tb.shape):
+                    raise RuntimeError("fold_pending_into_current: tensor shapes differ between the two pyramids")
+                if ta is not None and not whole:
+                    ta.copy_(tb)
+        if whole:
+            a_cur.buf.copy_(a_new.buf)
+    _persistent.append((cur, pending[3], a_cur))
 
 
 def join(device=None):

@@ -51,6 +51,44 @@ def _p(t):
     return t.data_ptr() if t is not None else None
 
 
+class Arena:
+    """One allocation that the OUTPUTS of the neighbourhood ops (lists, subsampled levels, inverse maps, orders) are carved
+    from while it is installed (`with arena:`): a whole pyramid then is one contiguous block — handed from one step to
+    the next with a single copy (neighbors.fold_pending_into_current).  Without a buffer it only measures (`need`)."""
+
+    _current = None
+
+    def __init__(self, nbytes=0, device=None):
+        self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device) if nbytes else None
+        self.off = 0
+        self.need = 0
+
+    def __enter__(self):
+        self._prev, Arena._current = Arena._current, self
+        return self
+
+    def __exit__(self, *exc):
+        Arena._current = self._prev
+
+    def take(self, shape, dtype, device):
+        n = int(torch.tensor([], dtype=dtype).element_size())
+        for d in shape:
+            n *= int(d)
+        aligned = (n + 255) // 256 * 256
+        self.need += aligned
+        if self.buf is None or self.off + aligned > self.buf.numel() or n == 0:
+            return torch.empty(shape, dtype=dtype, device=device)
+        t = self.buf[self.off:self.off + n].view(dtype).view(shape)
+        self.off += aligned
+        return t
+
+
+def _out(shape, dtype, device):
+    """Output tensor of a neighbourhood op: from the installed Arena, else a fresh allocation."""
+    a = Arena._current
+    return torch.empty(shape, dtype=dtype, device=device) if a is None else a.take(shape, dtype, device)
+
+
 # ------------------------------------------------------------------------------------------------
 # neighbourhood construction
 # ------------------------------------------------------------------------------------------------
@@ -63,11 +101,11 @@ def ball_query(query_xyz, support_xyz, query_mask, support_mask, radius, nsample
     qm, sm = _i32(query_mask, "query_mask"), _i32(support_mask, "support_mask")
     B, M, N = q.shape[0], q.shape[1], s.shape[1]
     with torch.cuda.device(q.device):
-        idx = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
-        msk = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device)
-        nv = torch.empty((B, M), dtype=torch.int32, device=q.device) if want_nvalid else None
+        idx = _out((B, M, nsample), torch.int32, q.device)
+        msk = _out((B, M, nsample), torch.int32, q.device)
+        nv = _out((B, M), torch.int32, q.device) if want_nvalid else None
         want_by_support = want_by_support and N <= 65536
-        bys = torch.empty((B, M, nsample), dtype=torch.int32, device=q.device) if want_by_support else None
+        bys = _out((B, M, nsample), torch.int32, q.device) if want_by_support else None
         ws = _ws(L.d3d_ball_query_workspace_bytes(B, M, N), q.device)
         _lib.check(L.d3d_ball_query(_p(q), _p(s), _p(qm), _p(sm), B, M, N, float(radius), int(nsample), _p(idx),
                                     _p(msk), _p(nv), _p(bys), _p(ws), ws.numel(), _stream()), "d3d_ball_query")
@@ -83,8 +121,8 @@ def nearest_query(query_xyz, support_xyz, query_mask, support_mask):
     qm, sm = _i32(query_mask, "query_mask"), _i32(support_mask, "support_mask")
     B, M, N = q.shape[0], q.shape[1], s.shape[1]
     with torch.cuda.device(q.device):
-        idx = torch.empty((B, M, 1), dtype=torch.int32, device=q.device)
-        msk = torch.empty((B, M, 1), dtype=torch.int32, device=q.device)
+        idx = _out((B, M, 1), torch.int32, q.device)
+        msk = _out((B, M, 1), torch.int32, q.device)
         ws = _ws(L.d3d_nearest_query_workspace_bytes(B), q.device)
         _lib.check(L.d3d_nearest_query(_p(q), _p(s), _p(qm), _p(sm), B, M, N, _p(idx), _p(msk), _p(ws), ws.numel(),
                                        _stream()), "d3d_nearest_query")
@@ -98,8 +136,8 @@ def grid_subsample(xyz, mask, npoint, sample_dl):
     p, mk = _f32(xyz, "points"), _i32(mask, "mask")
     B, N = p.shape[0], p.shape[1]
     with torch.cuda.device(p.device):
-        sub = torch.empty((B, npoint, 3), dtype=torch.float32, device=p.device)
-        subm = torch.empty((B, npoint), dtype=torch.int32, device=p.device)
+        sub = _out((B, npoint, 3), torch.float32, p.device)
+        subm = _out((B, npoint), torch.int32, p.device)
         ws = _ws(L.d3d_grid_subsample_workspace_bytes(B, N), p.device)
         _lib.check(L.d3d_grid_subsample(_p(p), _p(mk), B, N, int(npoint), float(sample_dl), _p(sub), _p(subm), _p(ws),
                                         ws.numel(), _stream()), "d3d_grid_subsample")
@@ -145,8 +183,8 @@ def build_inverse_map(idx, n_support):
         i = i.unsqueeze(-1)
     B, M, ns = i.shape
     with torch.cuda.device(i.device):
-        rowptr = torch.empty((B * n_support + 1,), dtype=torch.int32, device=i.device)
-        entries = torch.empty((max(B * M * ns, 1),), dtype=torch.int32, device=i.device)
+        rowptr = _out((B * n_support + 1,), torch.int32, i.device)
+        entries = _out((max(B * M * ns, 1),), torch.int32, i.device)
         ws = _ws(L.d3d_inverse_map_workspace_bytes(B, n_support, M, ns), i.device)
         _lib.check(L.d3d_build_inverse_map(_p(i), B, int(n_support), M, ns, _p(rowptr), _p(entries), _p(ws),
                                            ws.numel(), _stream()), "d3d_build_inverse_map")
@@ -192,7 +230,7 @@ def spatial_order(xyz):
     if N > TILE_MAX_POINTS:
         return None
     with torch.cuda.device(p.device):
-        order = torch.empty((B, N), dtype=torch.int32, device=p.device)
+        order = _out((B, N), torch.int32, p.device)
         _lib.check(L.d3d_spatial_order(_p(p), B, N, _p(order), _stream()), "d3d_spatial_order")
     _count()
     return order

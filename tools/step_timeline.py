@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--gaps", type=int, default=15)
     ap.add_argument("--list", default=None, help="comma-separated substrings: print every launch of matching kernels (start, us, grid)")
+    ap.add_argument("--pipeline", action="store_true", help="the one-step pipelined form (next batch's pyramid during backward)")
     args = ap.parse_args()
     for kv in filter(None, os.environ.get("D3D_RUNTIME", "").split(",")):
         k, v = kv.split("=")
@@ -37,13 +38,22 @@ def main():
     opt = torch.optim.Adam([bucket.param], lr=cfg.base_learning_rate, weight_decay=cfg.weight_decay, capturable=True, fused=True)
     batch = [torch.from_numpy(a).to(dev) for a in synthetic.make_batch(0, 16, 8192)]
 
-    def step():
+    nxt = [t.clone() for t in batch]
+
+    def step(piped=False):
+        from deep3dpointclouddenoising_b200 import neighbors
         bucket.zero()
         loss = criterion(model(batch[0], batch[1], batch[2]).transpose(1, 2), batch[3], batch[1])
+        if piped:
+            model.prefetch_neighbors(nxt[0], nxt[1])
         loss.backward()
         bucket.reduce()
         torch.nn.utils.clip_grad_norm_([bucket.param], 10)
         opt.step()
+        if piped:
+            neighbors.fold_pending_into_current()
+            for d, src in zip(batch, nxt):
+                d.copy_(src)
         return loss
 
     side = torch.cuda.Stream()
@@ -53,8 +63,12 @@ def main():
             step()
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        step()
+    if args.pipeline:
+        from deep3dpointclouddenoising_b200 import neighbors
+        model.prefetch_neighbors(batch[0], batch[1])
+        neighbors.settle()
+    with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=-1) if args.pipeline else None):
+        step(args.pipeline)
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize()
