@@ -651,18 +651,33 @@ def main():
                         "tflops": round(f["flops"] / 1e9 / f["ms_per_step"], 2) if f["flops"] and f["ms_per_step"] > 0 else None,
                         "frac_of_tf32_peak": round(f["flops"] / 1e9 / f["ms_per_step"] / tf32_peak, 4) if f["flops"] and f["ms_per_step"] > 0 else None}
                     for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms_per_step"])}
-        rooflines = [roof(k, v) for k, v in ranked[:5] if v["ms_per_call"] > 0]
+        # `roofline`: the dominant KERNEL FAMILY of the step — one op over all its launches (the step runs every op at five
+        # resolutions): achieved = summed algorithmic bytes (or flops) / summed device time = average bytes per launch /
+        # average launch duration.  `rooflines`: the five largest families; `per_shape`: the five largest single shapes.
+        def fam_roof(name, f):
+            n = max(f["launches"], 1e-9)
+            v = {"flops_per_call": f["flops"] / n, "bytes_per_call": f["bytes"] / n, "ms_per_call": f["ms_per_step"] / n,
+                 "calls": f["launches"] * n_inst, "ms_per_step": f["ms_per_step"]}
+            r = roof(name, v)
+            r["kernel"] = f"{name} (all {f['launches']:g} launches of the step, five resolutions)"
+            shapes = [k for k, pv in per.items() if pv["op"] == name]
+            known = [traffic_table.get(k) for k in shapes]
+            r["traffic"] = None  # per-shape ncu DRAM traffic: see `per_shape` and profiles/roofline_traffic.json
+            r["traffic_largest_shape"] = next((t for t in known if t), None)
+            return r
+
+        fam_ranked = [(k, f) for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms_per_step"])
+                      if f["ms_per_step"] > 0 and (f["bytes"] or f["flops"])]
+        rooflines = [fam_roof(k, f) for k, f in fam_ranked[:5]]
+        per_shape = [roof(k, v) for k, v in ranked[:5] if v["ms_per_call"] > 0]
         roofline = dict(rooflines[0])
-        top_key, top = ranked[0]
-        sh = top["shape"]
-        if top["op"] in ("pospool_fwd", "pospool_bwd", "pseudogrid_fwd", "pseudogrid_bwd", "gather_max_fwd", "gather_max_bwd"):
-            gb = 4 * sh["B"] * sh["M"] * max(sh.get("ns", 0), 1) * sh["C"]  # rows gathered through L2 (never materialised)
-            roofline["gather"] = {"l2_gather_bytes_per_launch": gb, "l2_gather_gbs": round(gb / 1e6 / top["ms_per_call"], 1)}
+        roofline["per_shape"] = per_shape
         roofline["our_kernels_share_of_step"] = round(ours_ms / step_ms, 4)
-        roofline["note"] = ("dominant op of the step by device time (CUDA events around every C-ABI call, every fused BatchNorm "
-                            "and every 1x1-convolution GEMM of an instrumented eager pass); algorithmic bytes = compulsory HBM "
-                            "traffic (DESIGN.md §3); 'rooflines' lists the top five, 'families' sums each op over the five "
-                            "resolutions; ncu evidence under profiles/")
+        roofline["note"] = ("dominant kernel family of the step by summed device time (CUDA events around every C-ABI call, every "
+                            "fused BatchNorm and every 1x1-convolution GEMM of an instrumented eager pass; neighbourhood ops run on "
+                            "a side stream there, so their times include contention); algorithmic bytes = compulsory HBM traffic "
+                            "(DESIGN.md §3); the ordered ball query is instruction-issue bound (67 % of issue slots, "
+                            "profiles/r01_ball_query_v3_ncu.md): its HBM fraction says little; ncu evidence under profiles/")
 
     # ---- neighbour build alone (BASELINE.json metric, second figure): the full 5-level pyramid of one batch ----
     neighbor_build = None

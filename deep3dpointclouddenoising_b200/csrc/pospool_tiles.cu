@@ -53,7 +53,19 @@ struct TileArgs {
   const int* order;          // (B, owners) processing order of the owner rows
   int M, N, C, nsample, reduction;
   float inv_radius;
+  unsigned long long* timing;  // diagnostics (tools/tile_phases.py): 8 timestamps per CTA, or null
 };
+
+unsigned long long* g_timing = nullptr;
+
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define D3D_STAMP(k)                                                                                                  \
+  if (a.timing && tid == 0)                                                                                           \
+  a.timing[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (k)] = now_ns()
 
 struct Layout {
   unsigned a, planes, plane_bytes, lbo_b, stage, row_bytes, ent, bitmap, prefix, owner_id, owner_info, owner_xyz, owner_rho,
@@ -137,6 +149,7 @@ pospool_tiles_kernel(const TileArgs a) {
   const int n_rows = min(kTQ, n_own - row0);
   const size_t qbase = (size_t)b * a.M;
 
+  D3D_STAMP(0);
   // ---- P0: owners, barriers, TMEM ---------------------------------------------------------------------------------
   if (warp == 4) tmem_alloc(tmem_slot, (unsigned)L.tmem_cols);
   if (tid == 160) {  // a warp that does not allocate TMEM
@@ -184,6 +197,7 @@ pospool_tiles_kernel(const TileArgs a) {
   const float ctr_x = (sCtr[0] + sCtr[3] + sCtr[6] + sCtr[9]) * inv_rows, ctr_y = (sCtr[1] + sCtr[4] + sCtr[7] + sCtr[10]) * inv_rows,
               ctr_z = (sCtr[2] + sCtr[5] + sCtr[8] + sCtr[11]) * inv_rows;
 
+  D3D_STAMP(1);
   // ---- P1: union of the referenced source rows --------------------------------------------------------------------
   if (kBackward) {
     // pass 1 over the owners' inverse-map segments: which queries gathered them through an unmasked slot
@@ -266,6 +280,7 @@ pospool_tiles_kernel(const TileArgs a) {
   }
   const int U = (int)sScan[16];
   __syncthreads();
+  D3D_STAMP(2);
   // source id -> rank inside the union (ranks ascend along every row's list: the union is ordered by index)
   if (kBackward) {
     for (int r = warp; r < n_rows; r += kThreads / 32) {
@@ -373,6 +388,7 @@ pospool_tiles_kernel(const TileArgs a) {
     }
   }
   __syncthreads();  // ranks (forward: sEnt; backward: rank_scratch, written by other threads of this CTA) are in place
+  D3D_STAMP(3);
 
   for (int j = 0; j < n_chunks; ++j) {
     const int pb = j & 1;
@@ -449,6 +465,7 @@ pospool_tiles_kernel(const TileArgs a) {
     if (tid >= kThreads - 64 && j + 1 < n_chunks) select_and_issue(j + 1);
   }
 
+  D3D_STAMP(4);
   // ---- epilogue: thread = owner row (TMEM lane); the two warp groups split the 16-column pieces --------------------
   if (n_chunks > 0) {
     mbar_wait(bar_mma, (unsigned)((n_chunks - 1) & 1));
@@ -489,6 +506,8 @@ pospool_tiles_kernel(const TileArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  D3D_STAMP(5);
+  if (a.timing && tid == 0) a.timing[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 6] = (unsigned long long)U;
   if (warp == 4) tmem_dealloc(tmem_base, (unsigned)L.tmem_cols);
 }
 
@@ -504,7 +523,9 @@ int launch_tiles(const TileArgs& a, int B, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(d3d_ceil_div(n_own, kTQ), d3d_ceil_div(a.C, kCB), B);
-  kernel<<<grid, kThreads, L.total, st>>>(a);
+  TileArgs b = a;
+  b.timing = g_timing;
+  kernel<<<grid, kThreads, L.total, st>>>(b);
   d3d_note_launches(1);
   return d3d_launch_status();
 }
@@ -512,6 +533,9 @@ int launch_tiles(const TileArgs& a, int B, cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+// diagnostics only: device buffer of 8 x uint64 per CTA that the next launches fill with phase timestamps (null: off)
+void d3d_pospool_tiles_debug_timing(void* buf) { g_timing = (unsigned long long*)buf; }
 
 int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx_by_support,
                           const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
