@@ -511,6 +511,370 @@ pospool_tiles_kernel(const TileArgs a) {
   if (warp == 4) tmem_dealloc(tmem_base, (unsigned)L.tmem_cols);
 }
 
+
+// ================================================================================================================
+// Backward in SCATTER form: the CTA owns 128 QUERIES (the forward tile) and distributes their gradient rows over the
+// union of the supports they gathered.  With A the forward multiplicity matrix (128 queries x U union rows),
+//      dF[u, c] += (S[u] - centre)[c mod 3] * D1[u, c] - D2[u, c],     D1 = A^T . G1,   D2 = A^T . G2,
+//      G1[q, c] = rho_q * grad_out[q, c],   G2[q, c] = rho_q * (Q[q] - centre)[c mod 3] * grad_out[q, c]
+// — the transpose of the forward contraction.  The 128 gradient rows are staged ONCE per tile (bulk copies) and split
+// into bf16 planes once (the gather form above stages the 3x larger union of the gathering queries chunk by chunk);
+// A^T is the same shared-memory image as A read with the MN-major descriptor.  The union is processed in blocks of
+// 128 rows = one accumulator (TMEM lanes); three roles run concurrently on double-buffered A blocks and accumulators:
+//   warps 0-3   build block m+1 of A (thread = query, cursor along its list as in the forward kernel),
+//   warp 12     issues the 48 MMAs of block m,
+//   warps 4-11  drain block m-1: TMEM -> registers -> red.global.add.v4.f32 into dF (zero-filled by the entry point).
+// The sums of one dF row over the (on average 3.6) tiles that reference it arrive as float atomics, like the
+// reference's own backward (group_points_gpu.cu:48-69): results are reproducible to rounding, not bit for bit.
+constexpr int kBT = 416;
+constexpr int kUB = 128;                       // union rows per block = MMA M
+constexpr unsigned kAtGroup = (kUB / 8) * 128; // one 8-query group of a block: 16 chunks of 8 union ranks, 2 KB
+constexpr unsigned kAtBytes = (kTQ / 8) * kAtGroup;  // 32 KB per block
+
+struct ScatterLayout {
+  unsigned a, planes, plane_bytes, lbo_b, row_bytes, ent, bitmap, prefix, owner_id, owner_info, owner_xyz, owner_rho, scan,
+      bars, total;
+  int W, np;
+};
+
+__host__ __device__ inline ScatterLayout make_scatter_layout(int cbn, int ns, int n_src) {
+  ScatterLayout L;
+  unsigned o = 0;
+  L.a = o; o += 2 * kAtBytes;  // the gradient rows are staged here before the first A block is built
+  L.lbo_b = (unsigned)((cbn + 7) / 8) * 128u;
+  L.plane_bytes = (kTQ / 8) * L.lbo_b;
+  L.planes = o; o += 6 * L.plane_bytes + 128;
+  L.row_bytes = (unsigned)cbn * 4u;
+  L.ent = o; o += align16((unsigned)(kTQ * ns * 2));
+  L.W = (n_src + 31) / 32;
+  L.bitmap = o; o += align16((unsigned)L.W * 4u);
+  L.prefix = o; o += align16((unsigned)(L.W + 1) * 4u);
+  L.owner_id = o; o += kTQ * 4;
+  L.owner_info = o; o += kTQ * 4;
+  L.owner_xyz = o; o += kTQ * 12;
+  L.owner_rho = o; o += kTQ * 4;
+  L.scan = o; o += 32 * 4;
+  L.bars = o; o += 64;
+  L.total = o;
+  L.np = (cbn + 15) & ~15;
+  return L;
+}
+
+__global__ void __launch_bounds__(kBT, 1)
+pospool_scatter_bwd_kernel(const TileArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x, b = blockIdx.z;
+  const int c0 = blockIdx.y * kCB, cbn = min(kCB, a.C - c0);
+  const int ns = a.nsample;
+  const ScatterLayout L = make_scatter_layout(cbn, ns, a.N);
+
+  unsigned char* sA = smem + L.a;
+  unsigned char* sPlanes = smem + L.planes;
+  unsigned short* sEnt = reinterpret_cast<unsigned short*>(smem + L.ent);
+  unsigned* sBitmap = reinterpret_cast<unsigned*>(smem + L.bitmap);
+  unsigned* sPrefix = reinterpret_cast<unsigned*>(smem + L.prefix);
+  int* sOwnerId = reinterpret_cast<int*>(smem + L.owner_id);
+  int* sOwnerInfo = reinterpret_cast<int*>(smem + L.owner_info);
+  float* sOwnerXyz = reinterpret_cast<float*>(smem + L.owner_xyz);
+  float* sOwnerRho = reinterpret_cast<float*>(smem + L.owner_rho);
+  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);
+  float* sCtr = reinterpret_cast<float*>(smem + L.scan) + 20;
+  const unsigned bar0 = smem_u32(smem + L.bars);
+  const unsigned bar_stage = bar0, tmem_slot = bar0 + 56;
+  auto bar_a_full = [&](int buf) { return bar0 + 8 + 8 * buf; };      // 128 builder arrivals
+  auto bar_mma = [&](int buf) { return bar0 + 24 + 8 * buf; };         // tcgen05.commit: A block free, accumulator full
+  auto bar_acc_free = [&](int buf) { return bar0 + 40 + 8 * buf; };    // 256 drain arrivals
+
+  const float* own_xyz = a.query_xyz + (size_t)b * a.M * 3;
+  const float* src_xyz = a.support_xyz + (size_t)b * a.N * 3;
+  const int* order = a.order + (size_t)b * a.M;
+  const int row0 = tile * kTQ;
+  const int n_rows = min(kTQ, a.M - row0);
+  const size_t qbase = (size_t)b * a.M;
+
+  // ---- owners (queries), barriers, TMEM: as in the gather kernel ------------------------------------------------
+  if (warp == 12) tmem_alloc(tmem_slot, 512u);
+  if (tid == 160) {
+    mbar_init(bar_stage, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_a_full(i), kTQ);
+      mbar_init(bar_mma(i), 1);
+      mbar_init(bar_acc_free(i), 256);
+    }
+    mbar_init_fence();
+  }
+  if (tid < kTQ) {
+    int own = -1, info = 0;
+    float px = 0.f, py = 0.f, pz = 0.f, rho = 0.f;
+    if (tid < n_rows) {
+      own = order[row0 + tid];
+      px = own_xyz[3 * (size_t)own]; py = own_xyz[3 * (size_t)own + 1]; pz = own_xyz[3 * (size_t)own + 2];
+      const int nv = min(a.nvalid[qbase + own], ns);
+      const bool padded = a.query_mask[qbase + own] == 0;
+      const int neff = padded ? ns : nv;
+      info = ((padded && nv == 0) ? 1 : nv) | (nv << 8) | ((padded ? 1 : 0) << 16);
+      rho = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;
+    }
+    sOwnerId[tid] = own; sOwnerInfo[tid] = info;
+    sOwnerXyz[3 * tid] = px; sOwnerXyz[3 * tid + 1] = py; sOwnerXyz[3 * tid + 2] = pz;
+    sOwnerRho[tid] = rho;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      px += __shfl_xor_sync(D3D_FULL_MASK, px, o);
+      py += __shfl_xor_sync(D3D_FULL_MASK, py, o);
+      pz += __shfl_xor_sync(D3D_FULL_MASK, pz, o);
+    }
+    if (lane == 0) { sCtr[3 * warp] = px; sCtr[3 * warp + 1] = py; sCtr[3 * warp + 2] = pz; }
+  }
+  for (int w = tid; w < L.W; w += kBT) sBitmap[w] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *reinterpret_cast<volatile unsigned*>(smem + L.bars + 56);
+  const float inv_rows = 1.0f / (float)n_rows;
+  const float ctr_x = (sCtr[0] + sCtr[3] + sCtr[6] + sCtr[9]) * inv_rows, ctr_y = (sCtr[1] + sCtr[4] + sCtr[7] + sCtr[10]) * inv_rows,
+              ctr_z = (sCtr[2] + sCtr[5] + sCtr[8] + sCtr[11]) * inv_rows;
+
+  // the tile's gradient rows start flying now (one bulk copy per row, issued by the last four warps)
+  const float* g_rows = a.src + (size_t)b * a.M * a.C + c0;
+  if (tid >= kBT - 128) {
+    const int t = tid - (kBT - 128);
+    if (t == 0) mbar_arrive_expect_tx(bar_stage, (unsigned)n_rows * L.row_bytes);
+    named_bar_sync(1, 128);  // expect_tx precedes every complete_tx
+    if (t < n_rows) bulk_g2s(smem_u32(sA + (size_t)t * L.row_bytes), g_rows + (size_t)sOwnerId[t] * a.C, L.row_bytes, bar_stage);
+  }
+
+  // ---- union of the referenced support rows (forward lists, ascending support index) ----------------------------
+  for (int r4 = warp; r4 < n_rows; r4 += 4 * (kBT / 32)) {
+    int v[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r4 + i * (kBT / 32);
+      v[i][0] = v[i][1] = -1;
+      if (r < n_rows) {
+        const int* lrow = a.by_support + (qbase + sOwnerId[r]) * ns;
+        if (lane < ns) v[i][0] = lrow[lane];
+        if (lane + 32 < ns) v[i][1] = lrow[lane + 32];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r4 + i * (kBT / 32);
+      if (r < n_rows) {
+        const int info = sOwnerInfo[r];
+        const int n_ent = info & 255;
+        const bool row0_only = ((info >> 16) & 1) && ((info >> 8) & 255) == 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int k = lane + 32 * h;
+          if (k < ns) {
+            unsigned id = 0xffffu;
+            if (k < n_ent) {
+              id = row0_only ? 0u : (unsigned)(v[i][h] & 0xffff);
+              if (id >= (unsigned)a.N) id = 0u;
+              atomicOr(&sBitmap[id >> 5], 1u << (id & 31));
+            }
+            sEnt[r * ns + k] = (unsigned short)id;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int w0 = 2 * tid;
+    const unsigned p0 = w0 < L.W ? __popc(sBitmap[w0]) : 0u, p1 = w0 + 1 < L.W ? __popc(sBitmap[w0 + 1]) : 0u;
+    const unsigned sum = p0 + p1;
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) sScan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned v = lane < kBT / 32 ? sScan[lane] : 0u;
+      unsigned vi = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(D3D_FULL_MASK, vi, o);
+        if (lane >= o) vi += up;
+      }
+      if (lane < kBT / 32) sScan[lane] = vi - v;
+      if (lane == 31) sScan[16] = vi;
+    }
+    __syncthreads();
+    const unsigned base = sScan[warp] + incl - sum;
+    if (w0 < L.W) sPrefix[w0] = base;
+    if (w0 + 1 < L.W) sPrefix[w0 + 1] = base + p0;
+  }
+  const int U = (int)sScan[16];
+  __syncthreads();
+  for (int e = tid; e < n_rows * ns; e += kBT) {
+    const unsigned v = sEnt[e];
+    if (v != 0xffffu) sEnt[e] = (unsigned short)(sPrefix[v >> 5] + __popc(sBitmap[v >> 5] & ((1u << (v & 31)) - 1u)));
+  }
+
+  // ---- gradient rows -> 3 bf16 planes of G1 and 3 of G2 (MN-major B operand, K = query) ----------------------------
+  const int n_groups = (cbn + 7) >> 3;
+  mbar_wait(bar_stage, 0u);
+  for (int task = tid; task < kTQ * n_groups; task += kBT) {
+    const int u = task & (kTQ - 1), g = task >> 7;
+    unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
+    unsigned hx[3][4], hy[3][4];
+    if (u >= n_rows) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hx[p][i] = hy[p][i] = 0u;
+    } else {
+      const float* row = reinterpret_cast<const float*>(sA + (size_t)u * L.row_bytes) + 8 * g;
+      const float4 xa = *reinterpret_cast<const float4*>(row);
+      const float4 xb = (8 * g + 4 < cbn) ? *reinterpret_cast<const float4*>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float sc = sOwnerRho[u];
+      const float x[8] = {xa.x * sc, xa.y * sc, xa.z * sc, xa.w * sc, xb.x * sc, xb.y * sc, xb.z * sc, xb.w * sc};
+      const float wx = sOwnerXyz[3 * u] - ctr_x, wy = sOwnerXyz[3 * u + 1] - ctr_y, wz = sOwnerXyz[3 * u + 2] - ctr_z;
+      const int base = (c0 + 8 * g) % 3;
+      const float w0 = rot3(wx, wy, wz, base), w1 = rot3(wy, wz, wx, base), w2 = rot3(wz, wx, wy, base);
+      const float y[8] = {x[0] * w0, x[1] * w1, x[2] * w2, x[3] * w0, x[4] * w1, x[5] * w2, x[6] * w0, x[7] * w1};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        split3_bf16x2(x[2 * i], x[2 * i + 1], hx[0][i], hx[1][i], hx[2][i]);
+        split3_bf16x2(y[2 * i], y[2 * i + 1], hy[0][i], hy[1][i], hy[2][i]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      *reinterpret_cast<uint4*>(dst + (size_t)p * L.plane_bytes) = make_uint4(hx[p][0], hx[p][1], hx[p][2], hx[p][3]);
+      *reinterpret_cast<uint4*>(dst + (size_t)(3 + p) * L.plane_bytes) = make_uint4(hy[p][0], hy[p][1], hy[p][2], hy[p][3]);
+    }
+  }
+  fence_async_smem();
+  __syncthreads();  // planes complete, ranks in place, the staging area (= the A blocks) is free
+
+  const int n_blocks = (U + kUB - 1) / kUB;
+  const int ksteps = (n_rows + 15) >> 4;
+  if (warp < 4) {
+    // ---- A blocks: thread = query; element (q, u) of block m at (q / 8) * 2 KB + (u / 8) * 128 + (q % 8) * 16 + (u % 8) * 2
+    const int info = tid < n_rows ? sOwnerInfo[tid] : 0;
+    const int cur_end = info & 255;
+    int cur = 0;
+    const int* prow = a.by_support + (qbase + (tid < n_rows ? sOwnerId[tid] : 0)) * ns;
+    const unsigned short* e = sEnt + tid * ns;
+    for (int m = 0; m < n_blocks; ++m) {
+      const int buf = m & 1;
+      if (m >= 2) {
+        mbar_wait(bar_mma(buf), (unsigned)(((m >> 1) - 1) & 1));
+        tc_fence_after();
+      }
+      unsigned char* arow = sA + buf * kAtBytes + (tid >> 3) * kAtGroup + (tid & 7) * 16;
+#pragma unroll
+      for (int g = 0; g < kUB / 8; ++g) *reinterpret_cast<uint4*>(arow + g * 128) = make_uint4(0u, 0u, 0u, 0u);
+      const int limit = (m + 1) * kUB;
+      while (cur < cur_end) {
+        const int r = e[cur];
+        if (r >= limit) break;
+        int mult = 1;
+        if (info >> 16) {  // padded query: slot k of the reference list repeats winner k % nvalid
+          const int nv = (info >> 8) & 255;
+          mult = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
+        }
+        *reinterpret_cast<unsigned short*>(arow + ((r & (kUB - 1)) >> 3) * 128 + (r & 7) * 2) = bf16_of_count(mult);
+        ++cur;
+      }
+      fence_async_smem();
+      mbar_arrive(bar_a_full(buf));
+    }
+  } else if (warp == 12) {
+    // ---- MMA issue: D1 += A^T . G1 planes, D2 += A^T . G2 planes; accumulator buffer = 2 * np columns -------------
+    if (lane == 0) {
+      const unsigned idesc = idesc_bf16(L.np, true, true);  // A^T MN-major (M = union rank), B MN-major
+      const unsigned p_addr = smem_u32(sPlanes);
+      for (int m = 0; m < n_blocks; ++m) {
+        const int buf = m & 1;
+        mbar_wait_short(bar_a_full(buf), (unsigned)((m >> 1) & 1));
+        if (m >= 2) mbar_wait_short(bar_acc_free(buf), (unsigned)(((m >> 1) - 1) & 1));
+        tc_fence_after();
+        const unsigned a_addr = smem_u32(sA + buf * kAtBytes);
+        const unsigned acc0 = tmem_base + (unsigned)(buf * 256);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const unsigned long long a_desc = smem_desc(a_addr + ks * 2 * kAtGroup, kAtGroup, 128);
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+            const unsigned long long b_desc = smem_desc(p_addr + p * L.plane_bytes + ks * 2 * L.lbo_b, L.lbo_b, 128);
+            mma_bf16(acc0 + (p < 3 ? 0u : (unsigned)L.np), a_desc, b_desc, idesc, (ks == 0 && (p == 0 || p == 3)) ? 0u : 1u);
+          }
+        }
+        mma_commit(bar_mma(buf));
+      }
+    }
+  } else {
+    // ---- drain: thread = union row of the block (TMEM lane); the two warp groups alternate over the 16-column pieces ----
+    const int lq = warp & 3, t = lq * 32 + lane, grp = (warp - 4) >> 2;
+    float* out_rows = a.out + (size_t)b * a.N * a.C + c0;
+    for (int m = 0; m < n_blocks; ++m) {
+      const int buf = m & 1;
+      const int r = m * kUB + t;
+      int src = -1;
+      float sx = 0.f, sy = 0.f, sz = 0.f;
+      if (r < U) {
+        int lo = 0, hi = L.W - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if ((int)sPrefix[mid] <= r) lo = mid; else hi = mid - 1;
+        }
+        src = lo * 32 + (int)__fns(sBitmap[lo], 0, r - (int)sPrefix[lo] + 1);
+        sx = src_xyz[3 * (size_t)src] - ctr_x; sy = src_xyz[3 * (size_t)src + 1] - ctr_y; sz = src_xyz[3 * (size_t)src + 2] - ctr_z;
+      }
+      mbar_wait(bar_mma(buf), (unsigned)((m >> 1) & 1));
+      tc_fence_after();
+      float* orow = out_rows + (size_t)(src >= 0 ? src : 0) * a.C;
+      for (int ch = grp; ch * 16 < cbn; ch += 2) {
+        unsigned d1[16], d2[16];
+        const unsigned taddr = tmem_base + ((unsigned)(lq * 32) << 16) + (unsigned)(buf * 256 + ch * 16);
+        tmem_ld16(taddr, d1);
+        tmem_ld16(taddr + (unsigned)L.np, d2);
+        tmem_ld_wait();
+        const int base = (c0 + 16 * ch) % 3;
+        const float r0 = rot3(sx, sy, sz, base), r1 = rot3(sy, sz, sx, base), r2 = rot3(sz, sx, sy, base);
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float rc = (i % 3 == 0) ? r0 : ((i % 3 == 1) ? r1 : r2);
+          o[i] = rc * __uint_as_float(d1[i]) - __uint_as_float(d2[i]);
+        }
+        if (src >= 0) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (16 * ch + 4 * v < cbn) red_add_v4(orow + 16 * ch + 4 * v, o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_free(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tmem_base, 512u);
+}
+
+int launch_scatter_bwd(const TileArgs& a, int B, cudaStream_t st) {
+  if (a.M > kMaxPoints || a.N > kMaxPoints || a.nsample > kMaxNs || a.C % 4 != 0) return D3D_ERR_UNSUPPORTED;
+  const int cbn_max = a.C < kCB ? a.C : kCB;
+  const ScatterLayout L = make_scatter_layout(cbn_max, a.nsample, a.N);
+  if ((unsigned)kTQ * L.row_bytes > 2 * kAtBytes) return D3D_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(pospool_scatter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(a.out, 0, (size_t)B * a.N * a.C * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(d3d_ceil_div(a.M, kTQ), d3d_ceil_div(a.C, kCB), B);
+  pospool_scatter_bwd_kernel<<<grid, kBT, L.total, st>>>(a);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <bool kBackward>
@@ -550,6 +914,23 @@ int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const fl
   a.nvalid = nvalid; a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
   a.reduction = reduction; a.inv_radius = 1.0f / radius;
   return launch_tiles<false>(a, B, (cudaStream_t)stream);
+}
+
+int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
+                            const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order,
+                            int B, int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl,
+                            void* stream) {
+  D3D_REQUIRE(grad_out_cl && query_xyz && support_xyz && idx_by_support && nvalid && query_mask && query_order && grad_feat_cl);
+  D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
+  D3D_REQUIRE(reduction == D3D_REDUCE_SUM || reduction == D3D_REDUCE_AVG);
+  if (!aligned16(grad_out_cl) || !aligned16(grad_feat_cl)) return D3D_ERR_UNSUPPORTED;
+  if (B == 0) return 0;
+  if (M == 0) return (int)cudaMemsetAsync(grad_feat_cl, 0, (size_t)B * N * C * sizeof(float), (cudaStream_t)stream);
+  TileArgs a{};
+  a.src = grad_out_cl; a.out = grad_feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.by_support = idx_by_support;
+  a.nvalid = nvalid; a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
+  a.reduction = reduction; a.inv_radius = 1.0f / radius;
+  return launch_scatter_bwd(a, B, (cudaStream_t)stream);
 }
 
 size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample) {

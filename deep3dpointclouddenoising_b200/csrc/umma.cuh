@@ -24,6 +24,9 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // try_wait suspends the thread up to the hinted time (ns) before it reports "not yet": few re-issues while waiting
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
@@ -113,6 +116,11 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned (&r)[16]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// vector reduction into global memory: four consecutive fp32 values, 16-byte aligned (SASS REDG.E.ADD.F32x4)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // ---- exact three-way bf16 split of two fp32 values: x = h1 + h2 + h3 (8 + 8 + 8 mantissa bits) -------------------
 // each result packs (x0 -> low half, x1 -> high half) like two adjacent bf16 in memory

@@ -119,11 +119,21 @@ class PosPoolFunction(Function):
     def backward(ctx, grad_out):
         query_xyz, support_xyz, query_mask = ctx.saved_tensors
         nbr = ctx.nbr
-        rowptr, entries = nbr.csr()
         g_cl = _rows(grad_out)
-        gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,
-                                nbr.nsample, ctx.radius, ctx.reduction,
-                                support_order=_neighbors.spatial_order(support_xyz) if runtime.staged_tiles_backward else None)
+        # False: segmented reduction over the inverse map | 'scatter': the forward tile transposed on the tensor cores, float
+        # atomics across tiles (faster at every level, also for strided lists where the forward tiles are not) |
+        # 'gather': support tiles, fixed order (slower: the union of gathering queries is 3x the forward union)
+        mode = runtime.staged_tiles_backward
+        order = (_neighbors.spatial_order(query_xyz)
+                 if mode == 'scatter' and ctx.reduction != 'sum' and nbr.by_support is not None else None)
+        if order is not None:
+            gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, None, None, nbr.nvalid, query_mask, nbr.n_support,
+                                    nbr.nsample, ctx.radius, ctx.reduction, query_order=order, idx_by_support=nbr.by_support)
+        else:
+            rowptr, entries = nbr.csr()
+            gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,
+                                    nbr.nsample, ctx.radius, ctx.reduction,
+                                    support_order=_neighbors.spatial_order(support_xyz) if mode in (True, 'gather') else None)
         return _logical(gf_cl, ctx.in_cl), None, None, None, None, None, None
 
 

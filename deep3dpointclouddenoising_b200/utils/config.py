@@ -95,10 +95,12 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #     is 0.1-0.4 ms slower with it — the weight gradients run on a side stream either way.
 #   wgrad_side_stream: with grads_in_place, the weight-gradient GEMMs run on a side stream (models/blocks.py); the
 #     training loop joins them with distributed.FlatParameters.reduce() / blocks.join_weight_grads() before the optimiser.
-#   staged_tiles_backward: same for the backward pass (measured slower than the segmented reduction: off).
+#   staged_tiles_backward: 'scatter' (default): PosPool backward as the transposed forward tile on the tensor cores, partial
+#     sums added with float atomics like the reference's backward (203 us against 322 us at the first level); 'gather': the
+#     support-tile form without atomics (slower, 838 us); False: the segmented reduction over the inverse map (bit-reproducible).
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
                     "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
-                    "staged_tiles_backward": False, "own_gemm": True, "wgrad_side_stream": True,
+                    "staged_tiles_backward": "scatter", "own_gemm": True, "wgrad_side_stream": True,
                     "own_wgrad": False, "own_wgrad_min_rows": 0})
 
 

@@ -148,7 +148,16 @@ int d3d_spatial_order(const float* xyz, int B, int N, int* order, void* stream);
 int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx_by_support,
                           const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
                           int nsample, float radius, int reduction, float* out_cl, void* stream);
-/* Workspace of the backward pass: one int per inverse-map entry (union ranks). */
+/* Backward pass in scatter form: the CTA owns the forward tile (128 queries), stages their gradient rows once, and
+ * contracts A^T (the forward multiplicity matrix read through the MN-major descriptor) with them on the tensor cores,
+ * 128 union rows per accumulator; the partial sums of a feature-gradient row over the tiles that reference it are added
+ * with red.global.add.v4.f32 (grad_feat_cl is zero-filled by the call) — float atomics like the reference's own
+ * backward (group_points_gpu.cu:48-69), so results are reproducible to rounding only.  Same limits as the forward. */
+int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
+                            const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order,
+                            int B, int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl,
+                            void* stream);
+/* Workspace of the gather-form backward pass: one int per inverse-map entry (union ranks). */
 size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample);
 int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* rowptr,
                           const int* entries, const int* nvalid, const int* query_mask, const int* support_order, int B,

@@ -146,19 +146,27 @@ def test_fused_ops_against_float_oracle(cuda_device, oracle, C, N, M, ns, radius
 
 
 def test_backward_is_deterministic(cuda_device):
-    """Two backward passes give identical bits (segmented reduction, no float atomics)."""
+    """Two backward passes give identical bits with the segmented reduction (runtime.staged_tiles_backward = False: no
+    float atomics); the default scatter tiles add partial sums atomically like the reference and agree to rounding."""
     from deep3dpointclouddenoising_b200 import fused, neighbors
+    from deep3dpointclouddenoising_b200.utils.config import runtime
     pts, mask, feats, _ = synthetic.make_batch(9, 4, 4096, ragged=True)
     dx, dm = dev(pts, cuda_device), dev(mask, cuda_device)
     f = torch.randn(4, 72, 4096, device=cuda_device, requires_grad=True)
     g = torch.randn(4, 72, 4096, device=cuda_device)
-    grads = []
-    for _ in range(2):
-        neighbors.cache.clear()
-        nbr = neighbors.ball_neighbors(dx, dx, dm, dm, 0.025, 52)
-        y = fused.PosPoolFunction.apply(f, dx, dx, dm, nbr, 0.025, 'avg')
-        grads.append(torch.autograd.grad(y, f, g)[0])
+    old = runtime.staged_tiles_backward
+    try:
+        grads = []
+        for mode in (False, False, 'scatter'):
+            runtime.staged_tiles_backward = mode
+            neighbors.cache.clear()
+            nbr = neighbors.ball_neighbors(dx, dx, dm, dm, 0.025, 52)
+            y = fused.PosPoolFunction.apply(f, dx, dx, dm, nbr, 0.025, 'avg')
+            grads.append(torch.autograd.grad(y, f, g)[0])
+    finally:
+        runtime.staged_tiles_backward = old
     assert torch.equal(grads[0], grads[1])
+    torch.testing.assert_close(grads[2], grads[0], rtol=1e-4, atol=2e-5)
 
 
 @pytest.mark.parametrize("C,N,M,ns,radius", [(72, 2048, 2048, 52, 0.025), (144, 2048, 512, 39, 0.03), (288, 512, 512, 32, 0.05),

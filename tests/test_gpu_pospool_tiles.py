@@ -109,6 +109,9 @@ def test_staged_pospool_against_float_oracle(cuda_device, oracle, C, N, M, ns, r
     np.testing.assert_allclose(out.cpu().numpy(), legacy.cpu().numpy(), **FWD)
     legacy_g = ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction)
     np.testing.assert_allclose(gf.cpu().numpy(), legacy_g.cpu().numpy(), **BWD)
+    # scatter form: the forward tile's transposed contraction, partial sums added with float atomics
+    gs = ops.pospool_bwd(g_cl, dq, ds, None, None, dnv, dqm, N, ns, radius, reduction, query_order=oq, idx_by_support=dbys)
+    np.testing.assert_allclose(gs.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
 
 
 def test_staged_pospool_at_the_benched_level0_shape(cuda_device, oracle):
@@ -130,6 +133,8 @@ def test_staged_pospool_at_the_benched_level0_shape(cuda_device, oracle):
     rowptr, entries = ops.build_inverse_map(didx, N)
     gf = ops.pospool_bwd(g_cl, ds, ds, rowptr, entries, dnv, dsm, N, ns, radius, 'avg', support_order=order)
     np.testing.assert_allclose(gf.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
+    gs = ops.pospool_bwd(g_cl, ds, ds, None, None, dnv, dsm, N, ns, radius, 'avg', query_order=order, idx_by_support=dbys)
+    np.testing.assert_allclose(gs.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
 
 
 def test_staged_pospool_far_from_the_origin(cuda_device, oracle):

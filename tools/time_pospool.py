@@ -52,6 +52,7 @@ def main():
         t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys))
         t["bwd gather"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg'))
         t["bwd tiles"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg', support_order=os_))
+        t["bwd scatter"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys))
         a = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg')
         b = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys)
         err = ((a - b).abs().max() / a.abs().max()).item()
