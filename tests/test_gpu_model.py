@@ -30,21 +30,27 @@ def _build(kind, num_points, device):
 @pytest.mark.parametrize("kind", ["pospool", "pseudo_grid"])
 def test_forward_backward_and_cache_equivalence(cuda_device, kind):
     from deep3dpointclouddenoising_b200 import neighbors
+    from deep3dpointclouddenoising_b200.utils.config import runtime
     B, N = 2, 1024
     model, criterion = _build(kind, N, cuda_device)
     pts, mask, feats, offs = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(5, B, N, ragged=True)]
     results = []
-    for cache_on in (True, False):
-        neighbors.cache.enabled = cache_on
-        model.zero_grad(set_to_none=True)
-        pred = model(pts, mask, feats)
-        assert pred.shape == (B, 3, N) and torch.isfinite(pred).all()
-        loss = criterion(pred.transpose(1, 2), offs, mask)
-        loss.backward()
-        grads = {n: p.grad.clone() for n, p in model.named_parameters()}
-        assert all(g is not None and torch.isfinite(g).all() for g in grads.values())
-        results.append((pred.detach().clone(), loss.item(), grads))
-    neighbors.cache.enabled = True
+    # bit-for-bit comparison: PosPool backward without float atomics (the default scatter tiles agree to rounding only)
+    old, runtime.staged_tiles_backward = runtime.staged_tiles_backward, False
+    try:
+        for cache_on in (True, False):
+            neighbors.cache.enabled = cache_on
+            model.zero_grad(set_to_none=True)
+            pred = model(pts, mask, feats)
+            assert pred.shape == (B, 3, N) and torch.isfinite(pred).all()
+            loss = criterion(pred.transpose(1, 2), offs, mask)
+            loss.backward()
+            grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+            assert all(g is not None and torch.isfinite(g).all() for g in grads.values())
+            results.append((pred.detach().clone(), loss.item(), grads))
+    finally:
+        neighbors.cache.enabled = True
+        runtime.staged_tiles_backward = old
     assert torch.equal(results[0][0], results[1][0]) and results[0][1] == results[1][1]
     for n in results[0][2]:
         assert torch.equal(results[0][2][n], results[1][2][n]), n

@@ -7,6 +7,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _bit_reproducible_backward():
+    """These tests compare training steps bit for bit (to 1e-6): PosPool backward without float atomics."""
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    old, runtime.staged_tiles_backward = runtime.staged_tiles_backward, False
+    yield
+    runtime.staged_tiles_backward = old
+
+
 def _setup(seed=0):
     import bench
     from deep3dpointclouddenoising_b200 import synthetic
