@@ -108,9 +108,10 @@ class PosPoolFunction(Function):
         # parity tolerance of a mean; a plain sum of nsample terms is nsample times larger in absolute terms)
         staged = runtime.staged_tiles == 'always' or (runtime.staged_tiles and reduction != 'sum'
                                                       and query_xyz.shape[1] == support_xyz.shape[1])
+        plan = nbr.tile_plan(query_xyz, query_mask) if staged else None
         out_cl = ops.pospool_fwd(feat_cl, query_xyz, support_xyz, nbr.idx, nbr.nvalid, query_mask, radius, reduction,
-                                 query_order=_neighbors.spatial_order(query_xyz) if staged else None,
-                                 idx_by_support=nbr.by_support)
+                                 query_order=_neighbors.spatial_order(query_xyz) if plan is not None else None,
+                                 idx_by_support=nbr.by_support, plan=plan)
         ctx.nbr, ctx.radius, ctx.reduction = nbr, radius, reduction
         ctx.save_for_backward(query_xyz, support_xyz, query_mask)
         return _logical(out_cl, runtime.channel_last)
@@ -124,11 +125,13 @@ class PosPoolFunction(Function):
         # atomics across tiles (faster at every level, also for strided lists where the forward tiles are not) |
         # 'gather': support tiles, fixed order (slower: the union of gathering queries is 3x the forward union)
         mode = runtime.staged_tiles_backward
-        order = (_neighbors.spatial_order(query_xyz)
-                 if mode == 'scatter' and ctx.reduction != 'sum' and nbr.by_support is not None else None)
+        plan = (nbr.tile_plan(query_xyz, query_mask)
+                if mode == 'scatter' and ctx.reduction != 'sum' and nbr.by_support is not None else None)
+        order = _neighbors.spatial_order(query_xyz) if plan is not None else None
         if order is not None:
             gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, None, None, nbr.nvalid, query_mask, nbr.n_support,
-                                    nbr.nsample, ctx.radius, ctx.reduction, query_order=order, idx_by_support=nbr.by_support)
+                                    nbr.nsample, ctx.radius, ctx.reduction, query_order=order, idx_by_support=nbr.by_support,
+                                    plan=plan)
         else:
             rowptr, entries = nbr.csr()
             gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,

@@ -52,13 +52,14 @@ class _Produced:
 
 class NeighborList(_Produced):
     __slots__ = ("idx", "idx_mask", "nvalid", "n_support", "by_support", "_csr", "_keepalive", "_stream", "_event",
-                 "_csr_event", "_csr_stream")
+                 "_csr_event", "_csr_stream", "_plan", "_plan_event", "_plan_stream")
 
     def __init__(self, idx, idx_mask, nvalid, n_support, keepalive=(), by_support=None):
         self.idx, self.idx_mask, self.nvalid, self.n_support = idx, idx_mask, nvalid, n_support
         self.by_support = by_support  # winners in ascending support index (staged-tile kernels), or None
         self._csr = None
         self._csr_event, self._csr_stream = None, None
+        self._plan, self._plan_event, self._plan_stream = None, None, None
         self._keepalive = keepalive  # the tensors the cache key points at must outlive the entry
         self._mark()
 
@@ -76,6 +77,25 @@ class NeighborList(_Produced):
         elif self._csr_event is not None and torch.cuda.current_stream() != self._csr_stream:
             torch.cuda.current_stream().wait_event(self._csr_event)
         return self._csr
+
+
+    def tile_plan(self, query_xyz, query_mask):
+        """Tile plan of this list under the Morton order of its queries (staged-tile PosPool kernels), built once; None
+        when the list has no by-support form or the sizes are beyond the kernels' limits."""
+        if self._plan is None:
+            order = spatial_order(query_xyz)
+            if order is None or self.by_support is None or self.idx.shape[-1] > ops.TILE_MAX_NSAMPLE \
+                    or self.n_support > ops.TILE_MAX_POINTS:
+                return None
+            with torch.no_grad():
+                self._plan = ops.tile_plan(self.by_support, self.nvalid, query_mask, order, self.n_support)
+            if _building_on_side[0]:
+                self._plan_stream = torch.cuda.current_stream()
+                self._plan_event = torch.cuda.Event()
+                self._plan_event.record(self._plan_stream)
+        elif self._plan_event is not None and torch.cuda.current_stream() != self._plan_stream:
+            torch.cuda.current_stream().wait_event(self._plan_event)
+        return self._plan
 
 
 class _Subsampled(_Produced):
@@ -196,6 +216,7 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order=True):
             levels, lists = [(xyz, mask)], [ball_neighbors(xyz, xyz, mask, mask, radius, nsample0)]
             if with_order:  # every level runs a self query (PosPool forward as staged tiles)
                 spatial_order(xyz)
+                lists[0].tile_plan(xyz, mask)
             for sample_dl, npoint, r_in, ns_in, r_out, ns_out in stages:
                 px, pm = levels[-1]
                 sx, sm = grid_subsample(px, pm, npoint, sample_dl)
@@ -203,12 +224,19 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order=True):
                 lists.append(ball_neighbors(sx, sx, sm, sm, r_out, ns_out))
                 if with_order:
                     spatial_order(sx)
+                    lists[-1].tile_plan(sx, sm)
+                    if with_csr:  # the strided list's plan serves the scatter-form backward only
+                        lists[-2].tile_plan(sx, sm)
                 levels.append((sx, sm))
             ups = [nearest_neighbors(levels[k - 1][0], levels[k][0], levels[k - 1][1], levels[k][1])
                    for k in range(len(levels) - 1, 0, -1)]
             if with_csr:  # in the order backward asks for them: decoder first, then coarse to fine
-                for nbr in ups + lists[::-1]:
-                    nbr.csr()
+                from .utils.config import runtime
+                # self lists feed local aggregation only: PosPool's scatter-form backward works from the tile plan
+                skip_self = with_order and runtime.staged_tiles and runtime.staged_tiles_backward == 'scatter'
+                for k, nbr in [(None, u) for u in ups] + list(enumerate(lists))[::-1]:
+                    if not (skip_self and k is not None and k % 2 == 0 and nbr._plan is not None):
+                        nbr.csr()
             final = torch.cuda.Event()
             final.record(side)
     finally:
@@ -275,7 +303,7 @@ def adopt(xyz, mask):
 def _tensors(item):
     if isinstance(item, NeighborList):
         csr = item._csr if item._csr is not None else (None, None)
-        return [item.idx, item.idx_mask, item.nvalid, item.by_support, csr[0], csr[1]]
+        return [item.idx, item.idx_mask, item.nvalid, item.by_support, csr[0], csr[1], item._plan]
     if isinstance(item, _Subsampled):
         return [item.sub_xyz, item.sub_mask]
     return [item.order]
@@ -293,6 +321,7 @@ def settle(device=None):
         item._event = None
         if isinstance(item, NeighborList):
             item._csr_event = None
+            item._plan_event = None
     _pending[key] = (pending[0], pending[1], None, pending[3], pending[4])
 
 

@@ -240,10 +240,25 @@ def _tiles_ok(M, N, ns, C):
     return 0 < M <= TILE_MAX_POINTS and N <= TILE_MAX_POINTS and ns <= TILE_MAX_NSAMPLE and C % 4 == 0
 
 
+def tile_plan(idx_by_support, nvalid, query_mask, query_order, n_support):
+    """Tile plan (uint8 buffer) of one (neighbour list, query order) pair for the staged-tile PosPool kernels: union
+    sizes, unions and union ranks per tile of 128 queries (d3d_pospool_tile_plan); shared by forward and backward."""
+    L = _lib.load()
+    bys = _i32(idx_by_support, "idx_by_support")
+    B, M, ns = bys.shape
+    with torch.cuda.device(bys.device):
+        plan = _out((max(int(L.d3d_pospool_tile_plan_bytes(B, M, int(n_support), ns)), 16),), torch.uint8, bys.device)
+        _lib.check(L.d3d_pospool_tile_plan(_p(bys), _p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")),
+                                           _p(_i32(query_order, "query_order")), B, M, int(n_support), ns, _p(plan),
+                                           plan.numel(), _stream()), "d3d_pospool_tile_plan")
+    _count()
+    return plan
+
+
 def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius, reduction, query_order=None,
-                idx_by_support=None):
-    """query_order (B, M) from `spatial_order` + idx_by_support from `ball_query`: the staged-tile tensor-core kernel;
-    otherwise the per-query gather kernel."""
+                idx_by_support=None, plan=None):
+    """query_order (B, M) from `spatial_order` + idx_by_support from `ball_query` (+ the pair's `tile_plan`, built here
+    when not given): the staged-tile tensor-core kernel; otherwise the per-query gather kernel."""
     L = _lib.load()
     f = _f32(feat_cl, "features")
     B, N, C = f.shape
@@ -253,8 +268,10 @@ def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius
         xyz = (_p(_f32(query_xyz, "query_xyz")), _p(_f32(support_xyz, "support_xyz")))
         tail = (_p(_i32(nvalid, "nvalid")), _p(_i32(query_mask, "query_mask")))
         if query_order is not None and idx_by_support is not None and _tiles_ok(M, N, ns, C):
+            if plan is None:
+                plan = tile_plan(idx_by_support, nvalid, query_mask, query_order, N)
             _lib.check(L.d3d_pospool_tiles_fwd(_p(f), *xyz, _p(_i32(idx_by_support, "idx_by_support")), *tail,
-                                               _p(_i32(query_order, "query_order")), B, M, N, C, ns, float(radius),
+                                               _p(_i32(query_order, "query_order")), _p(plan), B, M, N, C, ns, float(radius),
                                                REDUCTIONS[reduction], _p(out), _stream()), "d3d_pospool_tiles_fwd")
         else:
             _lib.check(L.d3d_pospool_fwd(_p(f), *xyz, _p(_i32(idx, "idx")), *tail, B, M, N, C, ns, float(radius),
@@ -264,7 +281,7 @@ def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius
 
 
 def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, query_mask, n_support, nsample, radius,
-                reduction, support_order=None, query_order=None, idx_by_support=None):
+                reduction, support_order=None, query_order=None, idx_by_support=None, plan=None):
     """query_order (B, M) + idx_by_support (the forward tile's inputs): the scatter-form staged-tile kernel (tensor cores,
     float atomics across tiles); support_order (B, N): the gather-form staged-tile kernel; otherwise the per-support
     segmented reduction over the inverse map."""
@@ -275,9 +292,11 @@ def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, qu
         out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
         if (query_order is not None and idx_by_support is not None and _tiles_ok(M, int(n_support), int(nsample), C)
                 and 128 * min(C, 72) * 4 <= 65536):
+            if plan is None:
+                plan = tile_plan(idx_by_support, nvalid, query_mask, query_order, n_support)
             _lib.check(L.d3d_pospool_scatter_bwd(_p(g), _p(query_xyz), _p(support_xyz),
                                                  _p(_i32(idx_by_support, "idx_by_support")), _p(nvalid), _p(query_mask),
-                                                 _p(_i32(query_order, "query_order")), B, M, int(n_support), C,
+                                                 _p(_i32(query_order, "query_order")), _p(plan), B, M, int(n_support), C,
                                                  int(nsample), float(radius), REDUCTIONS[reduction], _p(out), _stream()),
                        "d3d_pospool_scatter_bwd")
         elif support_order is not None and _tiles_ok(M, int(n_support), int(nsample), C):

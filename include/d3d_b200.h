@@ -145,9 +145,16 @@ int d3d_spatial_order(const float* xyz, int B, int N, int* order, void* stream);
  * accumulation); the backward pass owns 128 SUPPORT rows and is a fixed-order reduction (no float atomics).
  *   replaces ref: pt_custom_ops/_ext_src/src/group_points_gpu.cu:13-33,48-69 + models/local_aggregation_operators.py:140-183
  * Limits: M, N <= 16384, nsample <= 64, C % 4 == 0 (D3D_ERR_UNSUPPORTED otherwise). */
+/* Tile plan of one (neighbour list, query order) pair, shared by every forward / scatter-backward launch on that pair
+ * (two LocalAggregation layers use the level-0 list: four launches): per tile of 128 queries the size of the union of
+ * the support rows they gather, the union itself (ascending indices) and the union rank of every list entry.  `plan`:
+ * d3d_pospool_tile_plan_bytes(B, M, N, nsample) bytes, 256-byte aligned. */
+size_t d3d_pospool_tile_plan_bytes(int B, int M, int N, int nsample);
+int d3d_pospool_tile_plan(const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order, int B,
+                          int M, int N, int nsample, void* plan, size_t plan_bytes, void* stream);
 int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx_by_support,
-                          const int* nvalid, const int* query_mask, const int* query_order, int B, int M, int N, int C,
-                          int nsample, float radius, int reduction, float* out_cl, void* stream);
+                          const int* nvalid, const int* query_mask, const int* query_order, const void* plan, int B, int M,
+                          int N, int C, int nsample, float radius, int reduction, float* out_cl, void* stream);
 /* Backward pass in scatter form: the CTA owns the forward tile (128 queries), stages their gradient rows once, and
  * contracts A^T (the forward multiplicity matrix read through the MN-major descriptor) with them on the tensor cores,
  * 128 union rows per accumulator; the partial sums of a feature-gradient row over the tiles that reference it are added
@@ -155,8 +162,8 @@ int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const fl
  * backward (group_points_gpu.cu:48-69), so results are reproducible to rounding only.  Same limits as the forward. */
 int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
                             const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order,
-                            int B, int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl,
-                            void* stream);
+                            const void* plan, int B, int M, int N, int C, int nsample, float radius, int reduction,
+                            float* grad_feat_cl, void* stream);
 /* Workspace of the gather-form backward pass: one int per inverse-map entry (union ranks). */
 size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample);
 int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* rowptr,

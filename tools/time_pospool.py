@@ -48,11 +48,13 @@ def main():
         f = torch.randn(B, N, C, device=dev)
         g = torch.randn(B, M, C, device=dev)
         t = {}
+        plan = ops.tile_plan(bys, nv, qm, oq, N)
+        t["plan"] = timeit(lambda: ops.tile_plan(bys, nv, qm, oq, N))
         t["fwd gather"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg'))
-        t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys))
+        t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan))
         t["bwd gather"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg'))
         t["bwd tiles"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg', support_order=os_))
-        t["bwd scatter"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys))
+        t["bwd scatter"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan))
         a = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg')
         b = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys)
         err = ((a - b).abs().max() / a.abs().max()).item()
