@@ -1279,8 +1279,7 @@ int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const fl
   a.src = feat_cl; a.out = out_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.by_support = idx_by_support;
   a.nvalid = nvalid; a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
   a.reduction = reduction; a.inv_radius = 1.0f / radius; a.plan = plan;
-  static const bool old_form = getenv("D3D_TILES_FWD_OLD") != nullptr;  // experiments: the unpipelined chunk loop
-  return old_form ? launch_tiles<false>(a, B, (cudaStream_t)stream) : launch_fwd_pipelined(a, B, (cudaStream_t)stream);
+  return launch_fwd_pipelined(a, B, (cudaStream_t)stream);
 }
 
 int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
