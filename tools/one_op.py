@@ -15,13 +15,21 @@ kp = torch.randn(15, 3, device=dev) * 0.006; w = torch.randn(15, C, device=dev)
 rowptr, entries = ops.build_inverse_map(idx, N)
 order = ops.spatial_order(pts)
 wg = torch.randn(144, C, device=dev)
+plan = ops.tile_plan(bys, nv, mask, order, N)
+gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+ybn, mean, invstd = ops.bn_act_cl_fwd(f, None, gam, bet, rm, rv, 1e-5, 0.1, True, True)
 torch.cuda.synchronize()
 for _ in range(n):
     if op == "ball_query": ops.ball_query(pts, pts, mask, mask, 0.025, 52)
     elif op == "inverse_map": ops.build_inverse_map(idx, N)
     elif op == "pospool_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg')
     elif op == "pospool_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg')
-    elif op == "pospool_tiles_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys)
+    elif op == "pospool_tiles_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys, plan=plan)
+    elif op == "pospool_scatter_bwd": ops.pospool_bwd(f, pts, pts, None, None, nv, mask, N, 52, 0.025, 'avg', query_order=order, idx_by_support=bys, plan=plan)
+    elif op == "tile_plan": ops.tile_plan(bys, nv, mask, order, N)
+    elif op == "bn_bwd": ops.bn_act_cl_bwd(f, f, ybn, gam, bet, mean, invstd, True, 1, False)
+    elif op == "bn_fwd": ops.bn_act_cl_fwd(f, None, gam, bet, rm, rv, 1e-5, 0.1, True, True)
     elif op == "pospool_tiles_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg', support_order=order)
     elif op == "gemm": ops.gemm_tf32(f.view(-1, C), wg)
     elif op == "gemm_stats": ops.gemm_tf32(f.view(-1, C), wg, want_stats=True)

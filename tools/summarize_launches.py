@@ -13,7 +13,7 @@ OURS = re.compile(r"ball_query_kernel|ball_grid_build|ball_nearest|nearest_query
                   r"transpose_kernel|count_kernel|scan_kernel|fill_kernel|sort_short_kernel|sort_long_kernel|aggregate_|"
                   r"nearest_gather|pseudogrid_|reduce_partials|inverse_|bn_stats|bn_apply|bn_bwd|bn_eval|chunk_count|chunk_scan|"
                   r"chunk_fill|chunk_sort|bbox_kernel|cell_count|cell_fill|nn_query|radius_patch|vote_kernel|voxel_id|barycentre|"
-                  r"gemm_tf32|bn_finalize|pospool_tiles|spatial_order|wgrad_")
+                  r"gemm_tf32|bn_finalize|pospool_tiles|pospool_scatter|pospool_fwd_pipelined|tile_plan|spatial_order|wgrad_")
 
 
 def short(name):
