@@ -489,6 +489,7 @@ def main():
     # the backward pass of batch k runs (it depends on coordinates only), and handed over at fixed addresses at the end
     # of the step; every replay trains on the batch the previous replay received.  D3D_PIPELINE=0: build inside forward.
     pipelined = use_graph and os.environ.get("D3D_PIPELINE", "1") != "0"
+    handover = torch.cuda.Stream() if pipelined else None
 
     def train_step_pipelined(cur, nxt):
         from deep3dpointclouddenoising_b200 import neighbors
@@ -497,11 +498,17 @@ def main():
         model.prefetch_neighbors(nxt[0], nxt[1])
         loss.backward()
         bucket.reduce()
+        # hand-over on a second stream, concurrently with the clipping and the optimiser (backward is complete: nothing
+        # reads this batch's pyramid or inputs any more)
+        main = torch.cuda.current_stream()
+        handover.wait_stream(main)
+        with torch.cuda.stream(handover):
+            neighbors.fold_pending_into_current()  # next batch's pyramid -> the addresses the next replay's forward reads
+            for d, src in zip(cur, nxt):
+                d.copy_(src)
         torch.nn.utils.clip_grad_norm_(opt_params, 10)
         opt.step()
-        neighbors.fold_pending_into_current()  # next batch's pyramid -> the addresses the next replay's forward reads
-        for d, src in zip(cur, nxt):
-            d.copy_(src)
+        main.wait_stream(handover)
         return loss
 
     def barrier():
