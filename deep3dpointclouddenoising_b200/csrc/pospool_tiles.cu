@@ -1,26 +1,25 @@
-// PosPool ('xyz' embedding, sum / avg) as a staged-tile kernel: bulk-asynchronous row staging + tcgen05 contraction.
+// PosPool ('xyz' embedding, sum / avg) as staged-tile kernels: bulk-asynchronous row staging + tcgen05 contraction.
 //
 //   ref: u_net_arch/models/local_aggregation_operators.py:140-147,165-183   (PosPool forward; autograd backward)
 //   ref: u_net_arch/pt_custom_ops/_ext_src/src/group_points_gpu.cu:13-33,48-69 (the gather / scatter-add it replaces)
 //
 // The per-query gather kernel (aggregate.cu) reads every (query, slot) row into registers: 1.96 GB through the LSU
-// write-back path at the first level, although 128 spatially adjacent queries only touch ~390 distinct rows.  Here a
-// CTA owns 128 rows that are adjacent in space (spatial_order.cu) and
-//   1. builds the UNION of the source rows their neighbourhoods reference (shared-memory bitmap + popcount ranks),
-//   2. stages the union 64 rows at a time with cp.async.bulk (global -> shared, no register write-back, completion
-//      counted on an mbarrier),
-//   3. turns the neighbourhood lists into a dense 128 x 64 multiplicity matrix A (0/1/2.. — exact in bf16); every
-//      row walks its list with a cursor: the ball query also emits each query's winners in ascending support index
-//      (idx_by_support), union ranks are monotone in the index, so a chunk consumes a contiguous run of the list,
-//   4. contracts  Y1 = A . X  and  Y2 = A . (w * X)  on the tensor cores (tcgen05.mma, accumulators in TMEM), where
-//      w[u, c] = (P[u] - centre)[c mod 3] is the source row's own coordinate relative to the tile centre.
-// PosPool's weight (P[u] - P[owner])[c mod 3] is bilinear in the two positions, so
-//      forward :  out[q, c]  =  rho_q  * (Y2[q, c] - (Q[q] - centre)[c mod 3] * Y1[q, c])       X = features
-//      backward:  dF[i, c]   = -1      * (Y2[i, c] - (S[i] - centre)[c mod 3] * Y1[i, c])       X = sigma_q * grad_out
-// with rho_q = sigma_q = 1 / (radius * neighbourhood size) (avg) or 1 / radius (sum).  The backward pass is the same
-// kernel with the roles swapped: a CTA owns 128 SUPPORT points and the union runs over the queries that gathered
-// them (inverse map) — a fixed-order reduction inside the tensor core, no float atomics.
-// fp32 accuracy: A is exact; X and w * X are split into three bf16 terms each (8 + 8 + 8 mantissa bits, an exact
+// write-back path at the first level, although 128 spatially adjacent queries only touch ~460 distinct rows.  Here a
+// CTA owns a TILE of 128 queries that are adjacent in space (spatial_order.cu).  Per (neighbour list, order) pair the
+// tile plan kernel computes once: the UNION of the support rows the tile gathers (shared-memory bitmap + popcount
+// ranks) and the union rank of every list entry.  With A the 128 x U multiplicity matrix of the tile (0/1/2.. — exact
+// in bf16; every row walks its list with a cursor: the ball query emits each query's winners in ascending support
+// index, union ranks are monotone in the index, so a chunk consumes a contiguous run of the list) and
+// w[u, c] = (S[u] - centre)[c mod 3] the union row's own coordinate relative to the tile centre — PosPool's weight
+// (S[u] - Q[q])[c mod 3] is bilinear in the two positions —
+//      forward  (pospool_fwd_pipelined_kernel):  out[q, c] = rho_q * (Y2[q, c] - (Q[q] - centre)[c mod 3] * Y1[q, c]),
+//                                                Y1 = A . X,  Y2 = A . (w * X),  X = the staged feature rows
+//      backward (pospool_scatter_bwd_kernel):    dF[u, c] += (S[u] - centre)[c mod 3] * D1[u, c] - D2[u, c],
+//                                                D1 = A^T . G1,  D2 = A^T . G2,  G1 = rho * g,  G2 = rho * (Q - centre) * g
+// with rho_q = 1 / (radius * neighbourhood size) (avg) or 1 / radius (sum).  Rows travel global -> shared with
+// cp.async.bulk (no register write-back, completion counted on an mbarrier); the contractions run on tcgen05.mma with
+// accumulators in TMEM.
+// fp32 accuracy: A is exact; X, w * X, G1, G2 are split into three bf16 terms each (8 + 8 + 8 mantissa bits, an exact
 // decomposition), products are exact, accumulation is fp32 in TMEM.  Centring on the tile keeps the cancellation in
 // (Y2 - rc * Y1) at the scale of (tile extent + radius) / radius.
 #include <cstdlib>
@@ -32,30 +31,23 @@ namespace {
 
 using namespace umma;
 
-constexpr int kTQ = 128;          // owner rows per CTA = MMA M = TMEM lanes
-constexpr int kThreads = 384;     // warps 0-3 fill A (thread = owner row), the others start converting, the last two also select rows
-constexpr int kKC = 64;           // source rows per chunk (4 K-steps of 16)
+constexpr int kTQ = 128;          // queries per tile = TMEM lanes
 constexpr int kCB = 72;           // channels per CTA (multiple of 24: 8-channel groups and the c mod 3 phase line up)
-constexpr int kMaxPoints = 16384; // the source bitmap lives in shared memory
+constexpr int kMaxPoints = 16384; // union indices and ranks are uint16; the plan kernel's bitmap lives in shared memory
 constexpr int kMaxNs = 64;
-constexpr unsigned kASbo = (kKC / 8) * 128;      // A: K-major, 8-row groups 1024 B apart, K chunks 128 B apart
-constexpr unsigned kABytes = (kTQ / 8) * kASbo;  // 16 KB
 
 struct TileArgs {
   const float* src;          // rows that are staged: features (B, N, C) forward, grad_out (B, M, C) backward
   float* out;                // (B, M, C) forward, (B, N, C) backward
   const float* query_xyz;    // (B, M, 3)
   const float* support_xyz;  // (B, N, 3)
-  const int* by_support;     // (B, M, ns) forward: winners in ascending support index, (distance rank << 16) | index
+  const int* by_support;     // (B, M, ns) winners in ascending support index, (distance rank << 16) | index
   const int* nvalid;         // (B, M)
   const int* query_mask;     // (B, M)
-  const int* rowptr;         // inverse map (backward)
-  const int* entries;
-  int* rank_scratch;         // backward: one int per inverse-map entry (union rank of its query, -1 = masked slot)
-  const int* order;          // (B, owners) processing order of the owner rows
+  const int* order;          // (B, M) processing order of the queries
   int M, N, C, nsample, reduction;
   float inv_radius;
-  const void* plan;          // tile plan of (by_support, order): forward tiles and scatter-form backward tiles
+  const void* plan;          // tile plan of (by_support, order)
   unsigned long long* timing;  // diagnostics (tools/tile_phases.py): 8 timestamps per CTA, or null
 };
 
@@ -70,42 +62,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
   if (a.timing && tid == 0)                                                                                           \
   a.timing[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + (k)] = now_ns()
 
-struct Layout {
-  unsigned a, planes, plane_bytes, lbo_b, stage, row_bytes, ent, bitmap, prefix, owner_id, owner_info, owner_xyz, owner_rho,
-      src_id, src_w, src_scale, scan, bars, total;
-  int W, np, tmem_cols;
-};
-
 __host__ __device__ inline unsigned align16(unsigned x) { return (x + 15u) & ~15u; }
-
-__host__ __device__ inline Layout make_layout(int cbn, int ns, int n_src, bool backward) {
-  Layout L;
-  unsigned o = 0;
-  L.a = o; o += kABytes;
-  L.lbo_b = (unsigned)((cbn + 7) / 8) * 128u;  // MN-major planes: 8-channel chunks 128 B apart, 8-row K groups lbo_b apart
-  L.plane_bytes = (kKC / 8) * L.lbo_b;
-  L.planes = o; o += 6 * L.plane_bytes + 128;  // +128: the MMA reads N rounded up to 16 channels
-  L.row_bytes = (unsigned)cbn * 4u;
-  L.stage = o; o += kKC * L.row_bytes;
-  L.ent = o; o += backward ? 0u : align16((unsigned)(kTQ * ns * 2));
-  L.W = (n_src + 31) / 32;
-  L.bitmap = o; o += align16((unsigned)L.W * 4u);
-  L.prefix = o; o += align16((unsigned)(L.W + 1) * 4u);
-  L.owner_id = o; o += kTQ * 4;
-  L.owner_info = o; o += kTQ * 4;
-  L.owner_xyz = o; o += kTQ * 12;
-  L.owner_rho = o; o += kTQ * 4;
-  L.src_id = o; o += 2 * kKC * 4;
-  L.src_w = o; o += 2 * kKC * 12;
-  L.src_scale = o; o += 2 * kKC * 4;
-  L.scan = o; o += 32 * 4;
-  L.bars = o; o += 32;
-  L.total = o;
-  L.np = (cbn + 15) & ~15;
-  L.tmem_cols = 32;
-  while (L.tmem_cols < 2 * L.np) L.tmem_cols <<= 1;
-  return L;
-}
 
 __device__ __forceinline__ float rot3(float x, float y, float z, int r) { return r == 0 ? x : (r == 1 ? y : z); }
 
@@ -241,381 +198,6 @@ tile_plan_kernel(const int* __restrict__ by_support, const int* __restrict__ nva
     }
   }
 }
-
-template <bool kBackward>
-__global__ void __launch_bounds__(kThreads, 2)
-pospool_tiles_kernel(const TileArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, b = blockIdx.z;
-  const int c0 = blockIdx.y * kCB, cbn = min(kCB, a.C - c0);
-  const int n_own = kBackward ? a.N : a.M, n_src = kBackward ? a.M : a.N;
-  const int ns = a.nsample;
-  const Layout L = make_layout(cbn, ns, n_src, kBackward);
-
-  unsigned char* sA = smem + L.a;
-  unsigned char* sPlanes = smem + L.planes;
-  unsigned char* sStage = smem + L.stage;
-  unsigned short* sEnt = reinterpret_cast<unsigned short*>(smem + L.ent);  // forward: union rank of every list entry
-  unsigned* sBitmap = reinterpret_cast<unsigned*>(smem + L.bitmap);
-  unsigned* sPrefix = reinterpret_cast<unsigned*>(smem + L.prefix);
-  int* sOwnerId = reinterpret_cast<int*>(smem + L.owner_id);
-  int* sOwnerInfo = reinterpret_cast<int*>(smem + L.owner_info);  // forward: entries | nvalid << 8 | padded << 16
-  float* sOwnerXyz = reinterpret_cast<float*>(smem + L.owner_xyz);
-  float* sOwnerRho = reinterpret_cast<float*>(smem + L.owner_rho);
-  int* sSrcId = reinterpret_cast<int*>(smem + L.src_id);           // [2][kKC]
-  float* sSrcW = reinterpret_cast<float*>(smem + L.src_w);         // [2][kKC][3]
-  float* sSrcScale = reinterpret_cast<float*>(smem + L.src_scale); // [2][kKC]
-  unsigned* sScan = reinterpret_cast<unsigned*>(smem + L.scan);    // [0..15] warp partials, [16] total
-  int* sTask = reinterpret_cast<int*>(smem + L.scan) + 17;         // [17..18] conversion task counters of the two parities
-  float* sCtr = reinterpret_cast<float*>(smem + L.scan) + 20;      // [20..31] 4 warps x (x, y, z) centre sums
-  const unsigned bar_stage = smem_u32(smem + L.bars), bar_mma = bar_stage + 8, tmem_slot = bar_stage + 16, bar_plan = bar_stage + 24;
-
-  const float* own_xyz = (kBackward ? a.support_xyz : a.query_xyz) + (size_t)b * n_own * 3;
-  const float* src_xyz = (kBackward ? a.query_xyz : a.support_xyz) + (size_t)b * n_src * 3;
-  const int* order = a.order + (size_t)b * n_own;
-  const int row0 = tile * kTQ;
-  const int n_rows = min(kTQ, n_own - row0);
-  const size_t qbase = (size_t)b * a.M;
-
-  D3D_STAMP(0);
-  // ---- P0: owners, barriers, TMEM ---------------------------------------------------------------------------------
-  if (warp == 4) tmem_alloc(tmem_slot, (unsigned)L.tmem_cols);
-  if (tid == 160) {  // a warp that does not allocate TMEM
-    mbar_init(bar_stage, 1);
-    mbar_init(bar_mma, 1);
-    mbar_init(bar_plan, 1);
-    mbar_init_fence();
-  }
-  if (tid < kTQ) {
-    int own = -1, info = 0;
-    float px = 0.f, py = 0.f, pz = 0.f, rho = 0.f;
-    if (tid < n_rows) {
-      own = order[row0 + tid];
-      px = own_xyz[3 * (size_t)own]; py = own_xyz[3 * (size_t)own + 1]; pz = own_xyz[3 * (size_t)own + 2];
-      if (kBackward) {
-        rho = -1.0f;
-      } else {
-        // feature_mask = idx_mask + (1 - query_mask): a padded query uses all nsample slots (:171)
-        const int nv = min(a.nvalid[qbase + own], ns);
-        const bool padded = a.query_mask[qbase + own] == 0;
-        const int neff = padded ? ns : nv;
-        // list entries: the nv distinct winners; a padded query with none gathers row 0 nsample times
-        info = ((padded && nv == 0) ? 1 : nv) | (nv << 8) | ((padded ? 1 : 0) << 16);
-        rho = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;  // :175-176
-      }
-    }
-    sOwnerId[tid] = own; sOwnerInfo[tid] = info;
-    sOwnerXyz[3 * tid] = px; sOwnerXyz[3 * tid + 1] = py; sOwnerXyz[3 * tid + 2] = pz;
-    sOwnerRho[tid] = rho;
-    // tile centre = mean owner position (any point works; the mean keeps |owner - centre| small)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      px += __shfl_xor_sync(D3D_FULL_MASK, px, o);
-      py += __shfl_xor_sync(D3D_FULL_MASK, py, o);
-      pz += __shfl_xor_sync(D3D_FULL_MASK, pz, o);
-    }
-    if (lane == 0) { sCtr[3 * warp] = px; sCtr[3 * warp + 1] = py; sCtr[3 * warp + 2] = pz; }
-  }
-  if (kBackward)
-    for (int w = tid; w < L.W; w += kThreads) sBitmap[w] = 0u;
-  if (tid == 0) { sTask[0] = 0; sTask[1] = 0; }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const unsigned tmem_base = *reinterpret_cast<volatile unsigned*>(smem + L.bars + 16);
-  const float inv_rows = 1.0f / (float)n_rows;
-  const float ctr_x = (sCtr[0] + sCtr[3] + sCtr[6] + sCtr[9]) * inv_rows, ctr_y = (sCtr[1] + sCtr[4] + sCtr[7] + sCtr[10]) * inv_rows,
-              ctr_z = (sCtr[2] + sCtr[5] + sCtr[8] + sCtr[11]) * inv_rows;
-
-  D3D_STAMP(1);
-  // ---- P1: union of the referenced source rows --------------------------------------------------------------------
-  if (kBackward) {
-    // pass 1 over the owners' inverse-map segments: which queries gathered them through an unmasked slot
-    for (int r = warp; r < n_rows; r += kThreads / 32) {
-      const size_t srow = (size_t)b * a.N + sOwnerId[r];
-      const int beg = a.rowptr[srow], end = a.rowptr[srow + 1];
-      for (int e = beg + lane; e < end; e += 32) {
-        const int packed = a.entries[e];
-        const int q = packed >> 8, k = packed & 255;
-        const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
-        if (k < neff) atomicOr(&sBitmap[q >> 5], 1u << (q & 31));
-      }
-    }
-  } else {
-    // the tile plan holds the union ranks of the rows' list entries: one bulk copy into sEnt
-    if (tid == 0) {
-      const PlanView pv = plan_view(a.plan, (int)gridDim.z, a.M, a.N, ns);
-      const unsigned bytes = (unsigned)(kTQ * ns * 2);
-      mbar_arrive_expect_tx(bar_plan, bytes);
-      bulk_g2s(smem_u32(sEnt), pv.ranks + ((size_t)b * gridDim.x + tile) * kTQ * ns, bytes, bar_plan);
-    }
-  }
-  __syncthreads();
-  if (kBackward) {  // exclusive prefix of the per-word popcounts: two words per thread (W <= 512)
-    const int w0 = 2 * tid;
-    const unsigned p0 = w0 < L.W ? __popc(sBitmap[w0]) : 0u, p1 = w0 + 1 < L.W ? __popc(sBitmap[w0 + 1]) : 0u;
-    const unsigned sum = p0 + p1;
-    unsigned incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned up = __shfl_up_sync(D3D_FULL_MASK, incl, o);
-      if (lane >= o) incl += up;
-    }
-    if (lane == 31) sScan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const unsigned v = lane < kThreads / 32 ? sScan[lane] : 0u;
-      unsigned vi = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned up = __shfl_up_sync(D3D_FULL_MASK, vi, o);
-        if (lane >= o) vi += up;
-      }
-      if (lane < kThreads / 32) sScan[lane] = vi - v;
-      if (lane == 31) sScan[16] = vi;
-    }
-    __syncthreads();
-    const unsigned base = sScan[warp] + incl - sum;
-    if (w0 < L.W) sPrefix[w0] = base;
-    if (w0 + 1 < L.W) sPrefix[w0 + 1] = base + p0;
-  }
-  const PlanView pv = kBackward ? PlanView{} : plan_view(a.plan, (int)gridDim.z, a.M, a.N, ns);
-  const unsigned short* tile_union = kBackward ? nullptr : pv.unions + ((size_t)b * gridDim.x + tile) * pv.stride;
-  const int U = kBackward ? (int)sScan[16] : pv.counts[(size_t)b * gridDim.x + tile];
-  __syncthreads();
-  D3D_STAMP(2);
-  // source id -> rank inside the union (ranks ascend along every row's list: the union is ordered by index)
-  if (kBackward) {
-    for (int r = warp; r < n_rows; r += kThreads / 32) {
-      const size_t srow = (size_t)b * a.N + sOwnerId[r];
-      const int beg = a.rowptr[srow], end = a.rowptr[srow + 1];
-      for (int e = beg + lane; e < end; e += 32) {
-        // recomputed from the entry (not read back from the scratch): the CTAs of the other channel blocks write the
-        // very same values to the same scratch, so the race between them is benign
-        const int packed = a.entries[e];
-        const int q = packed >> 8, k = packed & 255;
-        const int neff = a.query_mask[qbase + q] != 0 ? a.nvalid[qbase + q] : ns;
-        a.rank_scratch[e] = k < neff ? (int)(sPrefix[q >> 5] + __popc(sBitmap[q >> 5] & ((1u << (q & 31)) - 1u))) : -1;
-      }
-    }
-  } else {
-    mbar_wait(bar_plan, 0u);  // the ranks have landed in sEnt
-  }
-
-  const int n_chunks = (U + kKC - 1) / kKC;
-  const unsigned idesc = idesc_bf16(L.np, false, true);  // A K-major, B MN-major, N = channels rounded up to 16
-  const int n_groups = (cbn + 7) >> 3;
-  const float* src_rows = a.src + (size_t)b * n_src * a.C + c0;
-
-  // rows of chunk j -> src buffers [j & 1], bulk copies into the staging buffer (warps 6-7, one row per thread)
-  auto select_and_issue = [&](int j) {
-    const int t = tid - (kThreads - 64), pb = j & 1;
-    const int r = j * kKC + t;
-    int src = -1;
-    if (r < U) {
-      if (kBackward) {
-        int lo = 0, hi = L.W - 1;
-        while (lo < hi) {  // last word whose prefix is <= r: it holds the set bit of rank r
-          const int mid = (lo + hi + 1) >> 1;
-          if ((int)sPrefix[mid] <= r) lo = mid; else hi = mid - 1;
-        }
-        src = lo * 32 + (int)__fns(sBitmap[lo], 0, r - (int)sPrefix[lo] + 1);
-      } else {
-        src = tile_union[r];
-      }
-      bulk_g2s(smem_u32(sStage + (size_t)t * L.row_bytes), src_rows + (size_t)src * a.C, L.row_bytes, bar_stage);
-      float* w = sSrcW + (pb * kKC + t) * 3;
-      w[0] = src_xyz[3 * (size_t)src] - ctr_x; w[1] = src_xyz[3 * (size_t)src + 1] - ctr_y; w[2] = src_xyz[3 * (size_t)src + 2] - ctr_z;
-      float scale = 1.0f;
-      if (kBackward) {
-        const int neff = a.query_mask[qbase + src] != 0 ? a.nvalid[qbase + src] : ns;
-        scale = a.reduction == D3D_REDUCE_AVG ? a.inv_radius / (float)neff : a.inv_radius;
-      }
-      sSrcScale[pb * kKC + t] = scale;
-    }
-    sSrcId[pb * kKC + t] = src;
-    named_bar_sync(1, 64);  // every selector's writes precede the arrive below (which the converters acquire)
-    if (t == 0) mbar_arrive_expect_tx(bar_stage, (unsigned)min(kKC, U - j * kKC) * L.row_bytes);
-  };
-
-  // staged fp32 row piece -> 3 bf16 planes of X and 3 of w * X, MN-major operand layout; task = (row, 8 channels)
-  auto convert = [&](int task, int pb) {
-    const int u = task & (kKC - 1), g = task >> 6;
-    unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
-    unsigned hx[3][4], hy[3][4];
-    if (sSrcId[pb * kKC + u] < 0) {
-#pragma unroll
-      for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hx[p][i] = hy[p][i] = 0u;
-    } else {
-      const float* row = reinterpret_cast<const float*>(sStage + (size_t)u * L.row_bytes) + 8 * g;
-      const float4 xa = *reinterpret_cast<const float4*>(row);
-      const float4 xb = (8 * g + 4 < cbn) ? *reinterpret_cast<const float4*>(row + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      const float* wv = sSrcW + (pb * kKC + u) * 3;
-      const float wx = wv[0], wy = wv[1], wz = wv[2];
-      const int base = (c0 + 8 * g) % 3;
-      const float w0 = rot3(wx, wy, wz, base), w1 = rot3(wy, wz, wx, base), w2 = rot3(wz, wx, wy, base);
-      if (kBackward) {
-        const float sc = sSrcScale[pb * kKC + u];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] *= sc;
-      }
-      const float y[8] = {x[0] * w0, x[1] * w1, x[2] * w2, x[3] * w0, x[4] * w1, x[5] * w2, x[6] * w0, x[7] * w1};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        split3_bf16x2(x[2 * i], x[2 * i + 1], hx[0][i], hx[1][i], hx[2][i]);
-        split3_bf16x2(y[2 * i], y[2 * i + 1], hy[0][i], hy[1][i], hy[2][i]);
-      }
-    }
-#pragma unroll
-    for (int p = 0; p < 3; ++p) {
-      *reinterpret_cast<uint4*>(dst + (size_t)p * L.plane_bytes) = make_uint4(hx[p][0], hx[p][1], hx[p][2], hx[p][3]);
-      *reinterpret_cast<uint4*>(dst + (size_t)(3 + p) * L.plane_bytes) = make_uint4(hy[p][0], hy[p][1], hy[p][2], hy[p][3]);
-    }
-  };
-
-  // ---- chunks of 64 union rows ---------------------------------------------------------------------------------
-  if (n_chunks > 0 && tid >= kThreads - 64) select_and_issue(0);
-  // A-build cursor of this thread's row
-  int cur = 0, cur_end = 0, row_info = 0;
-  const int* prow = nullptr;  // forward, padded rows only: the list with the distance ranks
-  if (tid < n_rows) {
-    if (kBackward) {
-      const size_t srow = (size_t)b * a.N + sOwnerId[tid];
-      cur = a.rowptr[srow]; cur_end = a.rowptr[srow + 1];
-    } else {
-      row_info = sOwnerInfo[tid];
-      cur_end = row_info & 255;
-      prow = a.by_support + (qbase + sOwnerId[tid]) * ns;
-    }
-  }
-  __syncthreads();  // ranks (forward: sEnt; backward: rank_scratch, written by other threads of this CTA) are in place
-  D3D_STAMP(3);
-
-  for (int j = 0; j < n_chunks; ++j) {
-    const int pb = j & 1;
-    const int rows_here = min(kKC, U - j * kKC);
-    const int ksteps = (rows_here + 15) >> 4;
-    if (j > 0) {  // the previous chunk's MMAs are done reading A and the planes
-      mbar_wait(bar_mma, (unsigned)((j - 1) & 1));
-      tc_fence_after();
-    }
-    if (warp < 4) {
-      // multiplicity matrix A[row][union rank - 64 j]: a thread owns its row — it clears it and writes the run of its
-      // list that falls into this chunk (ranks ascend along the list).  No atomics, no dependence on timing.
-      unsigned char* arow = sA + (tid >> 3) * kASbo + (tid & 7) * 16;
-#pragma unroll
-      for (int g = 0; g < kKC / 8; ++g) *reinterpret_cast<uint4*>(arow + g * 128) = make_uint4(0u, 0u, 0u, 0u);
-      const int limit = (j + 1) * kKC;
-      if (kBackward) {
-        while (cur < cur_end) {
-          const int r = a.rank_scratch[cur];
-          if (r >= limit) break;
-          if (r >= 0) {  // equal ranks are adjacent (a padded query repeats its slots): add
-            unsigned short* p = reinterpret_cast<unsigned short*>(arow + ((r & 63) >> 3) * 128 + (r & 7) * 2);
-            *p = (unsigned short)(__float_as_uint(__uint_as_float((unsigned)*p << 16) + 1.0f) >> 16);
-          }
-          ++cur;
-        }
-      } else {
-        const unsigned short* e = sEnt + tid * ns;
-        while (cur < cur_end) {
-          const int r = e[cur];
-          if (r >= limit) break;
-          int m = 1;
-          if (row_info >> 16) {  // padded query: slot k of the reference list repeats winner k % nvalid (cyclic padding)
-            const int nv = (row_info >> 8) & 255;
-            m = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
-          }
-          *reinterpret_cast<unsigned short*>(arow + ((r & 63) >> 3) * 128 + (r & 7) * 2) = bf16_of_count(m);
-          ++cur;
-        }
-      }
-    }
-    // staged rows -> operand planes: every warp takes 32 tasks at a time (the A warps join when their rows are done)
-    mbar_wait(bar_stage, (unsigned)(j & 1));
-    {
-      const int rows16 = ksteps * 16, n_tasks = kKC * n_groups;  // task = (8-channel group, row): 32 rows per grab
-      for (;;) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sTask[pb], 32);
-        base = __shfl_sync(D3D_FULL_MASK, base, 0);
-        if (base >= n_tasks) break;
-        if ((base & (kKC - 1)) < rows16) convert(base + lane, pb);  // warp-uniform: rows beyond the last K-step are not read
-      }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    if (tid == 0) sTask[pb ^ 1] = 0;
-    __syncthreads();
-    // Y1 += A . X planes, Y2 += A . (w X) planes
-    if (tid == 0) {
-      tc_fence_after();
-      const unsigned a_addr = smem_u32(sA), p_addr = smem_u32(sPlanes);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const unsigned long long a_desc = smem_desc(a_addr + ks * 256, 128, kASbo);
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          const unsigned long long b_desc = smem_desc(p_addr + p * L.plane_bytes + ks * 2 * L.lbo_b, L.lbo_b, 128);
-          const unsigned acc = (j == 0 && ks == 0 && (p == 0 || p == 3)) ? 0u : 1u;
-          mma_bf16(tmem_base + (p < 3 ? 0u : (unsigned)L.np), a_desc, b_desc, idesc, acc);
-        }
-      }
-      mma_commit(bar_mma);
-    }
-    // the staging buffer is free (all conversions ended before the barrier): next chunk's rows fly during the MMAs
-    if (tid >= kThreads - 64 && j + 1 < n_chunks) select_and_issue(j + 1);
-  }
-
-  D3D_STAMP(4);
-  // ---- epilogue: thread = owner row (TMEM lane); the two warp groups split the 16-column pieces --------------------
-  if (n_chunks > 0) {
-    mbar_wait(bar_mma, (unsigned)((n_chunks - 1) & 1));
-    tc_fence_after();
-  }
-  {
-    const int lq = warp & 3, t = lq * 32 + lane;
-    const int own = sOwnerId[t];
-    const float rcx = sOwnerXyz[3 * t] - ctr_x, rcy = sOwnerXyz[3 * t + 1] - ctr_y, rcz = sOwnerXyz[3 * t + 2] - ctr_z;
-    const float rho = sOwnerRho[t];
-    float* orow = a.out + ((size_t)b * n_own + (own >= 0 ? own : 0)) * a.C + c0;
-    for (int ch = warp >> 2; ch * 16 < cbn; ch += kThreads / 128) {
-      unsigned y1[16], y2[16];
-      if (n_chunks > 0) {
-        const unsigned taddr = tmem_base + ((unsigned)(lq * 32) << 16) + (unsigned)(ch * 16);
-        tmem_ld16(taddr, y1);
-        tmem_ld16(taddr + (unsigned)L.np, y2);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y1[i] = y2[i] = 0u;
-      }
-      const int base = (c0 + 16 * ch) % 3;
-      const float r0 = rot3(rcx, rcy, rcz, base), r1 = rot3(rcy, rcz, rcx, base), r2 = rot3(rcz, rcx, rcy, base);
-      float o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float rc = (i % 3 == 0) ? r0 : ((i % 3 == 1) ? r1 : r2);
-        o[i] = rho * (__uint_as_float(y2[i]) - rc * __uint_as_float(y1[i]));
-      }
-      if (own >= 0) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          if (16 * ch + 4 * v < cbn)
-            *reinterpret_cast<float4*>(orow + 16 * ch + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  D3D_STAMP(5);
-  if (a.timing && tid == 0) a.timing[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 6] = (unsigned long long)U;
-  if (warp == 4) tmem_dealloc(tmem_base, (unsigned)L.tmem_cols);
-}
-
 
 // ================================================================================================================
 // Backward in SCATTER form: the CTA owns 128 QUERIES (the forward tile) and distributes their gradient rows over the
@@ -1222,23 +804,6 @@ int launch_fwd_pipelined(const TileArgs& a, int B, cudaStream_t st) {
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-template <bool kBackward>
-int launch_tiles(const TileArgs& a, int B, cudaStream_t st) {
-  const int n_own = kBackward ? a.N : a.M, n_src = kBackward ? a.M : a.N;
-  if (n_own > kMaxPoints || n_src > kMaxPoints || a.nsample > kMaxNs || a.C % 4 != 0) return D3D_ERR_UNSUPPORTED;
-  const int cbn_max = a.C < kCB ? a.C : kCB;
-  const Layout L = make_layout(cbn_max, a.nsample, n_src, kBackward);
-  auto kernel = pospool_tiles_kernel<kBackward>;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-  if (e != cudaSuccess) return (int)e;
-  dim3 grid(d3d_ceil_div(n_own, kTQ), d3d_ceil_div(a.C, kCB), B);
-  TileArgs b = a;
-  b.timing = g_timing;
-  kernel<<<grid, kThreads, L.total, st>>>(b);
-  d3d_note_launches(1);
-  return d3d_launch_status();
-}
-
 }  // namespace
 
 extern "C" {
@@ -1298,31 +863,6 @@ int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, co
   a.nvalid = nvalid; a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
   a.reduction = reduction; a.inv_radius = 1.0f / radius; a.plan = plan;
   return launch_scatter_bwd(a, B, (cudaStream_t)stream);
-}
-
-size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample) {
-  if (B <= 0 || M <= 0 || nsample <= 0) return 0;
-  return (size_t)B * M * nsample * sizeof(int);
-}
-
-int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* rowptr,
-                          const int* entries, const int* nvalid, const int* query_mask, const int* support_order, int B,
-                          int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl, void* ws,
-                          size_t ws_bytes, void* stream) {
-  D3D_REQUIRE(grad_out_cl && query_xyz && support_xyz && rowptr && entries && nvalid && query_mask);
-  D3D_REQUIRE(support_order && grad_feat_cl);
-  D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
-  D3D_REQUIRE(reduction == D3D_REDUCE_SUM || reduction == D3D_REDUCE_AVG);
-  if (!aligned16(grad_out_cl) || !aligned16(grad_feat_cl)) return D3D_ERR_UNSUPPORTED;
-  if (B == 0) return 0;
-  if (M == 0) return (int)cudaMemsetAsync(grad_feat_cl, 0, (size_t)B * N * C * sizeof(float), (cudaStream_t)stream);
-  if (!ws || ws_bytes < d3d_pospool_tiles_bwd_workspace_bytes(B, M, nsample)) return D3D_ERR_WORKSPACE;
-  TileArgs a{};
-  a.src = grad_out_cl; a.out = grad_feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz;
-  a.rowptr = rowptr; a.entries = entries; a.rank_scratch = (int*)ws; a.nvalid = nvalid; a.query_mask = query_mask;
-  a.order = support_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample; a.reduction = reduction;
-  a.inv_radius = 1.0f / radius;
-  return launch_tiles<true>(a, B, (cudaStream_t)stream);
 }
 
 }  // extern "C"

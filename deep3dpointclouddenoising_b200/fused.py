@@ -123,22 +123,18 @@ class PosPoolFunction(Function):
         query_xyz, support_xyz, query_mask = ctx.saved_tensors
         nbr = ctx.nbr
         g_cl = _rows(grad_out)
-        # False: segmented reduction over the inverse map | 'scatter': the forward tile transposed on the tensor cores, float
-        # atomics across tiles (faster at every level, also for strided lists where the forward tiles are not) |
-        # 'gather': support tiles, fixed order (slower: the union of gathering queries is 3x the forward union)
-        mode = runtime.staged_tiles_backward
+        # 'scatter': the forward tile transposed on the tensor cores, float atomics across tiles (faster at every level, also
+        # for strided lists where the forward tiles are not); False: segmented reduction over the inverse map
         plan = (nbr.tile_plan(query_xyz, query_mask)
-                if mode == 'scatter' and ctx.reduction != 'sum' and nbr.by_support is not None else None)
-        order = _neighbors.spatial_order(query_xyz) if plan is not None else None
-        if order is not None:
+                if runtime.staged_tiles_backward == 'scatter' and ctx.reduction != 'sum' and nbr.by_support is not None else None)
+        if plan is not None:
             gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, None, None, nbr.nvalid, query_mask, nbr.n_support,
-                                    nbr.nsample, ctx.radius, ctx.reduction, query_order=order, idx_by_support=nbr.by_support,
-                                    plan=plan)
+                                    nbr.nsample, ctx.radius, ctx.reduction, query_order=_neighbors.spatial_order(query_xyz),
+                                    idx_by_support=nbr.by_support, plan=plan)
         else:
             rowptr, entries = nbr.csr()
             gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,
-                                    nbr.nsample, ctx.radius, ctx.reduction,
-                                    support_order=_neighbors.spatial_order(support_xyz) if mode in (True, 'gather') else None)
+                                    nbr.nsample, ctx.radius, ctx.reduction)
         return _logical(gf_cl, ctx.in_cl), None, None, None, None, None, None
 
 

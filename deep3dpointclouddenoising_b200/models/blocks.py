@@ -229,6 +229,10 @@ class FusedSequential(nn.Sequential):
         mods = list(self._modules.values())
         parts = list(x) if isinstance(x, (list, tuple)) else None
         on_gpu = parts[0].is_cuda if parts is not None else x.is_cuda
+        if not on_gpu and not runtime.cpu_modules:
+            # the product has no CPU path; the CPU oracle (oracle/cpu_model.py: tests, bench's CPU arm) opts in explicitly
+            raise RuntimeError("CPU not supported: the convolution / BatchNorm blocks run on CUDA tensors only "
+                               "(utils.config.runtime.cpu_modules = True lets the CPU oracle drive the module tree)")
         use_fused = on_gpu and runtime.fused_batchnorm
 
         def feeds_training_bn(k):

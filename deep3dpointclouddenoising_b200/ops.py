@@ -281,17 +281,16 @@ def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius
 
 
 def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, query_mask, n_support, nsample, radius,
-                reduction, support_order=None, query_order=None, idx_by_support=None, plan=None):
-    """query_order (B, M) + idx_by_support (the forward tile's inputs): the scatter-form staged-tile kernel (tensor cores,
-    float atomics across tiles); support_order (B, N): the gather-form staged-tile kernel; otherwise the per-support
-    segmented reduction over the inverse map."""
+                reduction, query_order=None, idx_by_support=None, plan=None):
+    """query_order (B, M) + idx_by_support (the forward tile's inputs; + the pair's `tile_plan`, built here when not
+    given): the scatter-form staged-tile kernel (tensor cores, float atomics across tiles; rowptr / entries are not read);
+    otherwise the per-support segmented reduction over the inverse map (bit-reproducible)."""
     L = _lib.load()
     g = _f32(grad_out_cl, "grad_out")
     B, M, C = g.shape
     with torch.cuda.device(g.device):
         out = torch.empty((B, n_support, C), dtype=torch.float32, device=g.device)
-        if (query_order is not None and idx_by_support is not None and _tiles_ok(M, int(n_support), int(nsample), C)
-                and 128 * min(C, 72) * 4 <= 65536):
+        if query_order is not None and idx_by_support is not None and _tiles_ok(M, int(n_support), int(nsample), C):
             if plan is None:
                 plan = tile_plan(idx_by_support, nvalid, query_mask, query_order, n_support)
             _lib.check(L.d3d_pospool_scatter_bwd(_p(g), _p(query_xyz), _p(support_xyz),
@@ -299,12 +298,6 @@ def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, qu
                                                  _p(_i32(query_order, "query_order")), _p(plan), B, M, int(n_support), C,
                                                  int(nsample), float(radius), REDUCTIONS[reduction], _p(out), _stream()),
                        "d3d_pospool_scatter_bwd")
-        elif support_order is not None and _tiles_ok(M, int(n_support), int(nsample), C):
-            ws = _ws(L.d3d_pospool_tiles_bwd_workspace_bytes(B, M, int(nsample)), g.device)
-            _lib.check(L.d3d_pospool_tiles_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
-                                               _p(query_mask), _p(_i32(support_order, "support_order")), B, M,
-                                               int(n_support), C, int(nsample), float(radius), REDUCTIONS[reduction],
-                                               _p(out), _p(ws), ws.numel(), _stream()), "d3d_pospool_tiles_bwd")
         else:
             _lib.check(L.d3d_pospool_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),
                                          _p(query_mask), B, M, int(n_support), C, int(nsample), float(radius),

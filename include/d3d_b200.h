@@ -137,12 +137,11 @@ int d3d_pospool_bwd(const float* grad_out_cl, const float* query_xyz, const floa
  * summation order.  N <= 16384 (D3D_ERR_UNSUPPORTED beyond).  No reference counterpart. */
 int d3d_spatial_order(const float* xyz, int B, int N, int* order, void* stream);
 
-/* PosPool as a staged-tile kernel (same math and arguments as d3d_pospool_fwd / _bwd, which remain the path for sizes
- * beyond the limits below): a CTA owns 128 spatially adjacent rows (query_order / support_order from
- * d3d_spatial_order), stages the union of the rows their neighbourhoods reference with cp.async.bulk and contracts
- * [128 x union] multiplicities (from idx_by_support of d3d_ball_query: every query's winners in ascending support
- * index) with the staged rows on the tensor cores (tcgen05, exact 3-term bf16 split, fp32
- * accumulation); the backward pass owns 128 SUPPORT rows and is a fixed-order reduction (no float atomics).
+/* PosPool as staged-tile kernels (same math as d3d_pospool_fwd / _bwd, which remain the path for other variants and for
+ * sizes beyond the limits below): a CTA owns a tile of 128 spatially adjacent queries (query_order from
+ * d3d_spatial_order), the union of the support rows the tile gathers travels global -> shared with cp.async.bulk and is
+ * contracted with the tile's [128 x union] multiplicity matrix (from idx_by_support of d3d_ball_query: every query's
+ * winners in ascending support index) on the tensor cores (tcgen05, exact 3-term bf16 split, fp32 accumulation).
  *   replaces ref: pt_custom_ops/_ext_src/src/group_points_gpu.cu:13-33,48-69 + models/local_aggregation_operators.py:140-183
  * Limits: M, N <= 16384, nsample <= 64, C % 4 == 0 (D3D_ERR_UNSUPPORTED otherwise). */
 /* Tile plan of one (neighbour list, query order) pair, shared by every forward / scatter-backward launch on that pair
@@ -164,13 +163,6 @@ int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, co
                             const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order,
                             const void* plan, int B, int M, int N, int C, int nsample, float radius, int reduction,
                             float* grad_feat_cl, void* stream);
-/* Workspace of the gather-form backward pass: one int per inverse-map entry (union ranks). */
-size_t d3d_pospool_tiles_bwd_workspace_bytes(int B, int M, int nsample);
-int d3d_pospool_tiles_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz, const int* rowptr,
-                          const int* entries, const int* nvalid, const int* query_mask, const int* support_order, int B,
-                          int M, int N, int C, int nsample, float radius, int reduction, float* grad_feat_cl, void* ws,
-                          size_t ws_bytes, void* stream);
-
 #define D3D_KP_CONSTANT 0
 #define D3D_KP_LINEAR   1
 #define D3D_KP_GAUSSIAN 2

@@ -82,7 +82,14 @@ class CpuUNet:
         return hd.head(feats)
 
     def forward(self, xyz, mask, feats):
-        return self.head(self.backbone(xyz, mask, feats))
+        # the module tree's 1x1 convolutions / BatchNorms are stock torch modules: the product refuses to run them on CPU
+        # tensors unless the oracle says so (utils.config.runtime.cpu_modules)
+        from deep3dpointclouddenoising_b200.utils.config import runtime
+        old, runtime.cpu_modules = runtime.cpu_modules, True
+        try:
+            return self.head(self.backbone(xyz, mask, feats))
+        finally:
+            runtime.cpu_modules = old
 
     __call__ = forward
 

@@ -22,6 +22,8 @@ def _worker(rank, world, port, out_dir):
     from deep3dpointclouddenoising_b200 import distributed, synthetic
     from deep3dpointclouddenoising_b200.models.heads import MultiDimHeadResNet
     from deep3dpointclouddenoising_b200.models.losses import MaskedL1Loss
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    runtime.cpu_modules = True  # host-side test of the data-parallel plumbing: conv / BN blocks as stock torch modules
     r, w, _ = distributed.init("gloo")
     assert (r, w) == (rank, world)
     torch.manual_seed(0)  # same initial weights on every rank, like DDP's initial broadcast would give

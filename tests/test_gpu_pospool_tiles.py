@@ -92,26 +92,26 @@ def test_staged_pospool_against_float_oracle(cuda_device, oracle, C, N, M, ns, r
     assert np.array_equal(didx.cpu().numpy(), idx)
     f_cl = dev(f.transpose(0, 2, 1), cuda_device)
     g_cl = dev(gout.transpose(0, 2, 1), cuda_device)
-    oq, os_ = ops.spatial_order(dq), ops.spatial_order(ds)
+    oq = ops.spatial_order(dq)
     out = ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq, idx_by_support=dbys)
     # 'sum' is 'avg' times the neighbourhood size: the same relative accuracy means an absolute tolerance nsample times larger
     FWD = dict(rtol=1e-5, atol=2e-6 * (ns if reduction == 'sum' else 1))
     BWD = dict(rtol=1e-4, atol=2e-5 * (ns if reduction == 'sum' else 1))
     np.testing.assert_allclose(out.cpu().numpy().transpose(0, 2, 1), ref.detach().numpy(), **FWD)
+    # backward, scatter form: the forward tile's transposed contraction, partial sums added with float atomics
+    plan = ops.tile_plan(dbys, dnv, dqm, oq, N)
+    gs = ops.pospool_bwd(g_cl, dq, ds, None, None, dnv, dqm, N, ns, radius, reduction, query_order=oq, idx_by_support=dbys,
+                         plan=plan)
+    np.testing.assert_allclose(gs.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
+    # the forward has a fixed summation order: same bits on a second run (also with the plan built inside the call)
+    assert torch.equal(out, ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq, idx_by_support=dbys,
+                                            plan=plan))
+    # and both agree with the per-query gather kernels
     rowptr, entries = ops.build_inverse_map(didx, N)
-    gf = ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction, support_order=os_)
-    np.testing.assert_allclose(gf.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
-    # same bits on a second run (fixed-order reduction, no atomics on floats), and close to the per-query gather kernels
-    assert torch.equal(out, ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq, idx_by_support=dbys))
-    assert torch.equal(gf, ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction,
-                                           support_order=os_))
     legacy = ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction)
     np.testing.assert_allclose(out.cpu().numpy(), legacy.cpu().numpy(), **FWD)
     legacy_g = ops.pospool_bwd(g_cl, dq, ds, rowptr, entries, dnv, dqm, N, ns, radius, reduction)
-    np.testing.assert_allclose(gf.cpu().numpy(), legacy_g.cpu().numpy(), **BWD)
-    # scatter form: the forward tile's transposed contraction, partial sums added with float atomics
-    gs = ops.pospool_bwd(g_cl, dq, ds, None, None, dnv, dqm, N, ns, radius, reduction, query_order=oq, idx_by_support=dbys)
-    np.testing.assert_allclose(gs.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
+    np.testing.assert_allclose(gs.cpu().numpy(), legacy_g.cpu().numpy(), **BWD)
 
 
 def test_staged_pospool_at_the_benched_level0_shape(cuda_device, oracle):
@@ -130,9 +130,6 @@ def test_staged_pospool_at_the_benched_level0_shape(cuda_device, oracle):
     f_cl, g_cl = dev(f.transpose(0, 2, 1), cuda_device), dev(gout.transpose(0, 2, 1), cuda_device)
     out = ops.pospool_fwd(f_cl, ds, ds, didx, dnv, dsm, radius, 'avg', query_order=order, idx_by_support=dbys)
     np.testing.assert_allclose(out.cpu().numpy().transpose(0, 2, 1), ref.detach().numpy(), **FWD)
-    rowptr, entries = ops.build_inverse_map(didx, N)
-    gf = ops.pospool_bwd(g_cl, ds, ds, rowptr, entries, dnv, dsm, N, ns, radius, 'avg', support_order=order)
-    np.testing.assert_allclose(gf.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
     gs = ops.pospool_bwd(g_cl, ds, ds, None, None, dnv, dsm, N, ns, radius, 'avg', query_order=order, idx_by_support=dbys)
     np.testing.assert_allclose(gs.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
 

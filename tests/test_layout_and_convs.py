@@ -2,6 +2,7 @@
 (fused.py: is_channel_last / rows_of / cat_channels; models/blocks.py: PointwiseConvRows, PointwiseConvCatRows, the
 batched split-K weight gradient) against torch.nn.Conv1d / torch.cat — the modules they replace
 (ref: u_net_arch/models/backbones/resnet.py:32-45, heads/multi_dimensional_head.py:36-37)."""
+import pytest
 import torch
 import torch.nn as nn
 
@@ -69,11 +70,19 @@ def test_split_weight_gradient_and_in_place_accumulation():
     torch.testing.assert_close(buf, ref + 1 + g[:100].t() @ x[:100])
 
 
-def test_fused_sequential_accepts_a_list_on_cpu():
-    """On CPU (no fused kernels) a list input is the plain concatenation followed by the reference modules."""
+def test_fused_sequential_refuses_cpu_unless_the_oracle_opts_in():
+    """The product has no CPU path: the conv / BN blocks raise on CPU tensors.  With runtime.cpu_modules (set by the CPU
+    oracle) a list input is the plain concatenation followed by the stock torch modules."""
+    from deep3dpointclouddenoising_b200.utils.config import runtime
     torch.manual_seed(3)
     block = blocks.conv_bn(7, 4).double()
     a, b = torch.randn(2, 3, 9, dtype=torch.float64), torch.randn(2, 4, 9, dtype=torch.float64)
     block.train()
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        block([a, b])
     ref = nn.Sequential(*list(block.children()))(torch.cat([a, b], 1))
-    torch.testing.assert_close(block([a, b]), ref)
+    runtime.cpu_modules = True
+    try:
+        torch.testing.assert_close(block([a, b]), ref)
+    finally:
+        runtime.cpu_modules = False

@@ -30,7 +30,6 @@ for _ in range(n):
     elif op == "tile_plan": ops.tile_plan(bys, nv, mask, order, N)
     elif op == "bn_bwd": ops.bn_act_cl_bwd(f, f, ybn, gam, bet, mean, invstd, True, 1, False)
     elif op == "bn_fwd": ops.bn_act_cl_fwd(f, None, gam, bet, rm, rv, 1e-5, 0.1, True, True)
-    elif op == "pospool_tiles_bwd": ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg', support_order=order)
     elif op == "gemm": ops.gemm_tf32(f.view(-1, C), wg)
     elif op == "gemm_stats": ops.gemm_tf32(f.view(-1, C), wg, want_stats=True)
     elif op == "pseudogrid_fwd": ops.pseudogrid_fwd(f, pts, pts, idx, nv, mask, kp, w, 0.01, 'linear', 0)

@@ -1,6 +1,6 @@
-"""Phase timing of the staged-tile PosPool kernel at the level-0 shape: per-CTA %globaltimer stamps written by the kernel
-itself (d3d_pospool_tiles_debug_timing), averaged.  Diagnostic only.
-usage: python tools/tile_phases.py [fwd|bwd]"""
+"""Phase timing of the staged-tile PosPool forward kernel at the level-0 shape: per-CTA %globaltimer stamps written by the
+kernel itself (d3d_pospool_tiles_debug_timing), averaged.  Diagnostic only.
+usage: python tools/tile_phases.py"""
 import ctypes
 import os
 import sys
@@ -10,13 +10,13 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deep3dpointclouddenoising_b200 import _lib, ops, synthetic  # noqa: E402
 
-which = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+which = "fwd"
 dev = torch.device("cuda:0")
 B, N, C = 16, 8192, 72
 pts, mask, _, _ = [torch.from_numpy(a).to(dev) for a in synthetic.make_batch(1, B, N)]
 idx, msk, nv, bys = ops.ball_query(pts, pts, mask, mask, 0.025, 52, want_nvalid=True, want_by_support=True)
-rowptr, entries = ops.build_inverse_map(idx, N)
 order = ops.spatial_order(pts)
+plan = ops.tile_plan(bys, nv, mask, order, N)
 f = torch.randn(B, N, C, device=dev)
 L = _lib.load()
 n_cta = (N // 128) * B
@@ -24,10 +24,7 @@ buf = torch.zeros(n_cta * 8, dtype=torch.int64, device=dev)
 
 
 def run():
-    if which == "fwd":
-        ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys)
-    else:
-        ops.pospool_bwd(f, pts, pts, rowptr, entries, nv, mask, N, 52, 0.025, 'avg', support_order=order)
+    ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys, plan=plan)
 
 
 for _ in range(3):
@@ -41,7 +38,7 @@ run()
 torch.cuda.synchronize()
 fn(None)
 t = buf.view(n_cta, 8).cpu().double()
-names = ["P0 owners/TMEM", "P1 union bitmap + prefix", "ranks", "chunk loop", "epilogue"]
+names = ["owners / TMEM / barriers", "(unused)", "(unused)", "chunk loop", "epilogue"]
 span = (t[:, 5].max() - t[:, 0].min()) / 1e3
 print(f"{which}: {n_cta} CTAs, kernel span {span:.1f} us, union rows per tile mean {t[:, 6].mean():.0f} (max {t[:, 6].max():.0f})")
 for k, nm in enumerate(names):
@@ -49,5 +46,5 @@ for k, nm in enumerate(names):
     print(f"  {nm:28s} mean {d.mean():6.2f} us   p90 {d.quantile(0.9):6.2f}   max {d.max():6.2f}")
 tot = (t[:, 5] - t[:, 0]) / 1e3
 print(f"  {'CTA lifetime':28s} mean {tot.mean():6.2f} us   p90 {tot.quantile(0.9):6.2f}   max {tot.max():6.2f}")
-chunks = torch.ceil(t[:, 6] / 64)
+chunks = torch.ceil(t[:, 6] / 32)
 print(f"  chunk loop per chunk: {((t[:, 4] - t[:, 3]) / 1e3 / chunks.clamp_min(1)).mean():.2f} us")

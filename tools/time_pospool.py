@@ -44,7 +44,7 @@ def main():
         M, N = q.shape[1], s.shape[1]
         idx, msk, nv, bys = ops.ball_query(q, s, qm, sm, r, ns, want_nvalid=True, want_by_support=True)
         rowptr, entries = ops.build_inverse_map(idx, N)
-        oq, os_ = ops.spatial_order(q), ops.spatial_order(s)
+        oq = ops.spatial_order(q)
         f = torch.randn(B, N, C, device=dev)
         g = torch.randn(B, M, C, device=dev)
         t = {}
@@ -53,7 +53,6 @@ def main():
         t["fwd gather"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg'))
         t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan))
         t["bwd gather"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg'))
-        t["bwd tiles"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg', support_order=os_))
         t["bwd scatter"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan))
         a = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg')
         b = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys)
