@@ -28,6 +28,7 @@ SIGNATURES = {
     "d3d_group_points": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "d3d_group_points_grad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "d3d_group_points_grad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "d3d_group_points_grad_atomic": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "d3d_inverse_map_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "d3d_build_inverse_map": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "d3d_cm_to_cl": (_i, [_vp, _i, _i, _i, _vp, _vp]),

@@ -72,6 +72,41 @@ group_points_grad_kernel(const float* __restrict__ grad_out, const int* __restri
     if (c < nc) grad_points[((size_t)b * C + c0 + c) * N + i] = acc[c];
 }
 
+// Fast form of the gather gradient: one block per (b, c) plane.  The N sums of the plane live in shared memory, the
+// (M, nsample) gradients and indices stream through coalesced (float4 / int4) and are added with shared-memory atomics —
+// the reference's own formulation (atomicAdd, group_points_gpu.cu:61-66) without its global-memory contention.
+// Reproducible to rounding only; d3d_group_points_grad (inverse map, fixed order) is the bit-reproducible form.
+__global__ void __launch_bounds__(1024)
+group_points_grad_plane_kernel(const float* __restrict__ grad_out, const int* __restrict__ idx, int C, int N, int P,
+                               float* __restrict__ grad_points) {
+  extern __shared__ float acc[];
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < N; i += blockDim.x) acc[i] = 0.0f;
+  __syncthreads();
+  const float* g = grad_out + ((size_t)b * C + c) * P;
+  const int* ix = idx + (size_t)b * P;
+  if ((P & 3) == 0) {
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const int4* i4 = reinterpret_cast<const int4*>(ix);
+    for (int p = tid; p < P / 4; p += blockDim.x) {
+      const float4 v = __ldg(g4 + p);
+      const int4 j = __ldg(i4 + p);
+      if ((unsigned)j.x < (unsigned)N) atomicAdd(&acc[j.x], v.x);
+      if ((unsigned)j.y < (unsigned)N) atomicAdd(&acc[j.y], v.y);
+      if ((unsigned)j.z < (unsigned)N) atomicAdd(&acc[j.z], v.z);
+      if ((unsigned)j.w < (unsigned)N) atomicAdd(&acc[j.w], v.w);
+    }
+  } else {
+    for (int p = tid; p < P; p += blockDim.x) {
+      const int j = __ldg(ix + p);
+      if ((unsigned)j < (unsigned)N) atomicAdd(&acc[j], __ldg(g + p));
+    }
+  }
+  __syncthreads();
+  float* o = grad_points + ((size_t)b * C + c) * N;
+  for (int i = tid; i < N; i += blockDim.x) o[i] = acc[i];
+}
+
 // (rows x cols) -> (cols x rows) per batch through a padded 32x32 shared tile
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
@@ -150,6 +185,24 @@ int d3d_group_points_grad(const float* grad_out, const int* idx, int B, int C, i
   if (rc != 0) return rc;
   dim3 grid(d3d_ceil_div(N, 128), d3d_ceil_div(C, kGradChan), B);
   group_points_grad_kernel<<<grid, 128, 0, st>>>(grad_out, rowptr, entries, C, N, M * nsample, nsample, grad_points);
+  d3d_note_launches(1);
+  return d3d_launch_status();
+}
+
+int d3d_group_points_grad_atomic(const float* grad_out, const int* idx, int B, int C, int N, int M, int nsample,
+                                 float* grad_points, void* stream) {
+  D3D_REQUIRE(grad_out && idx && grad_points);
+  D3D_REQUIRE(B >= 0 && C >= 0 && N > 0 && M >= 0 && nsample > 0);
+  if (B == 0 || C == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long P = (long long)M * nsample;
+  if (P >= (1ll << 31) || (size_t)N * sizeof(float) > 200 * 1024) return D3D_ERR_UNSUPPORTED;
+  if (M == 0) return (int)cudaMemsetAsync(grad_points, 0, (size_t)B * C * N * sizeof(float), st);
+  const size_t smem = (size_t)N * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(group_points_grad_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(C, B);
+  group_points_grad_plane_kernel<<<grid, 1024, smem, st>>>(grad_out, idx, C, N, (int)P, grad_points);
   d3d_note_launches(1);
   return d3d_launch_status();
 }

@@ -161,16 +161,25 @@ def group_points(points, idx):
     return out
 
 
-def group_points_grad(grad_out, idx, n):
-    """(B,C,M,ns),(B,M,ns) -> (B,C,n) — _ext.group_points_grad (group_points.cpp:42-65), deterministic."""
+def group_points_grad(grad_out, idx, n, deterministic=None):
+    """(B,C,M,ns),(B,M,ns) -> (B,C,n) — _ext.group_points_grad (group_points.cpp:42-65).  deterministic=False (the default unless
+    `runtime.deterministic_scatter`): the reference's own atomicAdd formulation on shared-memory planes, 7x faster;
+    True: fixed summation order over an inverse map built inside the call (bit-reproducible)."""
+    from .utils.config import runtime
     L = _lib.load()
     g, i = _f32(grad_out, "grad_out"), _i32(idx, "idx")
     B, C, M, ns = g.shape
+    if deterministic is None:
+        deterministic = bool(runtime.deterministic_scatter)
     with torch.cuda.device(g.device):
         out = torch.empty((B, C, int(n)), dtype=torch.float32, device=g.device)
-        ws = _ws(L.d3d_group_points_grad_workspace_bytes(B, int(n), M, ns), g.device)
-        _lib.check(L.d3d_group_points_grad(_p(g), _p(i), B, C, int(n), M, ns, _p(out), _p(ws), ws.numel(), _stream()),
-                   "d3d_group_points_grad")
+        if not deterministic and int(n) * 4 <= 200 * 1024:
+            _lib.check(L.d3d_group_points_grad_atomic(_p(g), _p(i), B, C, int(n), M, ns, _p(out), _stream()),
+                       "d3d_group_points_grad_atomic")
+        else:
+            ws = _ws(L.d3d_group_points_grad_workspace_bytes(B, int(n), M, ns), g.device)
+            _lib.check(L.d3d_group_points_grad(_p(g), _p(i), B, C, int(n), M, ns, _p(out), _p(ws), ws.numel(), _stream()),
+                       "d3d_group_points_grad")
     _count()
     return out
 

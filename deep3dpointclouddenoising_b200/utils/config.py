@@ -98,12 +98,16 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   staged_tiles_backward: 'scatter' (default): PosPool backward as the transposed forward tile on the tensor cores, partial
 #     sums added with float atomics like the reference's backward (203 us against 322 us at the first level); 'gather': the
 #     support-tile form without atomics (slower, 838 us); False: the segmented reduction over the inverse map (bit-reproducible).
+#   deterministic_scatter: False — _ext.group_points_grad adds with shared-memory float atomics like the reference's
+#     kernel (1.04 ms at B=16 x 8192, C=72, ns=52; the reference's kernel: 23.7 ms); True: fixed-order sums over an inverse
+#     map (7.8 ms, bit-reproducible).
 #   cpu_modules: False — the 1x1-convolution / BatchNorm blocks raise on CPU tensors (no CPU path in the product); the CPU
 #     oracle (oracle/cpu_model.py) sets it while it drives the module tree with the reference's formulas.
 runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "channel_last": True,
                     "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
                     "staged_tiles_backward": "scatter", "own_gemm": True, "wgrad_side_stream": True,
-                    "own_wgrad": False, "own_wgrad_min_rows": 0, "cpu_modules": False})
+                    "own_wgrad": False, "own_wgrad_min_rows": 0, "cpu_modules": False,
+                    "deterministic_scatter": False})
 
 
 def reset_config():

@@ -97,6 +97,11 @@ int d3d_group_points(const float* points, const int* idx, int B, int C, int N, i
 size_t d3d_group_points_grad_workspace_bytes(int B, int N, int M, int nsample);
 int d3d_group_points_grad(const float* grad_out, const int* idx, int B, int C, int N, int M, int nsample,
                           float* grad_points, void* ws, size_t ws_bytes, void* stream);
+/* The same sums in the reference's own formulation (atomicAdd, group_points_gpu.cu:61-66), one block per (b, c) plane
+ * with the N sums in shared memory and the gradients / indices streamed coalesced: 7x faster than the fixed-order
+ * form (1.04 ms against 7.8 ms) at B=16, C=72, M=N=8192, nsample=52, reproducible to rounding only.  N <= 51200 (D3D_ERR_UNSUPPORTED beyond). */
+int d3d_group_points_grad_atomic(const float* grad_out, const int* idx, int B, int C, int N, int M, int nsample,
+                                 float* grad_points, void* stream);
 
 /* Inverse neighbour map (CSR by support point) of one idx tensor; shared by every backward kernel
  * of a (query set, support set) pair.

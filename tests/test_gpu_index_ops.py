@@ -134,10 +134,12 @@ def test_group_points_and_grad(cuda_device, oracle):
         assert np.array_equal(out.cpu().numpy(), oracle.group_points(f, idx))  # a copy: exact
         g = rng.standard_normal((B, C, M, ns)).astype(np.float32)
         dg, di = dev(g, cuda_device), dev(idx, cuda_device)
-        gp = ops.group_points_grad(dg, di, N)
+        gp = ops.group_points_grad(dg, di, N, deterministic=True)
         # tolerance: fp32 sum of <= a few hundred terms in a different order than the oracle's exact sum
         np.testing.assert_allclose(gp.cpu().numpy(), oracle.group_points_grad(g, idx, N), rtol=1e-4, atol=1e-4)
-        assert torch.equal(gp, ops.group_points_grad(dg, di, N))  # deterministic (no float atomics)
+        assert torch.equal(gp, ops.group_points_grad(dg, di, N, deterministic=True))  # fixed order, no float atomics
+        fast = ops.group_points_grad(dg, di, N)  # default: shared-memory atomics per (b, c) plane, like the reference
+        np.testing.assert_allclose(fast.cpu().numpy(), oracle.group_points_grad(g, idx, N), rtol=1e-4, atol=1e-4)
 
 
 def test_inverse_map_is_sorted_and_complete(cuda_device, oracle):
