@@ -220,7 +220,7 @@ int d3d_cl_to_cm(const float* src_cl, int B, int C, int N, float* dst_cm, void* 
 static long long g_launches = 0;
 long long d3d_kernel_launches(void) { return g_launches; }
 
-int d3d_abi_version(void) { return 3; }
+int d3d_abi_version(void) { return 4; }
 
 const char* d3d_error_string(int code) {
   switch (code) {

@@ -48,6 +48,7 @@ struct TileArgs {
   int M, N, C, nsample, reduction;
   float inv_radius;
   const void* plan;          // tile plan of (by_support, order)
+  float* partial;            // ordered backward: per-tile partial rows [tile][stride][C] (null: float atomics)
   unsigned long long* timing;  // diagnostics (tools/tile_phases.py): 8 timestamps per CTA, or null
 };
 
@@ -79,27 +80,43 @@ __device__ __forceinline__ unsigned short bf16_of_count(int m) { return (unsigne
 //   counts[tile]            U = size of the union of the support rows the tile's 128 queries gather
 //   ranks [tile][128][ns]   union rank of every list entry (uint16, 0xffff = unused slot), rows in tile order
 //   unions[tile][stride]    the union's support indices in ascending order (uint16: N <= 16384)
+//   tilemask[n], rank_of[tile][n]   the inverse view for the ordered (atomic-free) backward: which tiles gather support
+//                           row n and at which union rank
 struct PlanView {
   const int* counts;
   const unsigned short* ranks;
   const unsigned short* unions;
+  const unsigned* tilemask;        // [B][N][4]: bit t set = tile t of the cloud gathers support row n (tiles <= 128)
+  const unsigned short* rank_of;   // [B][tiles][N]: union rank of support n inside tile t (valid where the bit is set)
   int stride;
 };
 
-__host__ __device__ inline size_t plan_counts_bytes(int B, int tiles) { return ((size_t)B * tiles * 4 + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t align256z(size_t x) { return (x + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t plan_counts_bytes(int B, int tiles) { return align256z((size_t)B * tiles * 4); }
 __host__ __device__ inline int plan_stride(int N, int ns) { return (min(N, kTQ * ns) + 7) & ~7; }
-__host__ __device__ inline size_t plan_ranks_bytes(int B, int tiles, int ns) { return (size_t)B * tiles * kTQ * ns * 2; }
+__host__ __device__ inline size_t plan_ranks_bytes(int B, int tiles, int ns) { return align256z((size_t)B * tiles * kTQ * ns * 2); }
+__host__ __device__ inline size_t plan_unions_bytes(int B, int tiles, int N, int ns) {
+  return align256z((size_t)B * tiles * plan_stride(N, ns) * 2);
+}
+__host__ __device__ inline size_t plan_tilemask_bytes(int B, int N) { return align256z((size_t)B * N * 16); }
 __host__ __device__ inline size_t plan_total_bytes(int B, int M, int N, int ns) {
   const int tiles = (M + kTQ - 1) / kTQ;
-  return plan_counts_bytes(B, tiles) + plan_ranks_bytes(B, tiles, ns) + (size_t)B * tiles * plan_stride(N, ns) * 2;
+  return plan_counts_bytes(B, tiles) + plan_ranks_bytes(B, tiles, ns) + plan_unions_bytes(B, tiles, N, ns) +
+         plan_tilemask_bytes(B, N) + align256z((size_t)B * tiles * N * 2);
 }
 __host__ __device__ inline PlanView plan_view(const void* plan, int B, int M, int N, int ns) {
   const int tiles = (M + kTQ - 1) / kTQ;
   const unsigned char* p = static_cast<const unsigned char*>(plan);
   PlanView v;
   v.counts = reinterpret_cast<const int*>(p);
-  v.ranks = reinterpret_cast<const unsigned short*>(p + plan_counts_bytes(B, tiles));
-  v.unions = reinterpret_cast<const unsigned short*>(p + plan_counts_bytes(B, tiles) + plan_ranks_bytes(B, tiles, ns));
+  p += plan_counts_bytes(B, tiles);
+  v.ranks = reinterpret_cast<const unsigned short*>(p);
+  p += plan_ranks_bytes(B, tiles, ns);
+  v.unions = reinterpret_cast<const unsigned short*>(p);
+  p += plan_unions_bytes(B, tiles, N, ns);
+  v.tilemask = reinterpret_cast<const unsigned*>(p);
+  p += plan_tilemask_bytes(B, N);
+  v.rank_of = reinterpret_cast<const unsigned short*>(p);
   v.stride = plan_stride(N, ns);
   return v;
 }
@@ -188,13 +205,18 @@ tile_plan_kernel(const int* __restrict__ by_support, const int* __restrict__ nva
                             : (unsigned short)(sPrefix[v >> 5] + __popc(sBitmap[v >> 5] & ((1u << (v & 31)) - 1u)));
   }
   unsigned short* uni = const_cast<unsigned short*>(pv.unions) + t_lin * pv.stride;
+  unsigned* tmask = const_cast<unsigned*>(pv.tilemask) + (size_t)b * N * 4 + (tile >> 5);
+  unsigned short* rank_of = const_cast<unsigned short*>(pv.rank_of) + t_lin * N;
   for (int w = tid; w < W; w += kPlanThreads) {
     unsigned bits = sBitmap[w];
     unsigned r = sPrefix[w];
     while (bits) {
       const int bit = __ffs(bits) - 1;
       bits &= bits - 1;
-      uni[r++] = (unsigned short)(w * 32 + bit);
+      const int n = w * 32 + bit;
+      atomicOr(tmask + (size_t)n * 4, 1u << (tile & 31));  // integer OR: the result does not depend on the order
+      rank_of[n] = (unsigned short)r;
+      uni[r++] = (unsigned short)n;
     }
   }
 }
@@ -461,9 +483,17 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
           o[i] = rc * __uint_as_float(d1[i]) - __uint_as_float(d2[i]);
         }
         if (src >= 0) {
+          if (a.partial) {  // ordered form: the tile's own row of partial sums; pospool_scatter_reduce_kernel adds them up
+            float* prow_out = a.partial + ((t_lin * pv.stride + (size_t)r) * a.C + c0);
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            if (16 * ch + 4 * v < cbn) red_add_v4(orow + 16 * ch + 4 * v, o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+            for (int v = 0; v < 4; ++v)
+              if (16 * ch + 4 * v < cbn)
+                *reinterpret_cast<float4*>(prow_out + 16 * ch + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+              if (16 * ch + 4 * v < cbn) red_add_v4(orow + 16 * ch + 4 * v, o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+          }
         }
       }
       tc_fence_before();
@@ -475,6 +505,51 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
   if (warp == 12) tmem_dealloc(tmem_base, 512u);
 }
 
+// Ordered form, second kernel: a warp owns one support row and adds the partial rows of the tiles that gathered it in
+// ascending tile order (tilemask / rank_of of the plan) — a fixed-order segmented reduction, no float atomics; rows no
+// tile gathered come out as zeros (no separate zero fill).
+__global__ void __launch_bounds__(256)
+pospool_scatter_reduce_kernel(const float* __restrict__ partial, const void* plan, int B, int M, int N, int C, int ns,
+                              float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * N) return;
+  const int b = (int)(row / N), n = (int)(row - (long long)b * N);
+  const PlanView pv = plan_view(plan, B, M, N, ns);
+  const int tiles = (M + kTQ - 1) / kTQ;
+  const uint4 mask = __ldg(reinterpret_cast<const uint4*>(pv.tilemask) + row);
+  const unsigned words[4] = {mask.x, mask.y, mask.z, mask.w};
+  // lane l looks up the rank of tile (32 w + l) for every word w with its bit set: at most four independent loads
+  unsigned rk[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    rk[w] = 0u;
+    const int t = 32 * w + lane;
+    if ((words[w] >> lane) & 1u) rk[w] = __ldg(pv.rank_of + ((size_t)b * tiles + t) * N + n);
+  }
+  const int groups = C >> 2;
+  float4* orow = reinterpret_cast<float4*>(out + (size_t)row * C);
+  for (int g0 = 0; g0 < groups; g0 += 32) {
+    const int g = g0 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      unsigned bits = words[w];
+      while (bits) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const unsigned r = __shfl_sync(D3D_FULL_MASK, rk[w], l);
+        const size_t t_lin = (size_t)b * tiles + 32 * w + l;
+        if (g < groups) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (t_lin * pv.stride + r) * C) + g);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+    }
+    if (g < groups) orow[g] = acc;
+  }
+}
+
 int launch_scatter_bwd(const TileArgs& a, int B, cudaStream_t st) {
   if (a.M > kMaxPoints || a.N > kMaxPoints || a.nsample > kMaxNs || a.C % 4 != 0) return D3D_ERR_UNSUPPORTED;
   const int cbn_max = a.C < kCB ? a.C : kCB;
@@ -482,11 +557,18 @@ int launch_scatter_bwd(const TileArgs& a, int B, cudaStream_t st) {
   if ((unsigned)kTQ * L.row_bytes > 2 * kAtBytes) return D3D_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(pospool_scatter_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
   if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(a.out, 0, (size_t)B * a.N * a.C * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
+  if (!a.partial) {  // atomic form: the kernel adds into the output
+    e = cudaMemsetAsync(a.out, 0, (size_t)B * a.N * a.C * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+  }
   dim3 grid(d3d_ceil_div(a.M, kTQ), d3d_ceil_div(a.C, kCB), B);
   pospool_scatter_bwd_kernel<<<grid, kBT, L.total, st>>>(a);
   d3d_note_launches(1);
+  if (a.partial) {
+    const long long rows = (long long)B * a.N;
+    pospool_scatter_reduce_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a.partial, a.plan, B, a.M, a.N, a.C, a.nsample, a.out);
+    d3d_note_launches(1);
+  }
   return d3d_launch_status();
 }
 
@@ -825,6 +907,9 @@ int d3d_pospool_tile_plan(const int* idx_by_support, const int* nvalid, const in
   if (plan_bytes < plan_total_bytes(B, M, N, nsample) || ((uintptr_t)plan & 255)) return D3D_ERR_WORKSPACE;
   const int W = (N + 31) / 32;
   const size_t smem = align16((unsigned)(kTQ * nsample * 2)) + (size_t)(((W + 3) & ~3) + ((W + 4) & ~3)) * 4 + 2 * kTQ * 4;
+  const PlanView pv = plan_view(plan, B, M, N, nsample);
+  cudaError_t e = cudaMemsetAsync(const_cast<unsigned*>(pv.tilemask), 0, (size_t)B * N * 16, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
   dim3 grid(d3d_ceil_div(M, kTQ), B);
   tile_plan_kernel<<<grid, kPlanThreads, smem, (cudaStream_t)stream>>>(idx_by_support, nvalid, query_mask, query_order, B, M, N,
                                                                       nsample, plan);
@@ -847,10 +932,15 @@ int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const fl
   return launch_fwd_pipelined(a, B, (cudaStream_t)stream);
 }
 
+size_t d3d_pospool_scatter_bwd_workspace_bytes(int B, int M, int N, int C, int nsample) {
+  if (B <= 0 || M <= 0 || N <= 0 || C <= 0 || nsample <= 0) return 0;
+  return (size_t)B * d3d_ceil_div(M, kTQ) * plan_stride(N, nsample) * C * sizeof(float);
+}
+
 int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
                             const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order,
                             const void* plan, int B, int M, int N, int C, int nsample, float radius, int reduction,
-                            float* grad_feat_cl, void* stream) {
+                            float* grad_feat_cl, void* ws, size_t ws_bytes, void* stream) {
   D3D_REQUIRE(grad_out_cl && query_xyz && support_xyz && idx_by_support && nvalid && query_mask && query_order && grad_feat_cl);
   D3D_REQUIRE(plan);
   D3D_REQUIRE(B >= 0 && M >= 0 && N > 0 && C > 0 && nsample > 0 && nsample <= D3D_MAX_NSAMPLE && radius > 0.f);
@@ -862,6 +952,10 @@ int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, co
   a.src = grad_out_cl; a.out = grad_feat_cl; a.query_xyz = query_xyz; a.support_xyz = support_xyz; a.by_support = idx_by_support;
   a.nvalid = nvalid; a.query_mask = query_mask; a.order = query_order; a.M = M; a.N = N; a.C = C; a.nsample = nsample;
   a.reduction = reduction; a.inv_radius = 1.0f / radius; a.plan = plan;
+  if (ws) {  // ordered (atomic-free) form
+    if (ws_bytes < d3d_pospool_scatter_bwd_workspace_bytes(B, M, N, C, nsample) || ((uintptr_t)ws & 15)) return D3D_ERR_WORKSPACE;
+    a.partial = (float*)ws;
+  }
   return launch_scatter_bwd(a, B, (cudaStream_t)stream);
 }
 

@@ -125,12 +125,13 @@ class PosPoolFunction(Function):
         g_cl = _rows(grad_out)
         # 'scatter': the forward tile transposed on the tensor cores, float atomics across tiles (faster at every level, also
         # for strided lists where the forward tiles are not); False: segmented reduction over the inverse map
+        mode = runtime.staged_tiles_backward
         plan = (nbr.tile_plan(query_xyz, query_mask)
-                if runtime.staged_tiles_backward == 'scatter' and ctx.reduction != 'sum' and nbr.by_support is not None else None)
+                if mode in ('scatter', 'ordered') and ctx.reduction != 'sum' and nbr.by_support is not None else None)
         if plan is not None:
             gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, None, None, nbr.nvalid, query_mask, nbr.n_support,
                                     nbr.nsample, ctx.radius, ctx.reduction, query_order=_neighbors.spatial_order(query_xyz),
-                                    idx_by_support=nbr.by_support, plan=plan)
+                                    idx_by_support=nbr.by_support, plan=plan, ordered=mode == 'ordered')
         else:
             rowptr, entries = nbr.csr()
             gf_cl = ops.pospool_bwd(g_cl, query_xyz, support_xyz, rowptr, entries, nbr.nvalid, query_mask, nbr.n_support,

@@ -233,7 +233,7 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order=True):
             if with_csr:  # in the order backward asks for them: decoder first, then coarse to fine
                 from .utils.config import runtime
                 # self lists feed local aggregation only: PosPool's scatter-form backward works from the tile plan
-                skip_self = with_order and runtime.staged_tiles and runtime.staged_tiles_backward == 'scatter'
+                skip_self = with_order and runtime.staged_tiles and runtime.staged_tiles_backward in ('scatter', 'ordered')
                 for k, nbr in [(None, u) for u in ups] + list(enumerate(lists))[::-1]:
                     if not (skip_self and k is not None and k % 2 == 0 and nbr._plan is not None):
                         nbr.csr()

@@ -290,10 +290,11 @@ def pospool_fwd(feat_cl, query_xyz, support_xyz, idx, nvalid, query_mask, radius
 
 
 def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, query_mask, n_support, nsample, radius,
-                reduction, query_order=None, idx_by_support=None, plan=None):
+                reduction, query_order=None, idx_by_support=None, plan=None, ordered=True):
     """query_order (B, M) + idx_by_support (the forward tile's inputs; + the pair's `tile_plan`, built here when not
-    given): the scatter-form staged-tile kernel (tensor cores, float atomics across tiles; rowptr / entries are not read);
-    otherwise the per-support segmented reduction over the inverse map (bit-reproducible)."""
+    given): the scatter-form staged-tile kernel on the tensor cores (rowptr / entries are not read) — ordered=True adds
+    the tiles' partial rows per support in a fixed order (no float atomics, bit-reproducible), ordered=False with float
+    atomics like the reference; otherwise the per-support segmented reduction over the inverse map."""
     L = _lib.load()
     g = _f32(grad_out_cl, "grad_out")
     B, M, C = g.shape
@@ -302,10 +303,12 @@ def pospool_bwd(grad_out_cl, query_xyz, support_xyz, rowptr, entries, nvalid, qu
         if query_order is not None and idx_by_support is not None and _tiles_ok(M, int(n_support), int(nsample), C):
             if plan is None:
                 plan = tile_plan(idx_by_support, nvalid, query_mask, query_order, n_support)
+            ws = _ws(L.d3d_pospool_scatter_bwd_workspace_bytes(B, M, int(n_support), C, int(nsample)), g.device) if ordered else None
             _lib.check(L.d3d_pospool_scatter_bwd(_p(g), _p(query_xyz), _p(support_xyz),
                                                  _p(_i32(idx_by_support, "idx_by_support")), _p(nvalid), _p(query_mask),
                                                  _p(_i32(query_order, "query_order")), _p(plan), B, M, int(n_support), C,
-                                                 int(nsample), float(radius), REDUCTIONS[reduction], _p(out), _stream()),
+                                                 int(nsample), float(radius), REDUCTIONS[reduction], _p(out), _p(ws),
+                                                 ws.numel() if ws is not None else 0, _stream()),
                        "d3d_pospool_scatter_bwd")
         else:
             _lib.check(L.d3d_pospool_bwd(_p(g), _p(query_xyz), _p(support_xyz), _p(rowptr), _p(entries), _p(nvalid),

@@ -96,9 +96,10 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #   wgrad_side_stream: with grads_in_place, the weight-gradient GEMMs run on a side stream (models/blocks.py); the
 #     training loop joins them with distributed.FlatParameters.reduce() / blocks.join_weight_grads() before the optimiser.
 #   staged_tiles_backward: 'scatter' (default): PosPool backward as the transposed forward tile on the tensor cores, partial
-#     sums added with float atomics like the reference's backward (164 us against 322 us at the first level); False: the
-#     atomic-free segmented reduction over the inverse map (bit-reproducible).  A support-tile tensor-core form without
-#     atomics was measured at 838 us and removed.
+#     sums added with float atomics like the reference's backward (164 us against 322 us at the first level, step 7.9 ms);
+#     'ordered': the same tiles store their partial rows and a second kernel adds them per support row in ascending tile
+#     order — no float atomics, bit-reproducible (247 us, step 8.2 ms); False: the atomic-free segmented reduction over the
+#     inverse map (322 us, step 8.6 ms).  A support-tile tensor-core form without atomics was measured at 838 us and removed.
 #   deterministic_scatter: False — _ext.group_points_grad adds with shared-memory float atomics like the reference's
 #     kernel (1.04 ms at B=16 x 8192, C=72, ns=52; the reference's kernel: 23.7 ms); True: fixed-order sums over an inverse
 #     map (7.8 ms, bit-reproducible).

@@ -151,7 +151,8 @@ int d3d_spatial_order(const float* xyz, int B, int N, int* order, void* stream);
  * Limits: M, N <= 16384, nsample <= 64, C % 4 == 0 (D3D_ERR_UNSUPPORTED otherwise). */
 /* Tile plan of one (neighbour list, query order) pair, shared by every forward / scatter-backward launch on that pair
  * (two LocalAggregation layers use the level-0 list: four launches): per tile of 128 queries the size of the union of
- * the support rows they gather, the union itself (ascending indices) and the union rank of every list entry.  `plan`:
+ * the support rows they gather, the union itself (ascending indices), the union rank of every list entry, and the inverse
+ * view (which tiles gather a support row, at which rank) for the ordered backward.  `plan`:
  * d3d_pospool_tile_plan_bytes(B, M, N, nsample) bytes, 256-byte aligned. */
 size_t d3d_pospool_tile_plan_bytes(int B, int M, int N, int nsample);
 int d3d_pospool_tile_plan(const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order, int B,
@@ -161,13 +162,19 @@ int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const fl
                           int N, int C, int nsample, float radius, int reduction, float* out_cl, void* stream);
 /* Backward pass in scatter form: the CTA owns the forward tile (128 queries), stages their gradient rows once, and
  * contracts A^T (the forward multiplicity matrix read through the MN-major descriptor) with them on the tensor cores,
- * 128 union rows per accumulator; the partial sums of a feature-gradient row over the tiles that reference it are added
- * with red.global.add.v4.f32 (grad_feat_cl is zero-filled by the call) — float atomics like the reference's own
- * backward (group_points_gpu.cu:48-69), so results are reproducible to rounding only.  Same limits as the forward. */
+ * 128 union rows per accumulator.  A feature-gradient row receives partial sums from every tile that gathered it:
+ *   ws != NULL (d3d_pospool_scatter_bwd_workspace_bytes): ORDERED form — every tile stores its partial rows, a second
+ *     kernel adds them per support row in ascending tile order (plan.tilemask / rank_of): a fixed-order segmented
+ *     reduction without float atomics, bit-reproducible;
+ *   ws == NULL: the partial sums are added with red.global.add.v4.f32 (grad_feat_cl is zero-filled by the call) — float
+ *     atomics like the reference's own backward (group_points_gpu.cu:48-69), reproducible to rounding only.
+ * Same limits as the forward. */
+size_t d3d_pospool_scatter_bwd_workspace_bytes(int B, int M, int N, int C, int nsample);
 int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, const float* support_xyz,
                             const int* idx_by_support, const int* nvalid, const int* query_mask, const int* query_order,
                             const void* plan, int B, int M, int N, int C, int nsample, float radius, int reduction,
-                            float* grad_feat_cl, void* stream);
+                            float* grad_feat_cl, void* ws, size_t ws_bytes, void* stream);
+
 #define D3D_KP_CONSTANT 0
 #define D3D_KP_LINEAR   1
 #define D3D_KP_GAUSSIAN 2

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_abi_version_and_error_strings(lib):
-    assert lib.d3d_abi_version() == 3
+    assert lib.d3d_abi_version() == 4
     assert lib.d3d_error_string(0) == b"ok"
     assert b"workspace" in lib.d3d_error_string(-3)
 

@@ -146,8 +146,9 @@ def test_fused_ops_against_float_oracle(cuda_device, oracle, C, N, M, ns, radius
 
 
 def test_backward_is_deterministic(cuda_device):
-    """Two backward passes give identical bits with the segmented reduction (runtime.staged_tiles_backward = False: no
-    float atomics); the default scatter tiles add partial sums atomically like the reference and agree to rounding."""
+    """Two backward passes give identical bits with the atomic-free forms (runtime.staged_tiles_backward = False: segmented
+    reduction over the inverse map; 'ordered': tensor-core tiles + fixed-order second pass); the default scatter tiles add
+    partial sums atomically like the reference and agree to rounding."""
     from deep3dpointclouddenoising_b200 import fused, neighbors
     from deep3dpointclouddenoising_b200.utils.config import runtime
     pts, mask, feats, _ = synthetic.make_batch(9, 4, 4096, ragged=True)
@@ -157,7 +158,7 @@ def test_backward_is_deterministic(cuda_device):
     old = runtime.staged_tiles_backward
     try:
         grads = []
-        for mode in (False, False, 'scatter'):
+        for mode in (False, False, 'scatter', 'ordered', 'ordered'):
             runtime.staged_tiles_backward = mode
             neighbors.cache.clear()
             nbr = neighbors.ball_neighbors(dx, dx, dm, dm, 0.025, 52)
@@ -165,8 +166,9 @@ def test_backward_is_deterministic(cuda_device):
             grads.append(torch.autograd.grad(y, f, g)[0])
     finally:
         runtime.staged_tiles_backward = old
-    assert torch.equal(grads[0], grads[1])
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[3], grads[4])  # both atomic-free forms: same bits twice
     torch.testing.assert_close(grads[2], grads[0], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(grads[3], grads[0], rtol=1e-4, atol=2e-5)
 
 
 @pytest.mark.parametrize("C,N,M,ns,radius", [(72, 2048, 2048, 52, 0.025), (144, 2048, 512, 39, 0.03), (288, 512, 512, 32, 0.05),

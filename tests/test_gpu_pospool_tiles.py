@@ -101,8 +101,14 @@ def test_staged_pospool_against_float_oracle(cuda_device, oracle, C, N, M, ns, r
     # backward, scatter form: the forward tile's transposed contraction, partial sums added with float atomics
     plan = ops.tile_plan(dbys, dnv, dqm, oq, N)
     gs = ops.pospool_bwd(g_cl, dq, ds, None, None, dnv, dqm, N, ns, radius, reduction, query_order=oq, idx_by_support=dbys,
-                         plan=plan)
+                         plan=plan, ordered=False)
     np.testing.assert_allclose(gs.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
+    # ordered form: the tiles' partial rows added per support in ascending tile order — no float atomics, same bits twice
+    go = ops.pospool_bwd(g_cl, dq, ds, None, None, dnv, dqm, N, ns, radius, reduction, query_order=oq, idx_by_support=dbys,
+                         plan=plan, ordered=True)
+    np.testing.assert_allclose(go.cpu().numpy().transpose(0, 2, 1), ref_g.numpy(), **BWD)
+    assert torch.equal(go, ops.pospool_bwd(g_cl, dq, ds, None, None, dnv, dqm, N, ns, radius, reduction, query_order=oq,
+                                           idx_by_support=dbys, plan=plan, ordered=True))
     # the forward has a fixed summation order: same bits on a second run (also with the plan built inside the call)
     assert torch.equal(out, ops.pospool_fwd(f_cl, dq, ds, didx, dnv, dqm, radius, reduction, query_order=oq, idx_by_support=dbys,
                                             plan=plan))

@@ -53,7 +53,8 @@ def main():
         t["fwd gather"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg'))
         t["fwd tiles"] = timeit(lambda: ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan))
         t["bwd gather"] = timeit(lambda: ops.pospool_bwd(g, q, s, rowptr, entries, nv, qm, N, ns, r, 'avg'))
-        t["bwd scatter"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan))
+        t["bwd scatter"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan, ordered=False))
+        t["bwd ordered"] = timeit(lambda: ops.pospool_bwd(g, q, s, None, None, nv, qm, N, ns, r, 'avg', query_order=oq, idx_by_support=bys, plan=plan, ordered=True))
         a = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg')
         b = ops.pospool_fwd(f, q, s, idx, nv, qm, r, 'avg', query_order=oq, idx_by_support=bys)
         err = ((a - b).abs().max() / a.abs().max()).item()
