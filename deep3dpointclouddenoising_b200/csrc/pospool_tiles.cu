@@ -295,10 +295,22 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
   const int n_rows = min(kTQ, a.M - row0);
   const size_t qbase = (size_t)b * a.M;
 
-  // ---- owners (queries), barriers, TMEM: as in the gather kernel ------------------------------------------------
+  D3D_STAMP(0);
+  // ---- owners (queries), barriers, TMEM ---------------------------------------------------------------------------
   if (warp == 12) tmem_alloc(tmem_slot, 512u);
+  const float* g_rows = a.src + (size_t)b * a.M * a.C + c0;
+  if (tid >= kBT - 128) {
+    // the tile's gradient rows start flying at once: these threads read the processing order themselves
+    const int t = tid - (kBT - 128);
+    if (t == 0) {
+      mbar_init(bar_stage, 1);
+      mbar_init_fence();
+      mbar_arrive_expect_tx(bar_stage, (unsigned)n_rows * L.row_bytes);
+    }
+    named_bar_sync(1, 128);  // barrier initialised, expect_tx precedes every complete_tx
+    if (t < n_rows) bulk_g2s(smem_u32(sA + (size_t)t * L.row_bytes), g_rows + (size_t)order[row0 + t] * a.C, L.row_bytes, bar_stage);
+  }
   if (tid == 160) {
-    mbar_init(bar_stage, 1);
     mbar_init(bar_plan, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_a_full(i), kTQ);
@@ -338,14 +350,7 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
   const float ctr_x = (sCtr[0] + sCtr[3] + sCtr[6] + sCtr[9]) * inv_rows, ctr_y = (sCtr[1] + sCtr[4] + sCtr[7] + sCtr[10]) * inv_rows,
               ctr_z = (sCtr[2] + sCtr[5] + sCtr[8] + sCtr[11]) * inv_rows;
 
-  // the tile's gradient rows start flying now (one bulk copy per row, issued by the last four warps)
-  const float* g_rows = a.src + (size_t)b * a.M * a.C + c0;
-  if (tid >= kBT - 128) {
-    const int t = tid - (kBT - 128);
-    if (t == 0) mbar_arrive_expect_tx(bar_stage, (unsigned)n_rows * L.row_bytes);
-    named_bar_sync(1, 128);  // expect_tx precedes every complete_tx
-    if (t < n_rows) bulk_g2s(smem_u32(sA + (size_t)t * L.row_bytes), g_rows + (size_t)sOwnerId[t] * a.C, L.row_bytes, bar_stage);
-  }
+  D3D_STAMP(1);
 
   // ---- union ranks of the list entries and the union itself: from the tile plan (one bulk copy into sEnt) ----------
   const PlanView pv = plan_view(a.plan, (int)gridDim.z, a.M, a.N, ns);
@@ -360,7 +365,8 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
 
   // ---- gradient rows -> 3 bf16 planes of G1 and 3 of G2 (MN-major B operand, K = query) ----------------------------
   const int n_groups = (cbn + 7) >> 3;
-  mbar_wait(bar_stage, 0u);
+  mbar_wait_short(bar_stage, 0u);
+  D3D_STAMP(2);
   for (int task = tid; task < kTQ * n_groups; task += kBT) {
     const int u = task & (kTQ - 1), g = task >> 7;
     unsigned char* dst = sPlanes + (u >> 3) * L.lbo_b + g * 128 + (u & 7) * 16;
@@ -393,8 +399,9 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
     }
   }
   fence_async_smem();
-  mbar_wait(bar_plan, 0u);
+  mbar_wait_short(bar_plan, 0u);
   __syncthreads();  // planes complete, ranks in place, the staging area (= the A blocks) is free
+  D3D_STAMP(3);
 
   const int n_blocks = (U + kUB - 1) / kUB;
   const int ksteps = (n_rows + 15) >> 4;
@@ -408,23 +415,31 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
     for (int m = 0; m < n_blocks; ++m) {
       const int buf = m & 1;
       if (m >= 2) {
-        mbar_wait(bar_mma(buf), (unsigned)(((m >> 1) - 1) & 1));
+        mbar_wait_short(bar_mma(buf), (unsigned)(((m >> 1) - 1) & 1));
         tc_fence_after();
       }
       unsigned char* arow = sA + buf * kAtBytes + (tid >> 3) * kAtGroup + (tid & 7) * 16;
 #pragma unroll
       for (int g = 0; g < kUB / 8; ++g) *reinterpret_cast<uint4*>(arow + g * 128) = make_uint4(0u, 0u, 0u, 0u);
       const int limit = (m + 1) * kUB;
-      while (cur < cur_end) {
-        const int r = e[cur];
-        if (r >= limit) break;
-        int mult = 1;
-        if (info >> 16) {  // padded query: slot k of the reference list repeats winner k % nvalid
-          const int nv = (info >> 8) & 255;
-          mult = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
+      while (cur < cur_end) {  // four list entries per round: their loads are independent of each other
+        int rr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rr[i] = cur + i < cur_end ? (int)e[cur + i] : 0x7fffffff;
+        bool full = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = rr[i];
+          if (r >= limit) { full = true; break; }
+          int mult = 1;
+          if (info >> 16) {  // padded query: slot k of the reference list repeats winner k % nvalid
+            const int nv = (info >> 8) & 255;
+            mult = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
+          }
+          *reinterpret_cast<unsigned short*>(arow + ((r & (kUB - 1)) >> 3) * 128 + (r & 7) * 2) = bf16_of_count(mult);
+          ++cur;
         }
-        *reinterpret_cast<unsigned short*>(arow + ((r & (kUB - 1)) >> 3) * 128 + (r & 7) * 2) = bf16_of_count(mult);
-        ++cur;
+        if (full) break;
       }
       fence_async_smem();
       mbar_arrive(bar_a_full(buf));
@@ -465,7 +480,7 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
         src = tile_union[r];
         sx = src_xyz[3 * (size_t)src] - ctr_x; sy = src_xyz[3 * (size_t)src + 1] - ctr_y; sz = src_xyz[3 * (size_t)src + 2] - ctr_z;
       }
-      mbar_wait(bar_mma(buf), (unsigned)((m >> 1) & 1));
+      mbar_wait_short(bar_mma(buf), (unsigned)((m >> 1) & 1));
       tc_fence_after();
       float* orow = out_rows + (size_t)(src >= 0 ? src : 0) * a.C;
       for (int ch = grp; ch * 16 < cbn; ch += 2) {
@@ -502,6 +517,9 @@ pospool_scatter_bwd_kernel(const TileArgs a) {
   }
   tc_fence_before();
   __syncthreads();
+  D3D_STAMP(4);
+  D3D_STAMP(5);
+  if (a.timing && tid == 0) a.timing[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + 6] = (unsigned long long)U;
   if (warp == 12) tmem_dealloc(tmem_base, 512u);
 }
 
@@ -562,7 +580,9 @@ int launch_scatter_bwd(const TileArgs& a, int B, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
   }
   dim3 grid(d3d_ceil_div(a.M, kTQ), d3d_ceil_div(a.C, kCB), B);
-  pospool_scatter_bwd_kernel<<<grid, kBT, L.total, st>>>(a);
+  TileArgs t = a;
+  t.timing = g_timing;
+  pospool_scatter_bwd_kernel<<<grid, kBT, L.total, st>>>(t);
   d3d_note_launches(1);
   if (a.partial) {
     const long long rows = (long long)B * a.N;
@@ -772,15 +792,23 @@ pospool_fwd_pipelined_kernel(const TileArgs a) {
 #pragma unroll
         for (int g = 0; g < kFC / 8; ++g) *reinterpret_cast<uint4*>(arow + g * 128) = make_uint4(0u, 0u, 0u, 0u);
         const int limit = (j + 1) * kFC;
-        while (cur < cur_end) {
-          const int r = e[cur];
-          if (r >= limit) break;
+        while (cur < cur_end) {  // two list entries per round (a 32-row chunk takes ~3.6 entries of a row)
+          const int ra = e[cur], rb = cur + 1 < cur_end ? (int)e[cur + 1] : 0x7fffffff;
+          if (ra >= limit) break;
           int m = 1;
           if (row_info >> 16) {  // padded query: slot k of the reference list repeats winner k % nvalid (cyclic padding)
             const int nv = (row_info >> 8) & 255;
             m = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
           }
-          *reinterpret_cast<unsigned short*>(arow + ((r & (kFC - 1)) >> 3) * 128 + (r & 7) * 2) = bf16_of_count(m);
+          *reinterpret_cast<unsigned short*>(arow + ((ra & (kFC - 1)) >> 3) * 128 + (ra & 7) * 2) = bf16_of_count(m);
+          ++cur;
+          if (rb >= limit) break;
+          m = 1;
+          if (row_info >> 16) {
+            const int nv = (row_info >> 8) & 255;
+            m = nv > 0 ? (ns - 1 - ((prow[cur] >> 16) & 255)) / nv + 1 : ns;
+          }
+          *reinterpret_cast<unsigned short*>(arow + ((rb & (kFC - 1)) >> 3) * 128 + (rb & 7) * 2) = bf16_of_count(m);
           ++cur;
         }
       }
