@@ -259,11 +259,14 @@ class OpTimer:
         per = {}
         for name, shape, s, e in self.records:
             key = name + "".join(f" {k}{v}" for k, v in sorted(shape.items()))
-            d = per.setdefault(key, {"op": name, "shape": shape, "ms": 0.0, "calls": 0})
-            d["ms"] += s.elapsed_time(e)
+            d = per.setdefault(key, {"op": name, "shape": shape, "times": [], "calls": 0})
+            d["times"].append(s.elapsed_time(e))
             d["calls"] += 1
         for d in per.values():
-            d["ms_per_call"] = d["ms"] / d["calls"]
+            # median over the calls of a shape: one call that happened to queue behind another stream's work (the neighbour
+            # ops run on a side stream in this eager pass) must not be charged to the op
+            d["ms_per_call"] = float(np.median(d.pop("times")))
+            d["ms"] = d["ms_per_call"] * d["calls"]
             d["ms_per_step"] = d["ms"] / n_steps
             d["bytes_per_call"] = algorithmic_bytes(d["op"], d["shape"])
             d["flops_per_call"] = algorithmic_flops(d["op"], d["shape"])
