@@ -56,6 +56,7 @@ SIGNATURES = {
     "d3d_voxel_barycentres": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "d3d_radius_patches_workspace_bytes": (_sz, [_i, _i, _i]),
     "d3d_radius_patches": (_i, [_vp, _i, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "d3d_radius_patches_tier": (_i, [_vp, _i, _vp, _i, _f, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "d3d_vote_mean": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "d3d_bn_act_workspace_bytes": (_sz, [_i]),
     "d3d_bn_act_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -48,6 +48,8 @@ struct PatchGrid {
 
 constexpr int kPatchThreads = 512;
 constexpr int kPatchSmemKeys = 12288;  // candidates sorted in shared memory (d2 as fp64 bits + index: 12 B each)
+constexpr int kSelBins = 512;          // selection histogram (few results out of many candidates)
+constexpr int kSelKeys = 2048;         // capacity of the selected set
 
 __device__ __forceinline__ int pcoord(float v, float mn, float inv_cell, int G) {
   return min(max((int)floorf((v - mn) * inv_cell), 0), G - 1);
@@ -57,14 +59,15 @@ __global__ void __launch_bounds__(kPatchThreads)
 radius_patch_kernel(const float* __restrict__ centres, int P, float radius, int num_points, PatchGrid g,
                     const int* __restrict__ cell_start, int n_cells, int N, const float4* __restrict__ sorted,
                     int* __restrict__ out_idx /* (P, num_points), -1 padded */, int* __restrict__ out_count,
-                    unsigned long long* __restrict__ scratch_keys, int* __restrict__ scratch_idx, int scratch_stride) {
+                    unsigned long long* __restrict__ scratch_keys, int* __restrict__ scratch_idx, int scratch_stride,
+                    int smem_keys) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int n_cand;
   const int pidx = blockIdx.x;
   const float cx = centres[3 * (size_t)pidx], cy = centres[3 * (size_t)pidx + 1], cz = centres[3 * (size_t)pidx + 2];
   unsigned long long* keys = scratch_stride > 0 ? scratch_keys + (size_t)pidx * scratch_stride : reinterpret_cast<unsigned long long*>(smem);
-  int* vals = scratch_stride > 0 ? scratch_idx + (size_t)pidx * scratch_stride : reinterpret_cast<int*>(smem + (size_t)kPatchSmemKeys * 8);
-  const int cap = scratch_stride > 0 ? scratch_stride : kPatchSmemKeys;
+  int* vals = scratch_stride > 0 ? scratch_idx + (size_t)pidx * scratch_stride : reinterpret_cast<int*>(smem + (size_t)smem_keys * 8);
+  const int cap = scratch_stride > 0 ? scratch_stride : smem_keys;
   if (threadIdx.x == 0) n_cand = 0;
   __syncthreads();
   const double r2 = (double)radius * (double)radius;
@@ -90,10 +93,70 @@ radius_patch_kernel(const float* __restrict__ centres, int P, float radius, int 
     }
   }
   __syncthreads();
-  const int n = min(n_cand, cap);
+  int n = min(n_cand, cap);
+  // ---- few results out of many candidates (neighbour lists: 26-52 nearest of hundreds to thousands in the ball): select
+  // before sorting.  A 512-bin histogram of d2 / r2 (monotone in the key) gives the bin b* where the cumulative count
+  // reaches num_points; every candidate of a bin <= b* is copied to a small buffer and only that buffer is sorted —
+  // the same first num_points entries as the full sort (ties in b* are all kept and ordered by the sort).
+  __shared__ int hist[kSelBins];
+  __shared__ int sel_bin, sel_n;
+  __shared__ unsigned long long sel_keys[kSelKeys];
+  __shared__ int sel_vals[kSelKeys];
+  if (n_cand <= cap && n > 4 * num_points && n > 256) {
+    for (int i = threadIdx.x; i < kSelBins; i += kPatchThreads) hist[i] = 0;
+    if (threadIdx.x == 0) { sel_bin = kSelBins - 1; sel_n = 0; }
+    __syncthreads();
+    const double to_bin = (double)kSelBins / r2;
+    for (int i = threadIdx.x; i < n; i += kPatchThreads)
+      atomicAdd(&hist[min(kSelBins - 1, (int)(__longlong_as_double((long long)keys[i]) * to_bin))], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {  // inclusive scan of the 512 bins by one warp, 16 bins per lane
+      int local[kSelBins / 32], sum = 0;
+#pragma unroll
+      for (int k = 0; k < kSelBins / 32; ++k) { sum += hist[threadIdx.x * (kSelBins / 32) + k]; local[k] = sum; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)threadIdx.x >= o) incl += up;
+      }
+      const int base = incl - sum;
+#pragma unroll
+      for (int k = 0; k < kSelBins / 32; ++k) {
+        const int c = base + local[k], before = c - hist[threadIdx.x * (kSelBins / 32) + k];
+        if (before < num_points && c >= num_points) sel_bin = threadIdx.x * (kSelBins / 32) + k;
+      }
+      __syncwarp();
+      int upto = 0;  // candidates in bins <= sel_bin
+      const int sb = sel_bin;
+#pragma unroll
+      for (int k = 0; k < kSelBins / 32; ++k)
+        if (threadIdx.x * (kSelBins / 32) + k <= sb) upto = base + local[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) upto = max(upto, __shfl_xor_sync(0xffffffffu, upto, o));
+      if (threadIdx.x == 0) sel_n = upto;
+    }
+    __syncthreads();
+    if (sel_n <= kSelKeys) {  // (a bin with thousands of equal distances would not fit: the full sort handles it)
+      __shared__ int fill;
+      if (threadIdx.x == 0) fill = 0;
+      __syncthreads();
+      const int sb = sel_bin;
+      for (int i = threadIdx.x; i < n; i += kPatchThreads) {
+        const unsigned long long key = keys[i];
+        if (min(kSelBins - 1, (int)(__longlong_as_double((long long)key) * to_bin)) <= sb) {
+          const int pos = atomicAdd(&fill, 1);
+          sel_keys[pos] = key; sel_vals[pos] = vals[i];
+        }
+      }
+      __syncthreads();
+      n = sel_n;
+      keys = sel_keys; vals = sel_vals;
+    }
+  }
   int P2 = 1;
   while (P2 < n) P2 <<= 1;
-  P2 = min(P2, cap);  // cap is a power of two or the candidates fit
+  if (keys != sel_keys) P2 = min(P2, cap);  // cap is a power of two or the candidates fit
   for (int i = n + threadIdx.x; i < P2; i += kPatchThreads) { keys[i] = ~0ull; vals[i] = 0x7fffffff; }
   __syncthreads();
   // bitonic sort by (distance, index): ties (duplicate points) resolve to the lower index
@@ -108,7 +171,7 @@ radius_patch_kernel(const float* __restrict__ centres, int P, float radius, int 
       }
       __syncthreads();
     }
-  const int take = min(n, num_points);
+  const int take = min(min(n_cand, cap), num_points);
   for (int i = threadIdx.x; i < num_points; i += kPatchThreads) out_idx[(size_t)pidx * num_points + i] = i < take ? vals[i] : -1;
   if (threadIdx.x == 0) out_count[pidx] = n_cand;  // > cap means the candidate buffer overflowed (caller re-runs with scratch)
 }
@@ -158,6 +221,10 @@ int d3d_voxel_barycentres(const float* points, const int* rowptr, const int* ent
   return d3d_launch_status();
 }
 
+int d3d_radius_patches_tier(const float* points, int N, const float* centres, int P, float radius, int num_points,
+                            int smem_keys, int overflow_stride, int* out_idx, int* out_count, void* ws, size_t ws_bytes,
+                            void* stream);
+
 size_t d3d_radius_patches_workspace_bytes(int N, int P, int overflow_stride) {
   if (N <= 0 || P <= 0) return 0;
   size_t b = d3d_internal_grid_bytes(N, 0);
@@ -170,7 +237,17 @@ size_t d3d_radius_patches_workspace_bytes(int N, int P, int overflow_stride) {
  * patch); if some out_count exceeds that, call again with overflow_stride = a power of two >= max(out_count). */
 int d3d_radius_patches(const float* points, int N, const float* centres, int P, float radius, int num_points,
                        int overflow_stride, int* out_idx, int* out_count, void* ws, size_t ws_bytes, void* stream) {
+  return d3d_radius_patches_tier(points, N, centres, P, radius, num_points, kPatchSmemKeys, overflow_stride, out_idx, out_count,
+                                 ws, ws_bytes, stream);
+}
+
+/* smem_keys: candidates a block can hold in shared memory — 12288 (one block per SM), or a smaller power of two
+ * (>= 256) when the balls are known to be small: 12 bytes per key, so 2048 keys let 6 blocks share an SM. */
+int d3d_radius_patches_tier(const float* points, int N, const float* centres, int P, float radius, int num_points,
+                            int smem_keys, int overflow_stride, int* out_idx, int* out_count, void* ws, size_t ws_bytes,
+                            void* stream) {
   D3D_REQUIRE(points && centres && out_idx && out_count && N > 0 && P > 0 && radius > 0.f && num_points > 0);
+  D3D_REQUIRE(smem_keys == kPatchSmemKeys || (smem_keys >= 256 && smem_keys < kPatchSmemKeys && (smem_keys & (smem_keys - 1)) == 0));
   D3D_REQUIRE(overflow_stride == 0 || (overflow_stride & (overflow_stride - 1)) == 0);
   if (!ws || ws_bytes < d3d_radius_patches_workspace_bytes(N, P, overflow_stride)) return D3D_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -184,7 +261,7 @@ int d3d_radius_patches(const float* points, int N, const float* centres, int P, 
   if (e != cudaSuccess) return (int)e;
   unsigned long long* sk = nullptr;
   int* si = nullptr;
-  size_t smem = (size_t)kPatchSmemKeys * 12;
+  size_t smem = (size_t)smem_keys * 12;
   if (overflow_stride > 0) {
     unsigned char* p = (unsigned char*)ws + d3d_internal_grid_bytes(N, 0);
     p = (unsigned char*)(((uintptr_t)p + 255) & ~(uintptr_t)255);
@@ -195,7 +272,7 @@ int d3d_radius_patches(const float* points, int N, const float* centres, int P, 
   e = cudaFuncSetAttribute(radius_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kPatchSmemKeys * 12));
   if (e != cudaSuccess) return (int)e;
   radius_patch_kernel<<<P, kPatchThreads, smem, st>>>(centres, P, radius, num_points, g, cell_start, G * G * G, N, sorted, out_idx,
-                                                      out_count, sk, si, overflow_stride);
+                                                      out_count, sk, si, overflow_stride, smem_keys);
   d3d_note_launches(1);
   return d3d_launch_status();
 }

@@ -621,7 +621,10 @@ def voxel_barycentres(points, rowptr, entries, n_cells):
     return bary, counts
 
 
-def radius_patches(points, centres, radius, num_points, overflow_stride=0):
+def radius_patches(points, centres, radius, num_points, overflow_stride=0, smem_keys=12288):
+    """(idx (P, num_points) ascending distance, -1 padded; count (P)) of the points within `radius` of every centre.
+    smem_keys: candidates a block holds in shared memory (12288, or a smaller power of two >= 256: more blocks per SM when
+    the balls are small); a count above it means that ball overflowed — call again with more (`radius_neighbors` does)."""
     L = _lib.load()
     p, c = _f32(points, "points"), _f32(centres, "centres")
     N, P = p.shape[0], c.shape[0]
@@ -629,10 +632,33 @@ def radius_patches(points, centres, radius, num_points, overflow_stride=0):
         idx = torch.empty((P, num_points), dtype=torch.int32, device=p.device)
         cnt = torch.empty((P,), dtype=torch.int32, device=p.device)
         ws = _ws(L.d3d_radius_patches_workspace_bytes(N, P, int(overflow_stride)), p.device)
-        _lib.check(L.d3d_radius_patches(_p(p), N, _p(c), P, float(radius), int(num_points), int(overflow_stride), _p(idx),
-                                        _p(cnt), _p(ws), ws.numel(), _stream()), "d3d_radius_patches")
+        _lib.check(L.d3d_radius_patches_tier(_p(p), N, _p(c), P, float(radius), int(num_points), int(smem_keys),
+                                             int(overflow_stride), _p(idx), _p(cnt), _p(ws), ws.numel(), _stream()),
+                   "d3d_radius_patches_tier")
     _count()
     return idx, cnt
+
+
+def radius_neighbors(points, centres, radius, num_points):
+    """radius_patches with the candidate storage sized from the data: a probe over 64 centres picks the tier (2048 keys in
+    shared memory, 12288, or global scratch); a ball that still overflows re-runs the call one tier up."""
+    P = centres.shape[0]
+    probe = centres[:: max(P // 64, 1)][:64].contiguous()
+    cmax = int(radius_patches(points, probe, radius, 1)[1].max()) if probe.shape[0] else 0
+    tiers = [2048, 12288]
+    k = 0 if 2 * cmax <= tiers[0] else 1
+    while True:
+        if k < len(tiers):
+            idx, cnt = radius_patches(points, centres, radius, num_points, smem_keys=tiers[k])
+            limit = tiers[k]
+        else:
+            stride = 1 << max(int(cmax - 1).bit_length(), 14)
+            idx, cnt = radius_patches(points, centres, radius, num_points, overflow_stride=stride)
+            limit = stride
+        cmax = int(cnt.max()) if cnt.numel() else 0
+        if cmax <= limit:
+            return idx, cnt
+        k += 1
 
 
 def vote_mean(pred, rowptr, entries, n_points, num_points):

@@ -301,6 +301,12 @@ int d3d_voxel_barycentres(const float* points, const int* rowptr, const int* ent
 size_t d3d_radius_patches_workspace_bytes(int N, int P, int overflow_stride);
 int d3d_radius_patches(const float* points, int N, const float* centres, int P, float radius, int num_points,
                        int overflow_stride, int* out_idx, int* out_count, void* ws, size_t ws_bytes, void* stream);
+/* The same with the shared-memory candidate capacity chosen by the caller: 12288 (the default above: one block per SM)
+ * or a smaller power of two >= 256 when the balls are small (2048 keys: six blocks per SM).  A block that asks for few
+ * results out of many candidates (num_points * 4 < count) selects them with a distance histogram before sorting. */
+int d3d_radius_patches_tier(const float* points, int N, const float* centres, int P, float radius, int num_points,
+                            int smem_keys, int overflow_stride, int* out_idx, int* out_count, void* ws, size_t ws_bytes,
+                            void* stream);
 /* per-point mean of the predictions that voted for it: pred (P, 3, num_points), inverse map of the (flattened,
  * 128-slot rows) patch indices; mean_offset (N, 3) = sum / (count + 1e-7); votes (N) may be NULL. */
 int d3d_vote_mean(const float* pred, const int* rowptr, const int* entries, int N, int num_points, float* mean_offset,

@@ -34,11 +34,7 @@ def list_specs():
 
 
 def radius_lists(support, query, radius, cap):
-    idx, cnt = ops.radius_patches(support, query, radius, cap)
-    cmax = int(cnt.max()) if cnt.numel() else 0
-    if cmax > 12288:  # candidate list larger than the shared-memory sort: global scratch (see patches.cu)
-        idx, cnt = ops.radius_patches(support, query, radius, cap, overflow_stride=1 << int(np.ceil(np.log2(cmax))))
-    return idx, cnt
+    return ops.radius_neighbors(support, query, radius, cap)  # candidate storage tier chosen from the data
 
 
 def gpu_pyramid(pts):
