@@ -105,10 +105,12 @@ class ResNet(nn.Module):
             # pyramid is long finished by the time the last stage has run.
             _neighbors.join()
 
-    def prefetch_neighbors(self, xyz, mask):
-        """Builds the pyramid of the NEXT batch now, on the side stream (call it between this step's forward and its
-        backward): the next forward on these very tensors adopts it instead of building its own (neighbors.prefetch)."""
-        _neighbors.prefetch(xyz, mask, self._radius0, self._nsample0, self._stages, True, self._with_order)
+    def prefetch_neighbors(self, xyz, mask, with_csr=None):
+        """Builds the pyramid of the NEXT batch now, on the side stream (training: call it between this step's forward and
+        its backward; inference: before this batch's forward): the next forward on these very tensors adopts it instead
+        of building its own (neighbors.prefetch).  with_csr: also the inverse maps backward needs (default: grad mode)."""
+        with_csr = torch.is_grad_enabled() if with_csr is None else with_csr
+        _neighbors.prefetch(xyz, mask, self._radius0, self._nsample0, self._stages, with_csr, self._with_order)
 
     def _forward(self, xyz, mask, features, end_points):
         features = self.conv1(features)

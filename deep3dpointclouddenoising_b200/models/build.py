@@ -26,10 +26,10 @@ class OffsetRegressionModel(nn.Module):
     def forward(self, xyz, mask, features):
         return self.segmentation_head(self.backbone(xyz, mask, features))
 
-    def prefetch_neighbors(self, xyz, mask):
+    def prefetch_neighbors(self, xyz, mask, with_csr=None):
         """Training loops call this between forward and backward with the NEXT batch's (xyz, mask): its neighbourhood
         pyramid is built on a side stream while backward runs, and the next forward on those tensors adopts it."""
-        self.backbone.prefetch_neighbors(xyz, mask)
+        self.backbone.prefetch_neighbors(xyz, mask, with_csr)
 
     def init_weights(self):
         for m in self.modules():

@@ -225,8 +225,7 @@ def prebuild(xyz, mask, radius, nsample0, stages, with_csr, with_order=True):
                 if with_order:
                     spatial_order(sx)
                     lists[-1].tile_plan(sx, sm)
-                    if with_csr:  # the strided list's plan serves the scatter-form backward only
-                        lists[-2].tile_plan(sx, sm)
+                    lists[-2].tile_plan(sx, sm)  # strided list: the scatter-form backward, and the forward on coarse levels
                 levels.append((sx, sm))
             ups = [nearest_neighbors(levels[k - 1][0], levels[k][0], levels[k - 1][1], levels[k][1])
                    for k in range(len(levels) - 1, 0, -1)]
