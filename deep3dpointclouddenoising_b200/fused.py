@@ -124,7 +124,8 @@ class PosPoolFunction(Function):
         nbr = ctx.nbr
         g_cl = _rows(grad_out)
         # 'scatter': the forward tile transposed on the tensor cores, float atomics across tiles (faster at every level, also
-        # for strided lists where the forward tiles are not); False: segmented reduction over the inverse map
+        # for strided lists where the forward tiles are not); 'ordered': the same tiles + a fixed-order second pass (no float
+        # atomics, bit-reproducible); False: segmented reduction over the inverse map
         mode = runtime.staged_tiles_backward
         plan = (nbr.tile_plan(query_xyz, query_mask)
                 if mode in ('scatter', 'ordered') and ctx.reduction != 'sum' and nbr.by_support is not None else None)

@@ -8,12 +8,16 @@ NeighborList is built once per combination and carries everything the fused kern
     idx, idx_mask   (B, M, ns) int32      what _ext.masked_ordered_ball_query returns
     nvalid          (B, M)     int32      in-radius count per query (replaces the dense mask in-kernel)
     rowptr, entries                      inverse map (CSR by support), built lazily for backward
+    by_support      (B, M, ns) int32      the winners in ascending support index, (distance rank << 16) | index
+    tile plan       uint8 buffer          per tile of 128 Morton-adjacent queries: union of the gathered support rows, the
+                                          rank of every list entry in it, and the inverse view (staged-tile PosPool kernels)
 
 `prebuild` enqueues the whole pyramid of one forward (subsamplings, ball queries, upsampling queries, inverse maps) on a
 SIDE stream: these are small-grid, latency-bound integer kernels (2.4 ms back to back for a 16 x 8192 batch) that depend
 on coordinates only, so they overlap with the convolutions / BatchNorm / aggregations of the main stream.  Every cached
 item carries the CUDA event recorded after its build; the first consumer on another stream waits for it (inside a CUDA
-graph capture this becomes a fork / join of two branches).
+graph capture this becomes a fork / join of two branches).  `prefetch` / `adopt` / `fold_pending_into_current` move the
+build of the NEXT batch's pyramid into the current step (one-step pipeline, see the section at the end of the file).
 """
 import torch
 
