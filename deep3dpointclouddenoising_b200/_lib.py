@@ -62,6 +62,10 @@ SIGNATURES = {
     "d3d_bn_act_fwd": (_i, [_vp] * 6 + [_i, _i, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "d3d_bn_act_bwd": (_i, [_vp] * 7 + [_i] * 5 + [_vp] * 5 + [_sz, _vp]),
     "d3d_bn_act_cl_fwd": (_i, [_vp] * 7 + [_ll, _i, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "d3d_linear_small_k": (_i, [_vp, _vp, _ll, _ll, _vp, _ll, _i, _i, _vp, _vp]),
+    "d3d_linear_small_n": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp]),
+    "d3d_wgrad_small_workspace_bytes": (_sz, [_i]),
+    "d3d_wgrad_small": (_i, [_vp, _vp, _ll, _i, _i, _vp, _ll, _ll, _i, _vp, _sz, _vp]),
     "d3d_gemm_row_tiles": (_i, [_ll]),
     "d3d_gemm_tf32": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp]),
     "d3d_wgrad_workspace_bytes": (_sz, [_ll, _i, _i]),

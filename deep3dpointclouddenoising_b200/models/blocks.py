@@ -132,6 +132,11 @@ class PointwiseConvRows(Function):
         ctx.has_bias = bias is not None
         ctx.wparam = weight  # the Parameter: its .grad buffer is written in place under runtime.grads_in_place
         ctx.set_materialize_grads(False)  # no zero tensor for the (non-differentiable) statistics output
+        ctx.small = (ops.small_linear_kind(w.shape[1], w.shape[0], rows, w, bias)
+                     if runtime.own_gemm and runtime.own_small_linear and rows.is_contiguous() and w.is_contiguous() else None)
+        if ctx.small:  # 3-channel input / output layers: streaming kernels on the CUDA cores (csrc/linear_small.cu)
+            y = ops.linear_small(rows.reshape(-1, rows.shape[-1]), w, bias).view(*rows.shape[:-1], w.shape[0])
+            return (y, None) if want_stats else y
         if bias is None and _own_gemm(w.shape[1], 0, w.shape[0], rows, w) and rows.is_contiguous():
             out = ops.gemm_tf32(rows, w, want_stats=want_stats)
             if want_stats:
@@ -148,6 +153,24 @@ class PointwiseConvRows(Function):
             return None, None, None, None
         g2 = grad.contiguous().view(-1, grad.shape[-1])
         d_rows = d_w = d_b = None
+        if ctx.small:
+            x2 = rows.reshape(-1, rows.shape[-1])
+            N, K = w.shape
+            if ctx.needs_input_grad[0]:
+                if ctx.small == 'n':  # dx = dy (R, N <= 4) . W (N, K): the small-K kernel over a strided view of W
+                    d_rows = ops.linear_small(g2, w, None, w_strides=(K, 1, K)).view_as(rows)
+                else:                 # dx (R, K <= 4) = dy (R, N) . W: the small-N kernel with W^T (K, N)
+                    d_rows = ops.linear_small(g2, w.t().contiguous(), None).view_as(rows)
+            if ctx.needs_input_grad[1]:
+                into = ctx.wparam.grad.view(w.shape) if runtime.grads_in_place and _is_grad_buffer(ctx.wparam) else None
+                if ctx.small == 'n':
+                    d_w = ops.wgrad_small(x2, g2, (N, K), True, into=into)
+                else:
+                    d_w = ops.wgrad_small(g2, x2, (N, K), False, into=into)
+                d_w = d_w.unsqueeze(-1) if d_w is not None else None
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                d_b = g2.sum(0)
+            return d_rows, d_w, d_b, None
         if ctx.needs_input_grad[0] and _own_gemm(w.shape[0], 0, w.shape[1], g2, w):
             d_rows = ops.gemm_tf32(g2, _transposed(w)).view_as(rows)
         with _conv_math():

@@ -516,6 +516,57 @@ def wgrad_tf32(dy_rows, x_rows, into=None):
     return out
 
 
+def small_linear_kind(K, N, *tensors):
+    """'k' / 'n' when a (R, K) x (N, K)^T product has a tiny side the skinny kernels take (csrc/linear_small.cu), else None."""
+    if not all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in tensors):
+        return None
+    if K <= 4 and N % 4 == 0 and N <= 1024:
+        return 'k'
+    if N <= 4 and K % 4 == 0 and K <= 1024:
+        return 'n'
+    return None
+
+
+def linear_small(x_rows, w, bias=None, w_strides=None):
+    """y (R, N) = x (R, K) . w^T (+ bias), fp32 on the CUDA cores, for K <= 4 (N % 4 == 0; w_strides = (N, stride_n, stride_k)
+    reads w[n, k] at w.data_ptr + n * stride_n + k * stride_k: a transposed view without a copy) or N <= 4 (K % 4 == 0)."""
+    L = _lib.load()
+    x = _f32(x_rows, "x")
+    R, K = x.shape
+    if w_strides is None:
+        N = w.shape[0]
+        sn, sk = w.stride(0), w.stride(1)
+    else:
+        N, sn, sk = w_strides
+    with torch.cuda.device(x.device):
+        y = torch.empty((R, N), dtype=torch.float32, device=x.device)
+        if K <= 4 and N % 4 == 0:
+            _lib.check(L.d3d_linear_small_k(_p(x), _p(w), int(sn), int(sk), _p(bias), R, K, N, _p(y), _stream()),
+                       "d3d_linear_small_k")
+        else:
+            wc = _f32(w, "w")
+            _lib.check(L.d3d_linear_small_n(_p(x), _p(wc), _p(bias), R, K, N, _p(y), _stream()), "d3d_linear_small_n")
+    _count()
+    return y
+
+
+def wgrad_small(big_rows, small_rows, out_shape, transposed, into=None):
+    """sum_r big[r, n] * small[r, k] as an (Nb, Ks) matrix — or its transpose (Ks, Nb) when `transposed` — written to a
+    new tensor or ADDED to `into` (the parameter's gradient buffer).  Fixed summation order."""
+    L = _lib.load()
+    big, small = _f32(big_rows, "big"), _f32(small_rows, "small")
+    R, Nb = big.shape
+    Ks = small.shape[1]
+    with torch.cuda.device(big.device):
+        out = into if into is not None else torch.empty(out_shape, dtype=torch.float32, device=big.device)
+        sn, sk = (1, Nb) if transposed else (Ks, 1)
+        ws = _ws(L.d3d_wgrad_small_workspace_bytes(Nb), big.device)
+        _lib.check(L.d3d_wgrad_small(_p(big), _p(small), R, Nb, Ks, _p(out), sn, sk, 1 if into is not None else 0, _p(ws),
+                                     ws.numel(), _stream()), "d3d_wgrad_small")
+    _count()
+    return None if into is not None else out
+
+
 def gemm_ok(K0, K1, N, *tensors):
     return K0 % 4 == 0 and K1 % 4 == 0 and N % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in tensors)
 

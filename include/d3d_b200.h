@@ -175,6 +175,21 @@ int d3d_pospool_scatter_bwd(const float* grad_out_cl, const float* query_xyz, co
                             const void* plan, int B, int M, int N, int C, int nsample, float radius, int reduction,
                             float* grad_feat_cl, void* ws, size_t ws_bytes, void* stream);
 
+/* 1x1 convolutions with a tiny channel count on one side (the U-Net's 3-channel input layer and its 3-channel output
+ * layer; TMA needs 16-byte rows, so d3d_gemm_tf32 does not take them), fp32 on the CUDA cores, row-major operands:
+ *   d3d_linear_small_k: y[R x N] = x[R x K] . w^T (+ bias), K <= 4, N % 4 == 0; w[n, k] = w[n * w_stride_n + k * w_stride_k]
+ *     (strided: the same kernel is the data gradient of the output layer, dx = dy[R x 3] . W[3 x K])
+ *   d3d_linear_small_n: y[R x N] = x[R x K] . w[N x K]^T (+ bias), N <= 4, K % 4 == 0
+ *   d3d_wgrad_small:    out[n * out_stride_n + k * out_stride_k] (+)= sum_r big[r, n] * small[r, k], big (R, Nb), Nb % 4 == 0,
+ *     small (R, Ks), Ks <= 4: the weight gradients of both layers; row-range partials + a fixed-order second pass.
+ *   replaces ref: models/backbones/resnet.py:100-103 (conv1), heads/multi_dimensional_head.py:45-50 (last Conv1d) */
+int d3d_linear_small_k(const float* x, const float* w, long long w_stride_n, long long w_stride_k, const float* bias,
+                       long long R, int K, int N, float* y, void* stream);
+int d3d_linear_small_n(const float* x, const float* w, const float* bias, long long R, int K, int N, float* y, void* stream);
+size_t d3d_wgrad_small_workspace_bytes(int Nb);
+int d3d_wgrad_small(const float* big, const float* small, long long R, int Nb, int Ks, float* out, long long out_stride_n,
+                    long long out_stride_k, int accumulate, void* ws, size_t ws_bytes, void* stream);
+
 #define D3D_KP_CONSTANT 0
 #define D3D_KP_LINEAR   1
 #define D3D_KP_GAUSSIAN 2

@@ -130,3 +130,34 @@ def test_weight_gradient_gemm(cuda_device, R, cout, cin):
     acc = base.clone()
     ops.wgrad_tf32(dy, x, into=acc)
     assert ((acc.double() - base.double() - ref).abs() / (1 + scale)).max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("R,K,N,bias", [(4099, 3, 72, False), (131072, 3, 72, False), (4099, 144, 3, True), (131072, 72, 3, True),
+                                        (257, 4, 8, True), (257, 8, 4, False), (5, 1, 4, False)])
+def test_skinny_layers_against_torch(cuda_device, R, K, N, bias):
+    """The 3-channel input / output convolutions (csrc/linear_small.cu): forward, data gradient and weight gradient through
+    the row-major convolution Function, against torch in float64."""
+    from deep3dpointclouddenoising_b200 import ops
+    from deep3dpointclouddenoising_b200.models import blocks
+    torch.manual_seed(R + K)
+    x = torch.randn(1, R, K, device=cuda_device, requires_grad=True)
+    w = torch.randn(N, K, 1, device=cuda_device, requires_grad=True)
+    b = torch.randn(N, device=cuda_device, requires_grad=True) if bias else None
+    assert ops.small_linear_kind(K, N, x, w, b) in ("k", "n")
+    y = blocks.PointwiseConvRows.apply(x, w, b)
+    g = torch.randn_like(y)
+    grads = torch.autograd.grad(y, [x, w] + ([b] if bias else []), g)
+    xd, wd = x.detach().double(), w.detach().double().squeeze(-1)
+    ref = xd @ wd.t() + (b.detach().double() if bias else 0)
+    torch.testing.assert_close(y.detach().double(), ref, rtol=1e-5, atol=1e-5)
+    gd = g.double()
+    torch.testing.assert_close(grads[0].double(), gd @ wd, rtol=1e-5, atol=1e-5)
+    ref_w = (gd.view(-1, N).t() @ xd.view(-1, K)).unsqueeze(-1)
+    torch.testing.assert_close(grads[1].double(), ref_w, rtol=1e-4, atol=1e-4 * float(ref_w.abs().max()))
+    if bias:
+        torch.testing.assert_close(grads[2].double(), gd.view(-1, N).sum(0), rtol=1e-4, atol=1e-3)
+    # in-place accumulation into a gradient buffer (runtime.grads_in_place path)
+    buf = torch.ones(N, K, device=cuda_device)
+    big, small = (g.view(-1, N), x.detach().view(-1, K)) if K <= 4 else (x.detach().view(-1, K), g.view(-1, N))
+    assert ops.wgrad_small(big, small, (N, K), K > 4, into=buf) is None
+    torch.testing.assert_close(buf.double(), ref_w.squeeze(-1) + 1, rtol=1e-4, atol=1e-4 * float(ref_w.abs().max()))
