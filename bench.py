@@ -392,6 +392,7 @@ def run_extras(args, dev, batch):
     except Exception as e:  # never lose the headline line to an extra
         extra["reference_gpu"] = {"error": f"{type(e).__name__}: {e}"}
     sys.path.insert(0, os.path.join(ROOT, "tools"))
+    torch.cuda.empty_cache()  # the training bench leaves several GB cached in its own block sizes
     try:
         import pyramid_100k
         extra["config1_pyramid_100k"] = pyramid_100k.run(dev, n_rep=5, cpu=True, single_thread=False)
