@@ -114,6 +114,14 @@ runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "c
                     "deterministic_scatter": False, "own_small_linear": True})
 
 
+def set_deterministic(on=True):
+    """Bit-reproducible training steps: every float reduction in a fixed order — PosPool backward as tensor-core tiles with
+    the ordered second pass, _ext.group_points_grad over the inverse map.  The defaults use float atomics in those two
+    places (like the reference's own backward) and are ~4 % faster."""
+    runtime.staged_tiles_backward = 'ordered' if on else 'scatter'
+    runtime.deterministic_scatter = bool(on)
+
+
 def reset_config():
     """Back to the defaults (the reference has no such call; tests need it because `config` is global)."""
     config.clear()

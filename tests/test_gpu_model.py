@@ -70,3 +70,23 @@ def test_one_adam_step_reduces_l1_on_fixed_batch(cuda_device):
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0]
+
+
+def test_deterministic_mode_gives_identical_training_steps(cuda_device):
+    """utils.config.set_deterministic(): two runs of the same training step produce the same bits (loss and every gradient)."""
+    from deep3dpointclouddenoising_b200.utils.config import runtime, set_deterministic
+    old = (runtime.staged_tiles_backward, runtime.deterministic_scatter)
+    set_deterministic(True)
+    try:
+        model, criterion = _build("pospool", 2048, cuda_device)
+        pts, mask, feats, offs = [torch.from_numpy(a).to(cuda_device) for a in synthetic.make_batch(8, 2, 2048, ragged=True)]
+        runs = []
+        for _ in range(2):
+            model.zero_grad(set_to_none=True)
+            loss = criterion(model(pts, mask, feats).transpose(1, 2), offs, mask)
+            loss.backward()
+            runs.append((loss.item(), [p.grad.clone() for p in model.parameters()]))
+        assert runs[0][0] == runs[1][0]
+        assert all(torch.equal(a, b) for a, b in zip(runs[0][1], runs[1][1]))
+    finally:
+        runtime.staged_tiles_backward, runtime.deterministic_scatter = old
