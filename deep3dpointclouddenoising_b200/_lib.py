@@ -68,6 +68,7 @@ SIGNATURES = {
     "d3d_wgrad_small": (_i, [_vp, _vp, _ll, _i, _i, _vp, _ll, _ll, _i, _vp, _sz, _vp]),
     "d3d_gemm_row_tiles": (_i, [_ll]),
     "d3d_gemm_tf32": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp]),
+    "d3d_gemm_tf32_act": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "d3d_wgrad_workspace_bytes": (_sz, [_ll, _i, _i]),
     "d3d_wgrad_tf32": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp, _sz, _vp]),
     "d3d_bn_finalize": (_i, [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -100,6 +100,10 @@ struct GemmArgs {
   int bn;            // column tile: multiple of 16, <= kBNMax
   int accumulate;    // C += instead of C =
   int tiles_m, tiles_n;
+  // inference epilogue (eval-mode BatchNorm folded into the convolution): C = act(acc + bias[col] + residual[row, col])
+  const float* bias;      // (N) or null
+  const float* residual;  // (M, N) row-major like C, or null
+  int relu;
 };
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
@@ -210,6 +214,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       if (slot < rows_per_pass) {
         const float4 shift = *reinterpret_cast<const float4*>(sC + 4 * c4);  // row 0 of the tile: common shift of the sums
         float* cbase = g.C + (long long)m0 * g.N + n0 + 4 * c4;
+        const float4 bias4 = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* rbase = g.residual ? g.residual + (long long)m0 * g.N + n0 + 4 * c4 : nullptr;
         const float* sbase = sC + 4 * c4;
         for (int rr = slot; rr < rows_valid; rr += 4 * rows_per_pass) {
           float4 o[4];
@@ -226,6 +232,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 const float4 old = *reinterpret_cast<const float4*>(dst);
                 w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
               }
+              if (g.bias) { w.x += bias4.x; w.y += bias4.y; w.z += bias4.z; w.w += bias4.w; }
+              if (rbase) {
+                const float4 rs = __ldg(reinterpret_cast<const float4*>(rbase + (long long)row * g.N));
+                w.x += rs.x; w.y += rs.y; w.z += rs.z; w.w += rs.w;
+              }
+              if (g.relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
               *reinterpret_cast<float4*>(dst) = w;
               const float dx = o[u].x - shift.x, dy = o[u].y - shift.y, dz = o[u].z - shift.z, dw = o[u].w - shift.w;
               s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
@@ -529,6 +541,10 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" {
 
+int d3d_gemm_tf32_act(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1,
+                      int accumulate, float* stats, const float* bias, const float* residual, int relu, void* stream);
+
+
 int d3d_gemm_row_tiles(long long M) { return (int)((M + kBM - 1) / kBM); }
 
 /* C[M x N] (+)= [A0 | A1] . B^T ;  A0 (M x K0), A1 (M x K1) or NULL, B (N x (K0 + K1)), all row-major fp32, TF32 tensor cores.
@@ -536,11 +552,21 @@ int d3d_gemm_row_tiles(long long M) { return (int)((M + kBM - 1) / kBM); }
  * Requires K0 % 4 == 0, K1 % 4 == 0, N % 4 == 0 and 16-byte aligned pointers (TMA). */
 int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1, int accumulate,
                   float* stats, void* stream) {
+  return d3d_gemm_tf32_act(A0, A1, B, C, M, N, K0, K1, accumulate, stats, nullptr, nullptr, 0, stream);
+}
+
+/* The same GEMM with the inference epilogue C = act(A . B^T + bias[col] + residual[row, col]): a convolution whose
+ * eval-mode BatchNorm has been folded into its weights (B scaled per output channel, bias = the BatchNorm shift), the
+ * bottleneck's residual add and the ReLU ride on the store.  bias (N), residual (M, N) may be NULL. */
+int d3d_gemm_tf32_act(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1,
+                      int accumulate, float* stats, const float* bias, const float* residual, int relu, void* stream) {
   D3D_REQUIRE(A0 && B && C && M > 0 && N > 0 && K0 > 0 && K1 >= 0 && (K1 == 0 || A1));
   if (K0 % 4 || K1 % 4 || N % 4 || !aligned16(A0) || !aligned16(A1) || !aligned16(B) || !aligned16(C)) return D3D_ERR_UNSUPPORTED;
-  if (stats && accumulate) return D3D_ERR_BAD_ARG;
+  if (!aligned16(bias) || !aligned16(residual)) return D3D_ERR_UNSUPPORTED;
+  if (stats && (accumulate || bias || residual || relu)) return D3D_ERR_BAD_ARG;
   GemmArgs g{};
   g.C = C; g.stats = stats; g.M = (int)M; g.N = N; g.K0 = K0; g.K1 = K1; g.accumulate = accumulate;
+  g.bias = bias; g.residual = residual; g.relu = relu;
   if (M > 0x7fffffffLL) return D3D_ERR_UNSUPPORTED;
   const int n16 = (N + 15) & ~15;
   g.bn = n16 < kBNMax ? n16 : kBNMax;

@@ -265,9 +265,52 @@ class FusedSequential(nn.Sequential):
             return (use_fused and isinstance(nxt, nn.BatchNorm1d) and (nxt.training or nxt.running_mean is None)
                     and nxt.momentum is not None)
 
+        def folded_eval(k):
+            """Inference: the convolution at position k is followed by a BatchNorm in eval mode — returns (weights scaled
+            per output channel, shift, relu after it?, is it the block's last?) so that conv + BN (+ residual) (+ ReLU) run
+            as ONE GEMM with the epilogue of d3d_gemm_tf32_act; None otherwise.  The folded weights are cached per block
+            and recomputed when a parameter or running statistic changes."""
+            nxt = mods[k + 1] if k + 1 < len(mods) else None
+            conv = mods[k]
+            if not (use_fused and runtime.channel_last and runtime.own_gemm and runtime.fold_eval_batchnorm
+                    and not torch.is_grad_enabled() and isinstance(nxt, nn.BatchNorm1d) and not nxt.training
+                    and nxt.running_mean is not None and torch.backends.cudnn.allow_tf32):
+                return None
+            w = conv.weight.squeeze(-1)
+            if not ops.gemm_ok(w.shape[1], 0, w.shape[0], w):
+                return None
+            srcs = [t for t in (conv.weight, conv.bias, nxt.weight, nxt.bias, nxt.running_mean, nxt.running_var) if t is not None]
+            key = tuple((t.data_ptr(), t._version) for t in srcs)
+            cache = self.__dict__.setdefault("_folded", {})
+            hit = cache.get(k)
+            if hit is None or hit[0] != key:
+                scale = torch.rsqrt(nxt.running_var + nxt.eps)
+                if nxt.weight is not None:
+                    scale = scale * nxt.weight
+                shift = -nxt.running_mean * scale
+                if nxt.bias is not None:
+                    shift = shift + nxt.bias
+                if conv.bias is not None:
+                    shift = shift + conv.bias * scale
+                hit = cache[k] = (key, (w * scale[:, None]).contiguous(), shift.contiguous())
+            relu_next = k + 2 < len(mods) and isinstance(mods[k + 2], nn.ReLU)
+            return hit[1], hit[2], relu_next, k + (3 if relu_next else 2) == len(mods)
+
         stats = None  # tile statistics of x from the GEMM that produced it (consumed by the BatchNorm right after)
         if parts is not None:
-            if on_gpu and runtime.channel_last and _is_pointwise(mods[0]) and all(is_channel_last(t) for t in parts):
+            fold = folded_eval(0) if (on_gpu and len(parts) == 2 and _is_pointwise(mods[0])
+                                      and all(is_channel_last(t) for t in parts)) else None
+            if fold is not None and fold[3] and residual is not None and not is_channel_last(residual):
+                fold = None
+            if fold is not None and all(t.shape[1] % 4 == 0 for t in parts):
+                w2, shift, relu_next, is_last = fold
+                res = rows_of(residual) if (is_last and residual is not None) else None
+                x = ops.gemm_tf32(rows_of(parts[0]), w2, a1=rows_of(parts[1]), bias=shift, residual=res,
+                                  relu=relu_next or (is_last and final_relu)).permute(0, 2, 1)
+                if is_last:
+                    residual, final_relu = None, False
+                mods = mods[(3 if relu_next else 2):]
+            elif on_gpu and runtime.channel_last and _is_pointwise(mods[0]) and all(is_channel_last(t) for t in parts):
                 want = feeds_training_bn(0)
                 x = PointwiseConvCatRows.apply(mods[0].weight, mods[0].bias, want, *[t.permute(0, 2, 1) for t in parts])
                 if want:
@@ -291,6 +334,18 @@ class FusedSequential(nn.Sequential):
                 i += 2 if next_is_relu else 1
                 continue
             stats = None
+            fold = folded_eval(i) if (use_rows and _is_pointwise(m) and is_channel_last(x)) else None
+            if fold is not None:
+                w2, shift, relu_next, is_last = fold
+                want_res = is_last and residual is not None
+                if not want_res or (is_channel_last(residual) and residual.shape == (x.shape[0], w2.shape[0], x.shape[2])):
+                    res = rows_of(residual) if want_res else None
+                    x = ops.gemm_tf32(rows_of(x), w2, bias=shift, residual=res,
+                                      relu=relu_next or (is_last and final_relu)).permute(0, 2, 1)
+                    if is_last:
+                        residual, final_relu = None, False
+                    i += 3 if relu_next else 2
+                    continue
             if use_rows and _is_pointwise(m):
                 want = feeds_training_bn(i)
                 x = PointwiseConvRows.apply(rows_of(x), m.weight, m.bias, want)

