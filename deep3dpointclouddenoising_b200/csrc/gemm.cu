@@ -113,6 +113,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 // Persistent: one CTA per SM walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The three roles run
 // decoupled — the producer streams stages of whatever tile comes next, the MMA thread fills one of TWO TMEM accumulators
 // while the epilogue warps drain the other — so loads, tensor-core work and stores of consecutive tiles overlap.
+template <bool kAct>  // kAct: the inference epilogue (bias / residual / ReLU) — compiled out of the training kernel
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
@@ -214,8 +215,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       if (slot < rows_per_pass) {
         const float4 shift = *reinterpret_cast<const float4*>(sC + 4 * c4);  // row 0 of the tile: common shift of the sums
         float* cbase = g.C + (long long)m0 * g.N + n0 + 4 * c4;
-        const float4 bias4 = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* rbase = g.residual ? g.residual + (long long)m0 * g.N + n0 + 4 * c4 : nullptr;
+        const float4 bias4 = (kAct && g.bias) ? __ldg(reinterpret_cast<const float4*>(g.bias + n0 + 4 * c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* rbase = (kAct && g.residual) ? g.residual + (long long)m0 * g.N + n0 + 4 * c4 : nullptr;
         const float* sbase = sC + 4 * c4;
         for (int rr = slot; rr < rows_valid; rr += 4 * rows_per_pass) {
           float4 o[4];
@@ -232,12 +233,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                 const float4 old = *reinterpret_cast<const float4*>(dst);
                 w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
               }
-              if (g.bias) { w.x += bias4.x; w.y += bias4.y; w.z += bias4.z; w.w += bias4.w; }
-              if (rbase) {
+              if (kAct && g.bias) { w.x += bias4.x; w.y += bias4.y; w.z += bias4.z; w.w += bias4.w; }
+              if (kAct && rbase) {
                 const float4 rs = __ldg(reinterpret_cast<const float4*>(rbase + (long long)row * g.N));
                 w.x += rs.x; w.y += rs.y; w.z += rs.z; w.w += rs.w;
               }
-              if (g.relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
+              if (kAct && g.relu) { w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f); }
               *reinterpret_cast<float4*>(dst) = w;
               const float dx = o[u].x - shift.x, dy = o[u].y - shift.y, dz = o[u].z - shift.z, dw = o[u].w - shift.w;
               s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
@@ -583,7 +584,8 @@ int d3d_gemm_tf32_act(const float* A0, const float* A1, const float* B, float* C
   const size_t smem = (size_t)kStages * kStageBytes + (size_t)kBM * kCStride * 4 + (size_t)kMaxSlots * 2 * kBNMax * 4 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
@@ -596,7 +598,8 @@ int d3d_gemm_tf32_act(const float* A0, const float* A1, const float* B, float* C
   }
   const long long n_tiles = (long long)g.tiles_m * g.tiles_n;
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
-  gemm_tf32_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma0, ma1, mb, g);
+  if (bias || residual || relu) gemm_tf32_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma0, ma1, mb, g);
+  else gemm_tf32_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma0, ma1, mb, g);
   d3d_note_launches(1);
   return d3d_launch_status();
 }
