@@ -19,6 +19,7 @@ plan = ops.tile_plan(bys, nv, mask, order, N)
 gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
 rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
 ybn, mean, invstd = ops.bn_act_cl_fwd(f, None, gam, bet, rm, rv, 1e-5, 0.1, True, True)
+gbn = torch.randn_like(f)
 torch.cuda.synchronize()
 for _ in range(n):
     if op == "ball_query": ops.ball_query(pts, pts, mask, mask, 0.025, 52)
@@ -28,7 +29,7 @@ for _ in range(n):
     elif op == "pospool_tiles_fwd": ops.pospool_fwd(f, pts, pts, idx, nv, mask, 0.025, 'avg', query_order=order, idx_by_support=bys, plan=plan)
     elif op == "pospool_scatter_bwd": ops.pospool_bwd(f, pts, pts, None, None, nv, mask, N, 52, 0.025, 'avg', query_order=order, idx_by_support=bys, plan=plan)
     elif op == "tile_plan": ops.tile_plan(bys, nv, mask, order, N)
-    elif op == "bn_bwd": ops.bn_act_cl_bwd(f, f, ybn, gam, bet, mean, invstd, True, 1, False)
+    elif op == "bn_bwd": ops.bn_act_cl_bwd(gbn, f, ybn, gam, bet, mean, invstd, True, 1, False)
     elif op == "bn_fwd": ops.bn_act_cl_fwd(f, None, gam, bet, rm, rv, 1e-5, 0.1, True, True)
     elif op == "gemm": ops.gemm_tf32(f.view(-1, C), wg)
     elif op == "gemm_stats": ops.gemm_tf32(f.view(-1, C), wg, want_stats=True)
