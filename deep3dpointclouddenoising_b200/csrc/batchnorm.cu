@@ -619,6 +619,26 @@ bn_bwd_reduce_cl_kernel(const float* __restrict__ dy, const float* __restrict__ 
   }
 }
 
+
+// L2 residency hints for the two-kernel backward: the reduction pass asks the L2 to KEEP what it reads (evict_last), the
+// apply pass reads the same rows a few microseconds later and marks them evict_first (their last use).
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_drop() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* ptr, unsigned long long policy) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(policy));
+  return v;
+}
+
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
@@ -639,12 +659,13 @@ bn_bwd_apply_cl_kernel(const float* __restrict__ dy, const float* __restrict__ x
     k2 = make_float4(sa.y * inv_count * is.x, sa.w * inv_count * is.y, sb.y * inv_count * is.z, sb.w * inv_count * is.w);
   }
   float4 xv[kApplyRows], dv[kApplyRows];
+  const unsigned long long drop = l2_policy_drop();
 #pragma unroll
   for (int k = 0; k < kApplyRows; ++k)
     if (row0 + k < R) {
       const long long e = (row0 + k) * c4 + group;
-      xv[k] = __ldg(reinterpret_cast<const float4*>(x) + e);
-      dv[k] = __ldg(reinterpret_cast<const float4*>(dy) + e);
+      xv[k] = ldg_hint(reinterpret_cast<const float4*>(x) + e, drop);
+      dv[k] = ldg_hint(reinterpret_cast<const float4*>(dy) + e, drop);
     }
 #pragma unroll
   for (int k = 0; k < kApplyRows; ++k)
@@ -691,14 +712,15 @@ bn_bwd_partial_cl_kernel(const float* __restrict__ dy, const float* __restrict__
   float4 s1 = make_float4(0, 0, 0, 0), s2 = s1;
   const float4* dy4 = reinterpret_cast<const float4*>(dy);
   const float4* x4 = reinterpret_cast<const float4*>(x);
+  const unsigned long long keep = l2_policy_keep();
   for (long long r = row_beg + rl; r < row_end; r += 4LL * lanes) {  // 8 independent loads in flight; predicated tail
     float4 dv[4], xv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (r + (long long)j * lanes < row_end) {
         const long long e = (r + (long long)j * lanes) * c4 + group;
-        dv[j] = __ldg(dy4 + e);
-        xv[j] = __ldg(x4 + e);
+        dv[j] = ldg_hint(dy4 + e, keep);
+        xv[j] = ldg_hint(x4 + e, keep);
       }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
