@@ -52,3 +52,18 @@ def test_hand_over_enumerates_every_tensor_of_an_item():
     sub = neighbors._Subsampled(torch.zeros(1, 2, 3), torch.ones(1, 2, dtype=torch.int32), ())
     assert len(neighbors._tensors(sub)) == 2
     assert neighbors._tensors(neighbors._Order(torch.zeros(1, 4, dtype=torch.int32), ())) [0].shape == (1, 4)
+
+
+def test_runtime_switch_helpers():
+    from deep3dpointclouddenoising_b200.utils.config import runtime, set_deterministic
+    old = (runtime.staged_tiles_backward, runtime.deterministic_scatter)
+    try:
+        set_deterministic(True)
+        assert runtime.staged_tiles_backward == 'ordered' and runtime.deterministic_scatter is True
+        set_deterministic(False)
+        assert runtime.staged_tiles_backward == 'scatter' and runtime.deterministic_scatter is False
+    finally:
+        runtime.staged_tiles_backward, runtime.deterministic_scatter = old
+    # the skinny-layer kernels only take CUDA fp32 tensors: anything else goes to the library path
+    x, w = torch.zeros(8, 3), torch.zeros(72, 3)
+    assert ops.small_linear_kind(3, 72, x, w) is None

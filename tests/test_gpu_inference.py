@@ -185,3 +185,19 @@ def test_denoise_cloud_graph_replay_equals_eager(cuda_device):
     out_e = inference.denoise_cloud(model, pts, 0.05, 0.05, 1024, batch_size=4, use_graph=False)
     assert torch.equal(out_g[2], out_e[2]) and bool((out_g[2] > 0).all())  # votes: every point covered
     torch.testing.assert_close(out_g[1], out_e[1], rtol=1e-5, atol=1e-6)
+
+
+def test_radius_lists_histogram_selection_equals_full_sort(cuda_device):
+    """Few results out of many candidates take the histogram-selection path of the radius kernel; asking for many results
+    takes the full sort — the first entries must be identical (same distance order, ties by index), in every storage tier."""
+    from deep3dpointclouddenoising_b200 import ops
+    pts = torch.from_numpy(_cloud(40000, 11)).to(cuda_device)
+    centres = pts[::97].contiguous()
+    full, cnt_full = ops.radius_patches(pts, centres, 0.12, 4096)              # n <= 4 * 4096: sorted as a whole
+    assert int(cnt_full.max()) > 600 and int(cnt_full.max()) <= 4096
+    for kw in (dict(smem_keys=12288), dict(smem_keys=4096), dict(overflow_stride=8192)):
+        few, cnt = ops.radius_patches(pts, centres, 0.12, 32, **kw)           # 32 of ~1000: selected, then sorted
+        assert torch.equal(cnt, cnt_full)
+        assert torch.equal(few, full[:, :32])
+    auto, cnt = ops.radius_neighbors(pts, centres, 0.12, 32)                   # tier chosen from a probe
+    assert torch.equal(auto, full[:, :32]) and torch.equal(cnt, cnt_full)
