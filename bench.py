@@ -758,6 +758,11 @@ def main():
                            "cuda_graph": graph is not None,
                            "pyramid": ("next batch's neighbourhood pyramid built during this batch's backward (one-step pipeline, "
                                        "one pyramid per step)") if (pipelined and graph is not None) else "built inside forward on a side stream",
+                           "pospool_backward": {"scatter": "tensor-core tiles, partial sums added with float atomics like the reference's backward",
+                                                "ordered": "tensor-core tiles + fixed-order second pass (no float atomics)",
+                                                False: "segmented reduction over the inverse map (no float atomics)"}.get(
+                               cfgmod.runtime.staged_tiles_backward, str(cfgmod.runtime.staged_tiles_backward))
+                           if args.operator == "pospool" else None,
                            "layout": "channel-last activations end to end" if cfgmod.runtime.channel_last else "channel-major",
                            "conv_math": "tf32" if torch.backends.cudnn.allow_tf32 else "fp32", "l2": "per-step working set (activations, "
                            "several GB) exceeds the 126 MB L2; 4 rotating input batches"},
