@@ -160,6 +160,7 @@ int d3d_linear_small_n(const float* x, const float* w, const float* bias, long l
   if (R == 0) return 0;
   const int blocks = (int)min((R + kSnRows - 1) / kSnRows, (long long)148 * 4);
   const size_t smem = ((size_t)kSnRows * (K + 1) + (size_t)N * K) * sizeof(float);
+  if (smem > 200 * 1024) return D3D_ERR_UNSUPPORTED;  // K beyond ~750: not a shape of this path
   cudaError_t e = cudaFuncSetAttribute(linear_small_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   linear_small_n_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(x, w, bias, R, K, N, y);

@@ -528,9 +528,9 @@ def small_linear_kind(K, N, *tensors):
     """'k' / 'n' when a (R, K) x (N, K)^T product has a tiny side the skinny kernels take (csrc/linear_small.cu), else None."""
     if not all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in tensors):
         return None
-    if K <= 4 and N % 4 == 0 and N <= 1024:
+    if K <= 4 and N % 4 == 0 and N <= 512:  # 512: the small-N kernel stages 64 rows of the wide side in shared memory
         return 'k'
-    if N <= 4 and K % 4 == 0 and K <= 1024:
+    if N <= 4 and K % 4 == 0 and K <= 512:
         return 'n'
     return None
 
