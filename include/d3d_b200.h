@@ -160,6 +160,9 @@ int d3d_pospool_tile_plan(const int* idx_by_support, const int* nvalid, const in
 int d3d_pospool_tiles_fwd(const float* feat_cl, const float* query_xyz, const float* support_xyz, const int* idx_by_support,
                           const int* nvalid, const int* query_mask, const int* query_order, const void* plan, int B, int M,
                           int N, int C, int nsample, float radius, int reduction, float* out_cl, void* stream);
+/* Diagnostics (tools/tile_phases.py): a device buffer of 8 x uint64 per CTA that the next tile-kernel launches fill with
+ * %globaltimer stamps of their phases; NULL switches it off (the default). */
+void d3d_pospool_tiles_debug_timing(void* buf);
 /* Backward pass in scatter form: the CTA owns the forward tile (128 queries), stages their gradient rows once, and
  * contracts A^T (the forward multiplicity matrix read through the MN-major descriptor) with them on the tensor cores,
  * 128 union rows per accumulator.  A feature-gradient row receives partial sums from every tile that gathered it:
