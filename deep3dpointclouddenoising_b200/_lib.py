@@ -39,6 +39,7 @@ SIGNATURES = {
     "d3d_pospool_tile_plan_bytes": (_sz, [_i, _i, _i, _i]),
     "d3d_pospool_tile_plan": (_i, [_vp] * 4 + [_i] * 4 + [_vp, _sz, _vp]),
     "d3d_pospool_tiles_fwd": (_i, [_vp] * 8 + [_i] * 5 + [_f, _i, _vp, _vp]),
+    "d3d_pospool_tiles_debug_timing": (None, [_vp]),
     "d3d_pospool_scatter_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "d3d_pospool_scatter_bwd": (_i, [_vp] * 8 + [_i] * 5 + [_f, _i, _vp, _vp, _sz, _vp]),
     "d3d_pseudogrid_fwd": (_i, [_vp] * 8 + [_i] * 6 + [_f, _i, _i, _vp, _vp]),
