@@ -727,19 +727,32 @@ pospool_fwd_pipelined_kernel(const TileArgs a) {
   D3D_STAMP(3);
 
   if (warp == 4) {
-    // ---- loader: one row per lane -------------------------------------------------------------------------------
+    // ---- loader: one row per lane.  The row numbers and coordinates of chunk j + 1 are fetched while chunk j is being
+    //      issued and its staging buffer waited for: the two dependent global loads (union entry -> coordinates) are the
+    //      longest latency of the loop and must not sit between two chunks
     const float* src_rows = a.src + (size_t)b * a.N * a.C + c0;
+    int nsrc = -1;
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    if (lane < U) {
+      nsrc = tile_union[lane];
+      nx = src_xyz[3 * (size_t)nsrc]; ny = src_xyz[3 * (size_t)nsrc + 1]; nz = src_xyz[3 * (size_t)nsrc + 2];
+    }
     for (int j = 0; j < n_chunks; ++j) {
       const int buf = j & 1;
+      const int src = nsrc;
+      const float sx = nx, sy = ny, sz = nz;
+      nsrc = -1;
+      const int rn = (j + 1) * kFC + lane;
+      if (rn < U) {  // next chunk's row: in flight during the wait below
+        nsrc = tile_union[rn];
+        nx = src_xyz[3 * (size_t)nsrc]; ny = src_xyz[3 * (size_t)nsrc + 1]; nz = src_xyz[3 * (size_t)nsrc + 2];
+      }
       if (j >= 2) mbar_wait(bar_stage_free(buf), (unsigned)(((j >> 1) - 1) & 1));
-      const int r = j * kFC + lane;
-      int src = -1;
-      if (r < U) {
-        src = tile_union[r];
+      if (src >= 0) {
         bulk_g2s(smem_u32(smem + L.stage + buf * L.stage_stride + (size_t)lane * L.row_bytes), src_rows + (size_t)src * a.C,
                  L.row_bytes, bar_stage_full(buf));
         float* w = sSrcW + (buf * kFC + lane) * 3;
-        w[0] = src_xyz[3 * (size_t)src] - ctr_x; w[1] = src_xyz[3 * (size_t)src + 1] - ctr_y; w[2] = src_xyz[3 * (size_t)src + 2] - ctr_z;
+        w[0] = sx - ctr_x; w[1] = sy - ctr_y; w[2] = sz - ctr_z;
       }
       sSrcId[buf * kFC + lane] = src;
       __syncwarp();
